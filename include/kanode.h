@@ -1,0 +1,188 @@
+/*
+ * kanode.h — C ABI of the B200-native KAN-ODE hot path (libkanode_b200.so).
+ *
+ * This is the drop-in boundary described in SURVEY.md §8(b).  The reference
+ * (maharshi-coding/KAN-ODEs) has no FFI: its "API" is three Julia call shapes.
+ * Each entry point below names the reference call site it replaces
+ * (LV/ = Lotka-Volterra/, PDE/ = "PDE examples/"):
+ *
+ *   kanode_create / kanode_set_params
+ *       <- KDense(I,O,G; normalizer, basis_func, use_base_act)   LV/src/kdense.jl:20-68
+ *          Lux.Chain(...), Lux.setup(rng, chain)                  LV/LV_driver_KANODE.jl:139-143
+ *          flat parameter vector p (ComponentArray data)          LV/LV_driver_KANODE.jl:173-175
+ *   kanode_rhs
+ *       <- (l::KDense)(x, p, st)                                  LV/src/kdense.jl:109-130
+ *          kan1(u, p, st) as ODE right-hand side                  LV/LV_driver_KANODE.jl:180
+ *          rc_kanode(u, p, t) (Laplacian + pointwise KAN)         PDE/Allen-Cahn_Source.jl:90-93
+ *   kanode_vjp
+ *       <- Zygote.pullback of the chain (rrule(_rbf))             LV/src/utils.jl:15-21
+ *   kanode_solve
+ *       <- NeuralODE(kan, tspan, Tsit5(); saveat)(u0, p, st)      LV/LV_driver_KANODE.jl:180-184
+ *          solve(ODEProblem(rc_kanode,u0,tspan,p;saveat),Tsit5()) PDE/Allen-Cahn_Source.jl:96-99
+ *   kanode_loss_grad
+ *       <- Zygote.gradient(loss, p)[1] with
+ *          loss(p) = mean(abs2, X .- predict(p))                  LV/LV_driver_KANODE.jl:197-203,284
+ *                                                                 PDE/Burgers_Surrogate.jl:105-107,191
+ *
+ * Conventions
+ *  - All functions return 0 on success, a negative kanode_status on failure;
+ *    kanode_last_error() gives the message.  No C++ exception crosses the ABI.
+ *  - Per-trajectory solver outcomes (MaxIters, DtLessThanMin, Unstable) are NOT
+ *    call failures: they are reported in kanode_stats.retcode.
+ *  - Host entry points take host pointers and copy in/out on the handle's
+ *    stream; *_dev entry points take device pointers (same layouts) and only
+ *    enqueue work — call kanode_sync() (or synchronise the stream) afterwards.
+ *  - There is NO CPU fallback: every compute entry point fails with
+ *    KANODE_ERR_NO_DEVICE if no sm_100-class CUDA device is usable.
+ *  - Layouts (column-major in Julia terms == "trajectory-major" here):
+ *      u0     [batch][n]            one trajectory's state is contiguous
+ *      out    [batch][nsave][n]     == Array(sol) (n x nsave) per trajectory
+ *      target [batch][nsave][n]
+ *      p      flat: per layer  C[O][G*I] column-major (column = i*G + g, i.e.
+ *             element (o,i,g) at  (i*G+g)*O + o ), then W[O][I] column-major
+ *             (element (o,i) at i*O + o)  — LV/src/kdense.jl:75,81 and
+ *             LV/Activation_getter.jl:9-10.
+ *  - Arithmetic type of the device path is fp32 for states/parameters and
+ *    fp64 for the time variable; the reference runs Float64.
+ */
+#ifndef KANODE_H_
+#define KANODE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KANODE_MAX_LAYERS 8
+
+typedef enum {
+    KANODE_OK = 0,
+    KANODE_ERR_INVALID = -1,      /* bad descriptor / argument                 */
+    KANODE_ERR_NO_DEVICE = -2,    /* no usable CUDA device (no CPU fallback)   */
+    KANODE_ERR_CUDA = -3,         /* CUDA runtime error, see kanode_last_error */
+    KANODE_ERR_NOMEM = -4,
+    KANODE_ERR_UNSUPPORTED = -5   /* valid request outside the built kernels   */
+} kanode_status;
+
+/* normalizer: LV/src/kdense.jl:25,41-47,57-61 (NNlib.fast_act maps tanh->tanh_fast) */
+typedef enum {
+    KANODE_NORM_TANH = 0,         /* tanh / tanh_fast  (LV_driver_KANODE.jl:131) */
+    KANODE_NORM_SOFTSIGN = 1,     /* softsign          (Burgers_Surrogate.jl:83) */
+    KANODE_NORM_SIGMOID = 2       /* sigmoid / sigmoid_fast                      */
+} kanode_normalizer;
+
+/* basis_func: LV/src/utils.jl:8-62 */
+typedef enum {
+    KANODE_BASIS_RBF = 0,         /* exp(-((x-z)/h)^2)   utils.jl:8-13  */
+    KANODE_BASIS_RSWAF = 1,       /* 1 - tanh(((x-z)/h))^2  utils.jl:27-34 */
+    KANODE_BASIS_IQF = 2          /* 1/(1+((x-z)/h)^2)   utils.jl:49-54 */
+} kanode_basis;
+
+/* rhs_kind */
+typedef enum {
+    KANODE_RHS_CHAIN = 0,         /* du = chain(u)                NeuralODE dudt       */
+    KANODE_RHS_SOURCE_LAPLACIAN = 1 /* du = lap_coef*lap(u) + chain_1to1.(u)  AC_Source:90-93 */
+} kanode_rhs_kind;
+
+typedef struct {
+    int32_t in_dims;              /* I */
+    int32_t out_dims;             /* O */
+    int32_t grid_len;             /* G */
+    int32_t normalizer;           /* kanode_normalizer */
+    int32_t basis;                /* kanode_basis      */
+    int32_t use_base_act;         /* 1: y += W*swish(x)  (kdense.jl:122-127) */
+    float   grid_lo;              /* grid_lims[1], default -1f0 (kdense.jl:26) */
+    float   grid_hi;              /* grid_lims[2], default  1f0               */
+    float   denominator;          /* h, default Float32(2/(G-1)) (kdense.jl:27) */
+} kanode_layer_desc;
+
+typedef struct {
+    int32_t n_layers;
+    kanode_layer_desc layers[KANODE_MAX_LAYERS];
+    int32_t rhs_kind;             /* kanode_rhs_kind */
+    int32_t n_state;              /* n: state length of one trajectory */
+    double  lap_coef;             /* s*D: AC_Source -1e-4, Fisher-KPP +0.01 (rhs_kind 1) */
+    double  dx;                   /* grid spacing of the periodic 3-point Laplacian      */
+} kanode_desc;
+
+/* retcode mirrors SciML ReturnCode names */
+typedef enum {
+    KANODE_RET_SUCCESS = 0,
+    KANODE_RET_MAXITERS = 1,
+    KANODE_RET_DT_LESS_THAN_MIN = 2,
+    KANODE_RET_UNSTABLE = 3,
+    KANODE_RET_RECORD_OVERFLOW = 4 /* internal: dense-record capacity hit; host retries larger */
+} kanode_retcode;
+
+typedef struct {
+    int32_t naccept;
+    int32_t nreject;
+    int32_t nf;                   /* RHS evaluations (backward: fused forward+VJP evals) */
+    int32_t retcode;              /* kanode_retcode */
+} kanode_stats;
+
+typedef struct kanode_handle kanode_handle;
+
+const char* kanode_version(void);
+/* message of the last failure on this handle (or of the last failed create if h==NULL) */
+const char* kanode_last_error(const kanode_handle* h);
+
+/* number of parameters implied by a descriptor (LuxCore.parameterlength, kdense.jl:98-107);
+ * returns 0 for an invalid descriptor. */
+size_t kanode_param_count(const kanode_desc* desc);
+
+/* device: CUDA device ordinal; stream: a cudaStream_t cast to void* (NULL = library-owned stream). */
+int kanode_create(const kanode_desc* desc, int device, void* stream, kanode_handle** out);
+int kanode_destroy(kanode_handle* h);
+int kanode_sync(kanode_handle* h);
+
+/* copy the flat parameter vector (np floats) to the device */
+int kanode_set_params(kanode_handle* h, const float* p, size_t np);
+int kanode_set_params_dev(kanode_handle* h, const float* d_p, size_t np);
+
+/* du[b] = f(u[b]) for b < batch */
+int kanode_rhs(kanode_handle* h, const float* u, float* du, int64_t batch);
+int kanode_rhs_dev(kanode_handle* h, const float* d_u, float* d_du, int64_t batch);
+
+/* ubar[b] = (df/du)^T lam[b];  pbar = sum_b (df/dp)^T lam[b]   (pbar has np floats) */
+int kanode_vjp(kanode_handle* h, const float* u, const float* lam,
+               float* ubar, float* pbar, int64_t batch);
+
+/* adaptive Tsit5, defaults of the reference are abstol=1e-6, reltol=1e-3 */
+int kanode_solve(kanode_handle* h, const float* u0, int64_t batch,
+                 double t0, double t1, const double* saveat, int32_t nsave,
+                 float abstol, float reltol,
+                 float* out, kanode_stats* stats /* [batch] or NULL */);
+int kanode_solve_dev(kanode_handle* h, const float* d_u0, int64_t batch,
+                     double t0, double t1, const double* saveat /* host */, int32_t nsave,
+                     float abstol, float reltol,
+                     float* d_out, kanode_stats* d_stats /* device, [batch] or NULL */);
+
+/* loss = mean over (batch, nsave, n) of (out - target)^2;  grad = dloss/dp (np floats).
+ * Each trajectory runs the reference's interpolating-adjoint backward solve on
+ * z=[lambda; g] with its own step control; grad = (1/batch) * sum_b g_b(t0).
+ * du0 (optional, [batch][n]) receives dloss_b/du0_b (lambda_b(t0), unscaled by 1/batch). */
+int kanode_loss_grad(kanode_handle* h, const float* u0, int64_t batch,
+                     double t0, double t1, const double* saveat, int32_t nsave,
+                     const float* target, float abstol, float reltol,
+                     float* loss, float* grad, float* du0 /* or NULL */,
+                     kanode_stats* fwd_stats /* [batch] or NULL */,
+                     kanode_stats* bwd_stats /* [batch] or NULL */);
+/* device-pointer variant.  d_loss_sum receives sum_b sum_{i,j}(out-target)^2 (a double, NOT yet
+ * divided) and d_grad_sum receives sum_b g_b(t0) (np floats, NOT yet divided by batch), so a
+ * data-parallel caller can all-reduce both and divide by the global counts. */
+int kanode_loss_grad_dev(kanode_handle* h, const float* d_u0, int64_t batch,
+                         double t0, double t1, const double* saveat /* host */, int32_t nsave,
+                         const float* d_target, float abstol, float reltol,
+                         double* d_loss_sum, float* d_grad_sum, float* d_du0 /* or NULL */,
+                         kanode_stats* d_fwd_stats, kanode_stats* d_bwd_stats);
+
+/* number of kernel launches issued by this handle since creation (for bench accounting) */
+int64_t kanode_launch_count(const kanode_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KANODE_H_ */

@@ -1,0 +1,119 @@
+"""ctypes wrapper of oracle/libkanode_oracle.so (TEST INFRASTRUCTURE ONLY).
+
+Follows oracle/kanode_oracle.cpp, which restates LV/src/kdense.jl:109-130, LV/src/utils.jl:8-21 and the
+un-vendored SciML solver/adjoint algorithms.  The descriptor structs are the public ones of include/kanode.h
+(kan_odes_b200.abi) — types only; nothing of the product's compute path is used here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from kan_odes_b200 import abi
+
+ORACLE_DIR = Path(__file__).resolve().parent
+ORACLE_LIB = ORACLE_DIR / "libkanode_oracle.so"
+
+
+def build_oracle(force: bool = False) -> Path:
+    src = ORACLE_DIR / "kanode_oracle.cpp"
+    if force or not ORACLE_LIB.exists() or ORACLE_LIB.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(ORACLE_DIR), "-B"], check=True, capture_output=True)
+    return ORACLE_LIB
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """dtype=np.float64 restates what the reference drivers run; np.float32 mirrors device arithmetic."""
+
+    def __init__(self, desc: abi.Desc, dtype=np.float64):
+        build_oracle()
+        self.lib = C.CDLL(str(ORACLE_LIB))
+        self.desc = desc
+        self.dtype = np.dtype(dtype)
+        self.suf = "f64" if self.dtype == np.float64 else "f32"
+        self.lib.kanode_oracle_param_count.restype = C.c_size_t
+        self.np_ = int(self.lib.kanode_oracle_param_count(C.byref(desc)))
+        if self.np_ == 0:
+            raise ValueError("invalid descriptor")
+        self.n = int(desc.n_state)
+
+    def _fn(self, name):
+        f = getattr(self.lib, f"kanode_oracle_{name}_{self.suf}")
+        f.restype = C.c_int
+        return f
+
+    def _a(self, x, shape=None):
+        a = np.ascontiguousarray(x, dtype=self.dtype)
+        return a if shape is None else a.reshape(shape)
+
+    def rhs(self, p, u):
+        u = self._a(u).reshape(-1, self.n); p = self._a(p)
+        du = np.empty_like(u)
+        rc = self._fn("rhs")(C.byref(self.desc), _ptr(p), _ptr(u), _ptr(du), C.c_int64(u.shape[0]))
+        assert rc == 0, rc
+        return du
+
+    def vjp(self, p, u, lam):
+        u = self._a(u).reshape(-1, self.n); lam = self._a(lam).reshape(-1, self.n); p = self._a(p)
+        ubar = np.empty_like(u); pbar = np.empty(self.np_, self.dtype)
+        rc = self._fn("vjp")(C.byref(self.desc), _ptr(p), _ptr(u), _ptr(lam), _ptr(ubar), _ptr(pbar),
+                             C.c_int64(u.shape[0]))
+        assert rc == 0, rc
+        return ubar, pbar
+
+    def solve(self, p, u0, tspan, saveat, abstol=1e-6, reltol=1e-3, step_cap=0):
+        u0 = self._a(u0).reshape(-1, self.n); p = self._a(p)
+        B = u0.shape[0]
+        sa = np.ascontiguousarray(saveat, dtype=np.float64)
+        out = np.empty((B, sa.size, self.n), self.dtype)
+        stats = (abi.Stats * B)()
+        step_t = np.full((B, step_cap), np.nan) if step_cap else None
+        rc = self._fn("solve")(C.byref(self.desc), _ptr(p), _ptr(u0), C.c_int64(B), C.c_double(tspan[0]),
+                               C.c_double(tspan[1]), _ptr(sa), C.c_int(sa.size), C.c_double(abstol),
+                               C.c_double(reltol), _ptr(out), stats, _ptr(step_t), C.c_int(step_cap))
+        assert rc == 0, rc
+        st = np.frombuffer(stats, dtype=np.int32).reshape(B, 4).copy()
+        return (out, st, step_t) if step_cap else (out, st)
+
+    def loss_grad(self, p, u0, tspan, saveat, target, abstol=1e-6, reltol=1e-3, want_out=False):
+        u0 = self._a(u0).reshape(-1, self.n); p = self._a(p)
+        B = u0.shape[0]
+        sa = np.ascontiguousarray(saveat, dtype=np.float64)
+        target = self._a(target).reshape(B, sa.size, self.n)
+        loss = C.c_double(0.0)
+        grad = np.empty(self.np_, self.dtype); du0 = np.empty_like(u0)
+        fst = (abi.Stats * B)(); bst = (abi.Stats * B)()
+        out = np.empty((B, sa.size, self.n), self.dtype) if want_out else None
+        rc = self._fn("loss_grad")(C.byref(self.desc), _ptr(p), _ptr(u0), C.c_int64(B), C.c_double(tspan[0]),
+                                   C.c_double(tspan[1]), _ptr(sa), C.c_int(sa.size), _ptr(target),
+                                   C.c_double(abstol), C.c_double(reltol), C.byref(loss), _ptr(grad), _ptr(du0),
+                                   fst, bst, _ptr(out))
+        assert rc == 0, rc
+        f = np.frombuffer(fst, dtype=np.int32).reshape(B, 4).copy()
+        b = np.frombuffer(bst, dtype=np.int32).reshape(B, 4).copy()
+        res = dict(loss=loss.value, grad=grad, du0=du0, fwd_stats=f, bwd_stats=b)
+        if want_out:
+            res["out"] = out
+        return res
+
+    # small helpers for the unit tests
+    def fastpower(self, x, y):
+        self.lib.kanode_oracle_fastpower.restype = C.c_float
+        return float(self.lib.kanode_oracle_fastpower(C.c_double(x), C.c_double(y)))
+
+    def interp_weights(self, th):
+        b = np.empty(7)
+        self.lib.kanode_oracle_interp_weights(C.c_double(th), _ptr(b))
+        return b
+
+    def tableau(self):
+        c = np.empty(6); a = np.empty((7, 7)); bt = np.empty(7)
+        self.lib.kanode_oracle_tableau(_ptr(c), _ptr(a), _ptr(bt))
+        return c, a, bt
