@@ -179,6 +179,33 @@ int kanode_loss_grad_dev(kanode_handle* h, const float* d_u0, int64_t batch,
                          double* d_loss_sum, float* d_grad_sum, float* d_du0 /* or NULL */,
                          kanode_stats* d_fwd_stats, kanode_stats* d_bwd_stats);
 
+/* ---- Float64 entry points ------------------------------------------------------------------------
+ * The reference drivers effectively run in Float64 (LV_driver_KANODE.jl:117,175 promote u0 and p), so a
+ * Julia binding passes Vector{Float64}.  These run the same kernels instantiated for double: they reproduce
+ * the reference's step sequence (same accepted-step count) where fp32 state arithmetic cannot (DESIGN.md,
+ * "precision").  Same layouts and semantics as the float versions above. */
+int kanode_set_params_f64(kanode_handle* h, const double* p, size_t np);
+int kanode_rhs_f64(kanode_handle* h, const double* u, double* du, int64_t batch);
+int kanode_vjp_f64(kanode_handle* h, const double* u, const double* lam,
+                   double* ubar, double* pbar, int64_t batch);
+int kanode_solve_f64(kanode_handle* h, const double* u0, int64_t batch,
+                     double t0, double t1, const double* saveat, int32_t nsave,
+                     double abstol, double reltol, double* out, kanode_stats* stats);
+int kanode_loss_grad_f64(kanode_handle* h, const double* u0, int64_t batch,
+                         double t0, double t1, const double* saveat, int32_t nsave,
+                         const double* target, double abstol, double reltol,
+                         double* loss, double* grad, double* du0,
+                         kanode_stats* fwd_stats, kanode_stats* bwd_stats);
+int kanode_loss_grad_dev_f64(kanode_handle* h, const double* d_u0, int64_t batch,
+                             double t0, double t1, const double* saveat /* host */, int32_t nsave,
+                             const double* d_target, double abstol, double reltol,
+                             double* d_loss_sum, double* d_grad_sum, double* d_du0,
+                             kanode_stats* d_fwd_stats, kanode_stats* d_bwd_stats);
+
+/* dense-record capacity (accepted forward steps kept per trajectory for the adjoint).  Host entry points grow
+ * it automatically on overflow; *_dev entry points report KANODE_RET_RECORD_OVERFLOW in the stats instead. */
+int kanode_set_record_capacity(kanode_handle* h, int32_t max_steps);
+
 /* number of kernel launches issued by this handle since creation (for bench accounting) */
 int64_t kanode_launch_count(const kanode_handle* h);
 

@@ -1,0 +1,11 @@
+"""kan_odes_b200 — B200-native (sm_100a) KAN-ODE hot path: KDense RHS + Tsit5 + interpolating adjoint.
+
+Host-side mirror of the reference's driver surface over the C ABI in include/kanode.h.  (The directory is named
+with an underscore so that it is importable; the project name is kan-odes_b200.)
+"""
+from .abi import KanodeError, load_library  # noqa: F401
+from .layers import (Chain, KDense, flatten_params, glorot_uniform, iqf, rbf, rswaf, setup, sigmoid,  # noqa: F401
+                     sigmoid_fast, softsign, swish, tanh, tanh_fast, unflatten_params)
+from .node import KanOde, NeuralODE, ODESolution, SourceODE, Stats, Tsit5  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,428 @@
+// kanode_api.cu — C ABI (include/kanode.h) over the sm_100a kernels.  Plain pointers and sizes only; no torch,
+// no C++ exceptions across the boundary, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kanode_host.h"
+#include "kanode_small.cuh"
+#include "kanode_generic.cuh"
+
+using namespace kanode;
+
+namespace {
+
+int enter(kanode_handle* h) {
+    if (!h) return fail(nullptr, KANODE_ERR_INVALID, "null handle");
+    CK(h, cudaSetDevice(h->device));
+    return 0;
+}
+
+int check_saveat(kanode_handle* h, double t0, double t1, const double* saveat, int nsave) {
+    if (!(t1 >= t0)) return fail(h, KANODE_ERR_INVALID, "tspan must be increasing");
+    if (nsave < 0 || (nsave > 0 && !saveat)) return fail(h, KANODE_ERR_INVALID, "bad saveat");
+    for (int s = 0; s < nsave; ++s) {
+        if (!(saveat[s] >= t0 && saveat[s] <= t1)) return fail(h, KANODE_ERR_INVALID, "saveat[%d] outside tspan", s);
+        if (s > 0 && saveat[s] < saveat[s - 1]) return fail(h, KANODE_ERR_INVALID, "saveat must be ascending");
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small-model registry: [I,H,I] chains with compile-time shapes (thread-per-trajectory kernels)
+// ---------------------------------------------------------------------------------------------------------
+struct SmallKey { int I, H, G, norm; };
+bool small_match(const kanode_desc& d, SmallKey& k) {
+    if (d.rhs_kind != KANODE_RHS_CHAIN || d.n_layers != 2) return false;
+    const kanode_layer_desc &a = d.layers[0], &b = d.layers[1];
+    if (a.basis != KANODE_BASIS_RBF || b.basis != KANODE_BASIS_RBF || !a.use_base_act || !b.use_base_act) return false;
+    if (a.grid_len != b.grid_len || a.normalizer != b.normalizer || a.grid_lo != b.grid_lo || a.grid_hi != b.grid_hi ||
+        a.denominator != b.denominator) return false;
+    k = SmallKey{a.in_dims, a.out_dims, a.grid_len, a.normalizer};
+    return true;
+}
+
+template <class T, class P> void fill_small(const kanode_handle* h, P& p) {
+    for (int i = 0; i < P::NP; ++i) p.w[i] = (T)h->params[i];
+    const kanode_layer_desc& s = h->desc.layers[0];
+    for (int g = 0; g < P::G; ++g) p.grid[g] = (T)grid_point(s, g);
+    p.inv_h = (T)(1.0f / s.denominator);                               // Float32 1/h (utils.jl:9)
+}
+
+// Visitor: calls fn.template operator()<P, NORM>() for the instantiation matching the descriptor.
+#define KANODE_SMALL_CASES(X) X(2, 10, 5, NORM_TANH)
+
+template <class T, class Fn> bool small_dispatch(const kanode_handle* h, Fn&& fn, int& rc) {
+    SmallKey k;
+    if (!small_match(h->desc, k)) return false;
+#define X(I_, H_, G_, N_)                                                         \
+    if (k.I == I_ && k.H == H_ && k.G == G_ && k.norm == N_) {                     \
+        rc = fn.template operator()<SmallParams<T, I_, H_, G_>, N_>();             \
+        return true;                                                               \
+    }
+    KANODE_SMALL_CASES(X)
+#undef X
+    return false;
+}
+
+inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+// ---------------------------------------------------------------------------------------------------------
+// templated implementations (T = float | double); all pointers are DEVICE pointers here
+// ---------------------------------------------------------------------------------------------------------
+template <class T> int put_saveat(kanode_handle* h, const double* saveat, int nsave, const double** d_saveat) {
+    double* d = nullptr;
+    ENSURE(h, W_SAVEAT, sizeof(double) * (size_t)(nsave > 0 ? nsave : 1), d);
+    if (nsave > 0) CK(h, cudaMemcpyAsync(d, saveat, sizeof(double) * nsave, cudaMemcpyHostToDevice, h->stream));
+    *d_saveat = d;
+    return 0;
+}
+
+template <class T> int rhs_dev(kanode_handle* h, const T* d_u, T* d_du, int64_t B) {
+    if (!h->have_params) return fail(h, KANODE_ERR_INVALID, "parameters not set");
+    if (B <= 0) return 0;
+    int rc = 0;
+    auto run = [&]<class P, int NORM>() -> int {
+        P prm; fill_small<T>(h, prm);
+        small_rhs_kernel<T, P, NORM><<<blocks_for(B, 128), 128, 0, h->stream>>>(prm, d_u, d_du, B);
+        ++h->launches;
+        CK(h, cudaGetLastError());
+        return 0;
+    };
+    if (small_dispatch<T>(h, run, rc)) return rc;
+    return generic_rhs<T>(h, d_u, d_du, B);
+}
+
+template <class T> int vjp_dev(kanode_handle* h, const T* d_u, const T* d_lam, T* d_ubar, T* d_pbar, int64_t B) {
+    if (!h->have_params) return fail(h, KANODE_ERR_INVALID, "parameters not set");
+    if (B <= 0) { CK(h, cudaMemsetAsync(d_pbar, 0, sizeof(T) * h->np, h->stream)); return 0; }
+    int rc = 0;
+    auto run = [&]<class P, int NORM>() -> int {
+        P prm; fill_small<T>(h, prm);
+        T *fac = nullptr, *rows = nullptr;
+        ENSURE(h, W_FAC, sizeof(T) * (size_t)P::NF * B, fac);
+        ENSURE(h, W_G, sizeof(T) * (size_t)P::NP * B, rows);
+        small_vjp_kernel<T, P, NORM><<<blocks_for(B, 64), 64, 0, h->stream>>>(prm, d_u, d_lam, d_ubar, fac, rows, B);
+        reduce_rows_kernel<T, T><<<P::NP, 256, 0, h->stream>>>(rows, B, d_pbar, 1.0);
+        h->launches += 2;
+        CK(h, cudaGetLastError());
+        return 0;
+    };
+    if (small_dispatch<T>(h, run, rc)) return rc;
+    return generic_vjp<T>(h, d_u, d_lam, d_ubar, d_pbar, B);
+}
+
+template <class T>
+int solve_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double t1, const double* saveat, int nsave,
+              double abstol, double reltol, T* d_out, kanode_stats* d_stats) {
+    if (!h->have_params) return fail(h, KANODE_ERR_INVALID, "parameters not set");
+    if (int rc = check_saveat(h, t0, t1, saveat, nsave)) return rc;
+    if (B <= 0) return 0;
+    const double* d_saveat = nullptr;
+    if (int rc = put_saveat<T>(h, saveat, nsave, &d_saveat)) return rc;
+    int rc = 0;
+    auto run = [&]<class P, int NORM>() -> int {
+        P prm; fill_small<T>(h, prm);
+        SmallFwdArgs<T> a{};
+        a.u0 = d_u0; a.B = B; a.t0 = t0; a.t1 = t1; a.saveat = d_saveat; a.nsave = nsave;
+        a.abstol = (T)abstol; a.reltol = (T)reltol; a.maxiters = 100000; a.out = d_out; a.stats = d_stats;
+        small_forward_kernel<T, P, NORM, false><<<blocks_for(B, 64), 64, 0, h->stream>>>(prm, a);
+        ++h->launches;
+        CK(h, cudaGetLastError());
+        return 0;
+    };
+    if (small_dispatch<T>(h, run, rc)) return rc;
+    return generic_solve<T>(h, d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);
+}
+
+template <class T>
+int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double t1, const double* saveat, int nsave,
+                  const T* d_target, double abstol, double reltol, double* d_loss_sum, T* d_grad_sum, T* d_du0,
+                  kanode_stats* d_fst, kanode_stats* d_bst, T* d_out_opt) {
+    if (!h->have_params) return fail(h, KANODE_ERR_INVALID, "parameters not set");
+    if (int rc = check_saveat(h, t0, t1, saveat, nsave)) return rc;
+    if (nsave < 1) return fail(h, KANODE_ERR_INVALID, "loss needs at least one save time");
+    CK(h, cudaMemsetAsync(d_loss_sum, 0, sizeof(double), h->stream));
+    if (B <= 0) { CK(h, cudaMemsetAsync(d_grad_sum, 0, sizeof(T) * h->np, h->stream)); return 0; }
+    const double* d_saveat = nullptr;
+    if (int rc = put_saveat<T>(h, saveat, nsave, &d_saveat)) return rc;
+    int rc = 0;
+    auto run = [&]<class P, int NORM>() -> int {
+        constexpr int I = P::I;
+        P prm; fill_small<T>(h, prm);
+        const int cap = h->rec_cap;
+        double* rec_t = nullptr; T *rec = nullptr, *dg = nullptr, *fac = nullptr, *g = nullptr;
+        int *nsteps = nullptr, *retc = nullptr;
+        ENSURE(h, W_REC_T, sizeof(double) * (size_t)cap * B, rec_t);
+        ENSURE(h, W_REC, sizeof(T) * (size_t)cap * (1 + 8 * I) * B, rec);
+        ENSURE(h, W_NSTEPS, sizeof(int) * (size_t)B, nsteps);
+        ENSURE(h, W_RET, sizeof(int) * (size_t)B, retc);
+        ENSURE(h, W_DG, sizeof(T) * (size_t)nsave * I * B, dg);
+        ENSURE(h, W_FAC, sizeof(T) * (size_t)7 * P::NF * B, fac);
+        ENSURE(h, W_G, sizeof(T) * (size_t)2 * P::NP * B, g);
+        SmallFwdArgs<T> a{};
+        a.u0 = d_u0; a.B = B; a.t0 = t0; a.t1 = t1; a.saveat = d_saveat; a.nsave = nsave;
+        a.abstol = (T)abstol; a.reltol = (T)reltol; a.maxiters = 100000; a.out = d_out_opt; a.stats = d_fst;
+        a.rec_t = rec_t; a.rec = rec; a.cap = cap; a.nsteps = nsteps; a.retcode = retc;
+        a.target = d_target; a.dg = dg; a.loss_sum = d_loss_sum;
+        small_forward_kernel<T, P, NORM, true><<<blocks_for(B, 64), 64, 0, h->stream>>>(prm, a);
+        SmallBwdArgs<T> bw{};
+        bw.B = B; bw.t0 = t0; bw.t1 = t1; bw.saveat = d_saveat; bw.nsave = nsave;
+        bw.abstol = (T)abstol; bw.reltol = (T)reltol; bw.maxiters = 100000;
+        bw.rec_t = rec_t; bw.rec = rec; bw.cap = cap; bw.nsteps = nsteps; bw.retcode = retc; bw.dg = dg;
+        bw.fac = fac; bw.g = g; bw.du0 = d_du0; bw.stats = d_bst;
+        small_backward_kernel<T, P, NORM><<<blocks_for(B, 64), 64, 0, h->stream>>>(prm, bw);
+        reduce_rows_kernel<T, T><<<P::NP, 256, 0, h->stream>>>(g, B, d_grad_sum, 1.0);
+        h->launches += 3;
+        CK(h, cudaGetLastError());
+        return 0;
+    };
+    if (small_dispatch<T>(h, run, rc)) return rc;
+    return generic_loss_grad<T>(h, d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum, d_grad_sum,
+                                d_du0, d_fst, d_bst, d_out_opt);
+}
+
+// ---- host-pointer wrappers -----------------------------------------------------------------------------------
+template <class T> int set_params_host(kanode_handle* h, const T* p, size_t np) {
+    if (int rc = enter(h)) return rc;
+    if (!p || np != h->np) return fail(h, KANODE_ERR_INVALID, "expected %zu parameters, got %zu", h->np, np);
+    for (size_t i = 0; i < np; ++i) h->params[i] = (double)p[i];
+    h->have_params = true;
+    return generic_upload_params(h);
+}
+
+template <class T> int rhs_host(kanode_handle* h, const T* u, T* du, int64_t B) {
+    if (int rc = enter(h)) return rc;
+    if (B < 0 || (B > 0 && (!u || !du))) return fail(h, KANODE_ERR_INVALID, "bad arguments");
+    if (B == 0) return 0;
+    const size_t bytes = sizeof(T) * (size_t)B * h->n;
+    T *d_u = nullptr, *d_du = nullptr;
+    ENSURE(h, W_U0, bytes, d_u); ENSURE(h, W_OUT, bytes, d_du);
+    CK(h, cudaMemcpyAsync(d_u, u, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (int rc = rhs_dev<T>(h, d_u, d_du, B)) return rc;
+    CK(h, cudaMemcpyAsync(du, d_du, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+template <class T> int vjp_host(kanode_handle* h, const T* u, const T* lam, T* ubar, T* pbar, int64_t B) {
+    if (int rc = enter(h)) return rc;
+    if (B < 0 || !pbar || (B > 0 && (!u || !lam || !ubar))) return fail(h, KANODE_ERR_INVALID, "bad arguments");
+    const size_t bytes = sizeof(T) * (size_t)(B > 0 ? B : 1) * h->n;
+    T *d_u = nullptr, *d_lam = nullptr, *d_ub = nullptr, *d_pb = nullptr;
+    ENSURE(h, W_U0, bytes, d_u); ENSURE(h, W_LAM, bytes, d_lam); ENSURE(h, W_OUT, bytes, d_ub);
+    ENSURE(h, W_GRAD, sizeof(T) * h->np, d_pb);
+    if (B > 0) {
+        CK(h, cudaMemcpyAsync(d_u, u, sizeof(T) * (size_t)B * h->n, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaMemcpyAsync(d_lam, lam, sizeof(T) * (size_t)B * h->n, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (int rc = vjp_dev<T>(h, d_u, d_lam, d_ub, d_pb, B)) return rc;
+    if (B > 0) CK(h, cudaMemcpyAsync(ubar, d_ub, sizeof(T) * (size_t)B * h->n, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(pbar, d_pb, sizeof(T) * h->np, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+template <class T>
+int solve_host(kanode_handle* h, const T* u0, int64_t B, double t0, double t1, const double* saveat, int nsave,
+               double abstol, double reltol, T* out, kanode_stats* stats) {
+    if (int rc = enter(h)) return rc;
+    if (B < 0 || (B > 0 && (!u0 || (nsave > 0 && !out)))) return fail(h, KANODE_ERR_INVALID, "bad arguments");
+    if (B == 0) return 0;
+    T *d_u0 = nullptr, *d_out = nullptr; kanode_stats* d_st = nullptr;
+    ENSURE(h, W_U0, sizeof(T) * (size_t)B * h->n, d_u0);
+    ENSURE(h, W_OUT, sizeof(T) * (size_t)B * (nsave > 0 ? nsave : 1) * h->n, d_out);
+    ENSURE(h, W_STATS_F, sizeof(kanode_stats) * (size_t)B, d_st);
+    CK(h, cudaMemcpyAsync(d_u0, u0, sizeof(T) * (size_t)B * h->n, cudaMemcpyHostToDevice, h->stream));
+    if (int rc = solve_dev<T>(h, d_u0, B, t0, t1, saveat, nsave, abstol, reltol, d_out, d_st)) return rc;
+    if (nsave > 0) CK(h, cudaMemcpyAsync(out, d_out, sizeof(T) * (size_t)B * nsave * h->n, cudaMemcpyDeviceToHost, h->stream));
+    if (stats) CK(h, cudaMemcpyAsync(stats, d_st, sizeof(kanode_stats) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+template <class T>
+int loss_grad_host(kanode_handle* h, const T* u0, int64_t B, double t0, double t1, const double* saveat, int nsave,
+                   const T* target, double abstol, double reltol, T* loss, T* grad, T* du0, kanode_stats* fst,
+                   kanode_stats* bst) {
+    if (int rc = enter(h)) return rc;
+    if (B <= 0 || !u0 || !target || !loss || !grad) return fail(h, KANODE_ERR_INVALID, "bad arguments");
+    const size_t nout = (size_t)B * nsave * h->n;
+    for (int attempt = 0;; ++attempt) {
+        T *d_u0 = nullptr, *d_tg = nullptr, *d_grad = nullptr, *d_du0 = nullptr; double* d_loss = nullptr;
+        kanode_stats *d_f = nullptr, *d_b = nullptr;
+        ENSURE(h, W_U0, sizeof(T) * (size_t)B * h->n, d_u0);
+        ENSURE(h, W_TARGET, sizeof(T) * (nout ? nout : 1), d_tg);
+        ENSURE(h, W_GRAD, sizeof(T) * h->np, d_grad);
+        ENSURE(h, W_DU0, sizeof(T) * (size_t)B * h->n, d_du0);
+        ENSURE(h, W_LOSS, sizeof(double), d_loss);
+        ENSURE(h, W_STATS_F, sizeof(kanode_stats) * (size_t)B, d_f);
+        ENSURE(h, W_STATS_B, sizeof(kanode_stats) * (size_t)B, d_b);
+        CK(h, cudaMemcpyAsync(d_u0, u0, sizeof(T) * (size_t)B * h->n, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaMemcpyAsync(d_tg, target, sizeof(T) * nout, cudaMemcpyHostToDevice, h->stream));
+        if (int rc = loss_grad_dev<T>(h, d_u0, B, t0, t1, saveat, nsave, d_tg, abstol, reltol, d_loss, d_grad, d_du0,
+                                      d_f, d_b, (T*)nullptr)) return rc;
+        std::vector<kanode_stats> f((size_t)B);
+        CK(h, cudaMemcpyAsync(f.data(), d_f, sizeof(kanode_stats) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        bool overflow = false;
+        for (int64_t b = 0; b < B; ++b) overflow |= (f[b].retcode == KANODE_RET_RECORD_OVERFLOW);
+        if (overflow && attempt < 6) { h->rec_cap *= 4; continue; }   // grow the dense record and redo the step
+        double lsum = 0;
+        std::vector<T> gs(h->np);
+        CK(h, cudaMemcpyAsync(&lsum, d_loss, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(gs.data(), d_grad, sizeof(T) * h->np, cudaMemcpyDeviceToHost, h->stream));
+        if (du0) CK(h, cudaMemcpyAsync(du0, d_du0, sizeof(T) * (size_t)B * h->n, cudaMemcpyDeviceToHost, h->stream));
+        if (bst) CK(h, cudaMemcpyAsync(bst, d_b, sizeof(kanode_stats) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        if (fst) std::memcpy(fst, f.data(), sizeof(kanode_stats) * (size_t)B);
+        *loss = (T)(lsum / ((double)B * nsave * h->n));
+        for (size_t i = 0; i < h->np; ++i) grad[i] = (T)((double)gs[i] / (double)B);
+        return 0;
+    }
+}
+
+}  // namespace
+
+// =============================================================================================================
+// C ABI
+// =============================================================================================================
+extern "C" {
+
+const char* kanode_version(void) { return "kanode-b200 0.1.0 (sm_100a)"; }
+
+const char* kanode_last_error(const kanode_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+size_t kanode_param_count(const kanode_desc* desc) { return count_params(desc); }
+
+int kanode_create(const kanode_desc* desc, int device, void* stream, kanode_handle** out) {
+    if (!out) return fail(nullptr, KANODE_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    const size_t np = count_params(desc);
+    if (np == 0) return fail(nullptr, KANODE_ERR_INVALID, "invalid descriptor");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        (void)cudaGetLastError();
+        return fail(nullptr, KANODE_ERR_NO_DEVICE, "no CUDA device visible; the KAN-ODE hot path has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, KANODE_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, KANODE_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, KANODE_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    kanode_handle* h = new (std::nothrow) kanode_handle();
+    if (!h) return fail(nullptr, KANODE_ERR_NOMEM, "out of host memory");
+    h->desc = *desc; h->device = device; h->np = np; h->n = desc->n_state;
+    h->params.assign(np, 0.0);
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, KANODE_ERR_CUDA, "cudaSetDevice failed"); }
+    if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, KANODE_ERR_CUDA, "cudaStreamCreate failed"); }
+        h->own_stream = true;
+    }
+    if (int rc = generic_init(h)) { g_create_error = h->err; kanode_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int kanode_destroy(kanode_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto& b : h->ws) if (b.p) cudaFree(b.p);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int kanode_sync(kanode_handle* h) {
+    if (int rc = enter(h)) return rc;
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int kanode_set_record_capacity(kanode_handle* h, int32_t max_steps) {
+    if (!h || max_steps < 1) return fail(h, KANODE_ERR_INVALID, "bad capacity");
+    h->rec_cap = max_steps;
+    return 0;
+}
+
+int64_t kanode_launch_count(const kanode_handle* h) { return h ? h->launches : 0; }
+
+int kanode_set_params(kanode_handle* h, const float* p, size_t np) { return set_params_host<float>(h, p, np); }
+int kanode_set_params_f64(kanode_handle* h, const double* p, size_t np) { return set_params_host<double>(h, p, np); }
+int kanode_set_params_dev(kanode_handle* h, const float* d_p, size_t np) {
+    if (int rc = enter(h)) return rc;
+    if (!d_p || np != h->np) return fail(h, KANODE_ERR_INVALID, "expected %zu parameters, got %zu", h->np, np);
+    std::vector<float> tmp(np);
+    CK(h, cudaMemcpyAsync(tmp.data(), d_p, sizeof(float) * np, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return set_params_host<float>(h, tmp.data(), np);
+}
+
+int kanode_rhs(kanode_handle* h, const float* u, float* du, int64_t batch) { return rhs_host<float>(h, u, du, batch); }
+int kanode_rhs_f64(kanode_handle* h, const double* u, double* du, int64_t batch) { return rhs_host<double>(h, u, du, batch); }
+int kanode_rhs_dev(kanode_handle* h, const float* d_u, float* d_du, int64_t batch) {
+    if (int rc = enter(h)) return rc;
+    return rhs_dev<float>(h, d_u, d_du, batch);
+}
+
+int kanode_vjp(kanode_handle* h, const float* u, const float* lam, float* ubar, float* pbar, int64_t batch) {
+    return vjp_host<float>(h, u, lam, ubar, pbar, batch);
+}
+int kanode_vjp_f64(kanode_handle* h, const double* u, const double* lam, double* ubar, double* pbar, int64_t batch) {
+    return vjp_host<double>(h, u, lam, ubar, pbar, batch);
+}
+
+int kanode_solve(kanode_handle* h, const float* u0, int64_t batch, double t0, double t1, const double* saveat,
+                 int32_t nsave, float abstol, float reltol, float* out, kanode_stats* stats) {
+    return solve_host<float>(h, u0, batch, t0, t1, saveat, nsave, abstol, reltol, out, stats);
+}
+int kanode_solve_f64(kanode_handle* h, const double* u0, int64_t batch, double t0, double t1, const double* saveat,
+                     int32_t nsave, double abstol, double reltol, double* out, kanode_stats* stats) {
+    return solve_host<double>(h, u0, batch, t0, t1, saveat, nsave, abstol, reltol, out, stats);
+}
+int kanode_solve_dev(kanode_handle* h, const float* d_u0, int64_t batch, double t0, double t1, const double* saveat,
+                     int32_t nsave, float abstol, float reltol, float* d_out, kanode_stats* d_stats) {
+    if (int rc = enter(h)) return rc;
+    return solve_dev<float>(h, d_u0, batch, t0, t1, saveat, nsave, abstol, reltol, d_out, d_stats);
+}
+
+int kanode_loss_grad(kanode_handle* h, const float* u0, int64_t batch, double t0, double t1, const double* saveat,
+                     int32_t nsave, const float* target, float abstol, float reltol, float* loss, float* grad,
+                     float* du0, kanode_stats* fwd_stats, kanode_stats* bwd_stats) {
+    return loss_grad_host<float>(h, u0, batch, t0, t1, saveat, nsave, target, abstol, reltol, loss, grad, du0,
+                                 fwd_stats, bwd_stats);
+}
+int kanode_loss_grad_f64(kanode_handle* h, const double* u0, int64_t batch, double t0, double t1, const double* saveat,
+                         int32_t nsave, const double* target, double abstol, double reltol, double* loss, double* grad,
+                         double* du0, kanode_stats* fwd_stats, kanode_stats* bwd_stats) {
+    return loss_grad_host<double>(h, u0, batch, t0, t1, saveat, nsave, target, abstol, reltol, loss, grad, du0,
+                                  fwd_stats, bwd_stats);
+}
+int kanode_loss_grad_dev(kanode_handle* h, const float* d_u0, int64_t batch, double t0, double t1, const double* saveat,
+                         int32_t nsave, const float* d_target, float abstol, float reltol, double* d_loss_sum,
+                         float* d_grad_sum, float* d_du0, kanode_stats* d_fwd_stats, kanode_stats* d_bwd_stats) {
+    if (int rc = enter(h)) return rc;
+    if (batch < 0 || !d_loss_sum || !d_grad_sum) return fail(h, KANODE_ERR_INVALID, "bad arguments");
+    return loss_grad_dev<float>(h, d_u0, batch, t0, t1, saveat, nsave, d_target, abstol, reltol, d_loss_sum,
+                                d_grad_sum, d_du0, d_fwd_stats, d_bwd_stats, (float*)nullptr);
+}
+int kanode_loss_grad_dev_f64(kanode_handle* h, const double* d_u0, int64_t batch, double t0, double t1,
+                             const double* saveat, int32_t nsave, const double* d_target, double abstol, double reltol,
+                             double* d_loss_sum, double* d_grad_sum, double* d_du0, kanode_stats* d_fwd_stats,
+                             kanode_stats* d_bwd_stats) {
+    if (int rc = enter(h)) return rc;
+    if (batch < 0 || !d_loss_sum || !d_grad_sum) return fail(h, KANODE_ERR_INVALID, "bad arguments");
+    return loss_grad_dev<double>(h, d_u0, batch, t0, t1, saveat, nsave, d_target, abstol, reltol, d_loss_sum,
+                                 d_grad_sum, d_du0, d_fwd_stats, d_bwd_stats, (double*)nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// kanode_host.h — handle definition and host-side helpers shared by kanode_api.cu and the kernel front-ends.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/kanode.h"
+
+namespace kanode {
+// layer table for the generic kernels (device-friendly POD)
+struct GenericLayer {
+    int I, O, G, norm, basis, use_base;
+    float grid_lo, grid_step_unused;
+    float inv_h;
+    long long offC, offW;     // offsets into the flat parameter vector
+    long long offGrid;        // offset into the grid table
+};
+struct GenericModel {
+    int n_layers, rhs_kind, n;
+    long long np;
+    double lap_scale;          // lap_coef / dx^2
+    GenericLayer L[KANODE_MAX_LAYERS];
+    float grid[KANODE_MAX_LAYERS * 64];   // Float32 LinRange points per layer (G <= 64)
+    int max_width;             // widest layer interface
+    long long nfac;            // factor floats per backward stage
+};
+}  // namespace kanode
+
+inline thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct kanode_handle {
+    kanode_desc desc{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    size_t np = 0;
+    int n = 0;
+    std::vector<double> params;      // host copy (drives the __grid_constant__ parameter blocks)
+    bool have_params = false;
+    int rec_cap = 32;
+    int64_t launches = 0;
+    std::string err;
+    // grow-only device workspace, keyed by purpose
+    enum { W_U0, W_OUT, W_TARGET, W_STATS_F, W_STATS_B, W_SAVEAT, W_REC_T, W_REC, W_NSTEPS, W_RET, W_DG, W_FAC, W_G,
+           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_LAM, W_GEN, W_COUNT };
+    DevBuf ws[W_COUNT];
+    kanode::GenericModel gm{};               // layer table for the generic kernels
+};
+
+inline int fail(kanode_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(h, call)                                                                                         \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess)                                                                              \
+            return fail(h, e_ == cudaErrorMemoryAllocation ? KANODE_ERR_NOMEM : KANODE_ERR_CUDA, "%s: %s",  \
+                        #call, cudaGetErrorString(e_));                                                     \
+    } while (0)
+
+inline size_t count_params(const kanode_desc* d) {
+    if (!d || d->n_layers < 1 || d->n_layers > KANODE_MAX_LAYERS) return 0;
+    size_t np = 0;
+    for (int l = 0; l < d->n_layers; ++l) {
+        const kanode_layer_desc& s = d->layers[l];
+        if (s.in_dims < 1 || s.out_dims < 1 || s.grid_len < 2) return 0;
+        if (s.normalizer < 0 || s.normalizer > 2 || s.basis < 0 || s.basis > 2) return 0;
+        if (!(s.grid_hi > s.grid_lo) || !(s.denominator > 0)) return 0;
+        if (l > 0 && d->layers[l - 1].out_dims != s.in_dims) return 0;
+        np += (size_t)s.in_dims * s.grid_len * s.out_dims;            // kdense.jl:101
+        if (s.use_base_act) np += (size_t)s.in_dims * s.out_dims;     // kdense.jl:103
+    }
+    if (d->rhs_kind == KANODE_RHS_CHAIN) {
+        if (d->layers[0].in_dims != d->n_state || d->layers[d->n_layers - 1].out_dims != d->n_state) return 0;
+    } else if (d->rhs_kind == KANODE_RHS_SOURCE_LAPLACIAN) {
+        if (d->layers[0].in_dims != 1 || d->layers[d->n_layers - 1].out_dims != 1 || d->n_state < 3 || !(d->dx > 0)) return 0;
+    } else return 0;
+    return np;
+}
+
+// Julia LinRange{Float32}(lo, hi, G)[g+1]  (kdense.jl:90)
+inline float grid_point(const kanode_layer_desc& s, int g) {
+    const double t = (double)g / (double)(s.grid_len - 1);
+    return (float)((1.0 - t) * (double)s.grid_lo + t * (double)s.grid_hi);
+}
+
+inline int ensure(kanode_handle* h, int which, size_t bytes, void** out) {
+    DevBuf& b = h->ws[which];
+    if (b.bytes < bytes) {
+        if (b.p) { CK(h, cudaStreamSynchronize(h->stream)); CK(h, cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); want = bytes; e = cudaMalloc(&b.p, want); }
+        if (e != cudaSuccess) { b.p = nullptr; return fail(h, KANODE_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+        b.bytes = want;
+    }
+    *out = b.p;
+    return 0;
+}
+#define ENSURE(h, which, bytes, ptr)                                   \
+    do {                                                               \
+        void* p_ = nullptr;                                            \
+        int rc_ = ensure(h, kanode_handle::which, (bytes), &p_);       \
+        if (rc_) return rc_;                                           \
+        ptr = reinterpret_cast<decltype(ptr)>(p_);                     \
+    } while (0)
+

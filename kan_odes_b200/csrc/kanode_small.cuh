@@ -1,0 +1,676 @@
+// kanode_small.cuh — ensemble kernels for small 2-layer KAN-ODEs ([I,H,I], e.g. Lotka-Volterra [2,10,2] G=5).
+//
+// Mapping: ONE THREAD PER TRAJECTORY.  The whole ODE state, the 7 Tsit5 stage vectors and the
+// per-trajectory step controller live in registers; the KAN weights (960 B for LV) are passed as a
+// __grid_constant__ kernel parameter so every weight is an immediate constant-bank operand of an FFMA (no load
+// instruction at all); the RBF features are produced and consumed in registers and never touch memory.
+// The backward kernel integrates z=[lambda; g] per trajectory exactly like the reference's InterpolatingAdjoint:
+// lambda and its stages stay in registers; the parameter-gradient part g (NP values per trajectory) is never
+// materialised per stage — each stage stores only the rank-1 factors of dg/dt (NF = 84 values for LV) and the
+// step-end pass rebuilds sum_s b_s k_s[j] and the error-estimate term per component.
+//
+// Reference semantics: see kanode_math.cuh and oracle/kanode_oracle.cpp (same algorithm, CPU).
+//   KDense forward            Lotka-Volterra/src/kdense.jl:109-130
+//   rbf reverse rule          Lotka-Volterra/src/utils.jl:15-21
+//   NeuralODE / loss / grad   Lotka-Volterra/LV_driver_KANODE.jl:180-184,197-203,284
+#pragma once
+#include "../../include/kanode.h"
+#include "kanode_math.cuh"
+
+namespace kanode {
+
+template <class T, int I_, int H_, int G_>
+struct SmallParams {
+    static constexpr int I = I_, H = H_, G = G_;
+    static constexpr int OC1 = 0, OW1 = H * G * I, OC2 = OW1 + H * I, OW2 = OC2 + I * G * H, NP = OW2 + I * H;
+    // rank-1 factor record of one backward stage: [hbar(H) | b1(I*G) sw1(I) | lam(I) | b2(H*G) sw2(H)]
+    static constexpr int F_HBAR = 0, F_CA = H, QA = I * G + I, F_LAM = F_CA + QA, F_CB = F_LAM + I, QB = H * G + H,
+                         NF = F_CB + QB;
+    T w[NP];
+    T grid[G];
+    T inv_h;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// KAN right-hand side, one sample, everything in registers
+// ------------------------------------------------------------------------------------------------------
+template <int NORM, class T, class P>
+__device__ __forceinline__ void small_rhs(const P& p, const T (&u)[P::I], T (&du)[P::I]) {
+    constexpr int I = P::I, H = P::H, G = P::G;
+    T h[H];
+#pragma unroll
+    for (int o = 0; o < H; ++o) h[o] = T(0);
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+        const T xn = normalize<NORM>(u[i]);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const T a = (xn - p.grid[g]) * p.inv_h;
+            const T y = kexp(-a * a);
+#pragma unroll
+            for (int o = 0; o < H; ++o) h[o] += p.w[P::OC1 + (i * G + g) * H + o] * y;
+        }
+        T s; swish_fwd(u[i], s);
+#pragma unroll
+        for (int o = 0; o < H; ++o) h[o] += p.w[P::OW1 + i * H + o] * s;
+    }
+#pragma unroll
+    for (int o = 0; o < I; ++o) du[o] = T(0);
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const T xn = normalize<NORM>(h[i]);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const T a = (xn - p.grid[g]) * p.inv_h;
+            const T y = kexp(-a * a);
+#pragma unroll
+            for (int o = 0; o < I; ++o) du[o] += p.w[P::OC2 + (i * G + g) * I + o] * y;
+        }
+        T s; swish_fwd(h[i], s);
+#pragma unroll
+        for (int o = 0; o < I; ++o) du[o] += p.w[P::OW2 + i * I + o] * s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// fused forward-recompute + VJP: ubar = (df/du)^T lam, and the rank-1 factors of (df/dp)^T lam via st(idx, v).
+// The layer-2 contraction is never computed (the adjoint does not need f(y)).
+// ------------------------------------------------------------------------------------------------------
+template <int NORM, class T, class P, class Store>
+__device__ __forceinline__ void small_vjp(const P& p, const T (&y)[P::I], const T (&lam)[P::I], T (&ubar)[P::I],
+                                          Store&& st) {
+    constexpr int I = P::I, H = P::H, G = P::G;
+    T h[H], xn1[I], db1[I * G], dsw1[I];
+#pragma unroll
+    for (int o = 0; o < H; ++o) h[o] = T(0);
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+        xn1[i] = normalize<NORM>(y[i]);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const T a = (xn1[i] - p.grid[g]) * p.inv_h;
+            const T b = kexp(-a * a);
+            db1[i * G + g] = T(-2) * a * b * p.inv_h;                    // utils.jl:18 times d(arg)/d(xn)
+            st(P::F_CA + i * G + g, b);
+#pragma unroll
+            for (int o = 0; o < H; ++o) h[o] += p.w[P::OC1 + (i * G + g) * H + o] * b;
+        }
+        T s; swish_both(y[i], s, dsw1[i]);
+        st(P::F_CA + I * G + i, s);
+#pragma unroll
+        for (int o = 0; o < H; ++o) h[o] += p.w[P::OW1 + i * H + o] * s;
+    }
+    T hbar[H];
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const T xn = normalize<NORM>(h[i]);
+        T xnbar = T(0);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const T a = (xn - p.grid[g]) * p.inv_h;
+            const T b = kexp(-a * a);
+            st(P::F_CB + i * G + g, b);
+            T bbar = T(0);
+#pragma unroll
+            for (int o = 0; o < I; ++o) bbar += p.w[P::OC2 + (i * G + g) * I + o] * lam[o];
+            xnbar += (T(-2) * a * b * p.inv_h) * bbar;
+        }
+        T s, ds; swish_both(h[i], s, ds);
+        st(P::F_CB + H * G + i, s);
+        T sbar = T(0);
+#pragma unroll
+        for (int o = 0; o < I; ++o) sbar += p.w[P::OW2 + i * I + o] * lam[o];
+        hbar[i] = xnbar * normalize_deriv<NORM>(xn) + sbar * ds;
+        st(P::F_HBAR + i, hbar[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+        T xnbar = T(0);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            T bbar = T(0);
+#pragma unroll
+            for (int o = 0; o < H; ++o) bbar += p.w[P::OC1 + (i * G + g) * H + o] * hbar[o];
+            xnbar += db1[i * G + g] * bbar;
+        }
+        T sbar = T(0);
+#pragma unroll
+        for (int o = 0; o < H; ++o) sbar += p.w[P::OW1 + i * H + o] * hbar[o];
+        ubar[i] = xnbar * normalize_deriv<NORM>(xn1[i]) + sbar * dsw1[i];
+        st(P::F_LAM + i, lam[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// argument blocks
+// ------------------------------------------------------------------------------------------------------
+template <class T> struct SmallFwdArgs {
+    const T* u0;            // [B][I]
+    int64_t B;
+    double t0, t1;
+    const double* saveat;   // device, ascending, inside [t0,t1]
+    int nsave;
+    T abstol, reltol;
+    int maxiters;
+    T* out;                 // [B][nsave][I] or null
+    kanode_stats* stats;    // [B] or null
+    // dense record for the adjoint (DENSE kernels)
+    double* rec_t;          // [cap][B]   start time of each accepted step
+    T* rec;                 // [cap][1 + 8*I][B]: dt, u, k1..k7
+    int cap;
+    int* nsteps;            // [B]
+    int* retcode;           // [B]
+    // loss pieces (DENSE kernels)
+    const T* target;        // [B][nsave][I]
+    T* dg;                  // [nsave][I][B]   dL/du(t_s)
+    double* loss_sum;       // scalar accumulator
+};
+
+template <class T> struct SmallBwdArgs {
+    int64_t B;
+    double t0, t1;
+    const double* saveat;
+    int nsave;
+    T abstol, reltol;
+    int maxiters;
+    const double* rec_t; const T* rec; int cap; const int* nsteps; const int* retcode;
+    const T* dg;            // [nsave][I][B]
+    T* fac;                 // [7][NF][B]  stage factors
+    T* g;                   // [2][NP][B]  double-buffered gradient state; result ends in buffer 0
+    T* du0;                 // [B][I] or null
+    kanode_stats* stats;    // [B] or null
+};
+
+// ------------------------------------------------------------------------------------------------------
+// forward: adaptive Tsit5 with saveat interpolation; DENSE additionally records every accepted step and
+// evaluates the loss / dL/du at the save times.
+// ------------------------------------------------------------------------------------------------------
+template <class T, class P, int NORM, bool DENSE>
+__global__ void __launch_bounds__(64) small_forward_kernel(const __grid_constant__ P prm, const SmallFwdArgs<T> a) {
+    constexpr int I = P::I;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = b < a.B;
+    double lsum = 0.0;
+    if (active) {
+        const int64_t B = a.B;
+        T u[I], uprev[I], k[7][I];
+#pragma unroll
+        for (int i = 0; i < I; ++i) { u[i] = a.u0[b * I + i]; uprev[i] = u[i]; }
+        small_rhs<NORM>(prm, u, k[0]);
+        int nf = 1, naccept = 0, nreject = 0, ret = RET_SUCCESS;
+        const double t0 = a.t0, t1 = a.t1, dtmax = fabs(t1 - t0);
+        const double dtmin0 = fmax(eps_of(t0), eps_of(t1));
+        const T abstol = a.abstol, reltol = a.reltol;
+        double t = t0, dt;
+        {   // ---- ode_determine_initdt (Hairer) ----
+            T s0 = T(0), s1 = T(0), sk[I], u1[I], f1[I];
+#pragma unroll
+            for (int i = 0; i < I; ++i) {
+                sk[i] = abstol + kabs(u[i]) * reltol;
+                const T x0 = u[i] / sk[i], x1 = k[0][i] / sk[i];
+                s0 += x0 * x0; s1 += x1 * x1;
+            }
+            const double d0 = sqrt((double)s0 / I), d1 = sqrt((double)s1 / I);
+            double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
+            dt0 = fmin(dt0, dtmax);
+#pragma unroll
+            for (int i = 0; i < I; ++i) u1[i] = u[i] + (T)dt0 * k[0][i];
+            small_rhs<NORM>(prm, u1, f1);
+            nf += 2;
+            T s2 = T(0);
+#pragma unroll
+            for (int i = 0; i < I; ++i) { const T x = (f1[i] - k[0][i]) / sk[i]; s2 += x * x; }
+            const double d2 = sqrt((double)s2 / I) / dt0;
+            const double mx = fmax(d1, d2);
+            const double dt1 = (mx <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / 5.0);
+            dt = fmax(dtmin0, fmin(fmin(100.0 * dt0, dt1), dtmax));
+        }
+        double qold = Ctrl::qoldinit, q11 = 1.0, dtpropose = dt;
+        bool accept = false;
+        int iter = 0, sidx = 0, nrec = 0;
+        if (t0 == t1) {   // degenerate span: outputs are u0
+            for (; sidx < a.nsave; ++sidx)
+#pragma unroll
+                for (int i = 0; i < I; ++i) if (a.out) a.out[(b * a.nsave + sidx) * I + i] = u[i];
+        }
+        while (t < t1) {
+            // ---- loopheader! ----
+            if (iter > 0) {
+                if (!accept) dt = dt / fmin(1.0 / Ctrl::qmin, q11 / Ctrl::gamma);
+                else dt = dtpropose;
+            }
+            ++iter;
+            const double dtmin_t = fmax(eps_of(t), dtmin0);
+            dt = fmin(fmax(fmin(fabs(dt), dtmax), dtmin_t), t1 - t);
+            if (iter > a.maxiters) { ret = RET_MAXITERS; break; }
+            if (!(dt > dtmin_t) && (t + dt < t1 || !accept) && iter > 1) { ret = RET_DTMIN; break; }
+            if (dt != dt) { ret = RET_UNSTABLE; break; }
+            // ---- perform_step! ----
+            const T h = (T)dt;
+            T unew[I];
+#pragma unroll 1
+            for (int s = 1; s < 7; ++s) {
+                T us[I], ks[I];
+#pragma unroll
+                for (int i = 0; i < I; ++i) {
+                    T acc = T(0);
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) acc += Tab<T>::a(s, j) * k[j][i];
+                    us[i] = uprev[i] + h * acc;
+                }
+                small_rhs<NORM>(prm, us, ks);
+#pragma unroll
+                for (int j = 1; j < 7; ++j)
+                    if (j == s) {
+#pragma unroll
+                        for (int i = 0; i < I; ++i) k[j][i] = ks[i];
+                    }
+                if (s == 6) {
+#pragma unroll
+                    for (int i = 0; i < I; ++i) unew[i] = us[i];
+                }
+            }
+            nf += 6;
+            T es = T(0);
+            bool bad = false;
+#pragma unroll
+            for (int i = 0; i < I; ++i) {
+                T ut = T(0);
+#pragma unroll
+                for (int j = 0; j < 7; ++j) ut += Tab<T>::bt(j) * k[j][i];
+                ut *= h;
+                const T sc = abstol + kmax(kabs(uprev[i]), kabs(unew[i])) * reltol;
+                const T r = ut / sc;
+                es += r * r;
+                bad |= (unew[i] != unew[i]);
+            }
+            const double EEst = (double)ksqrt(es / T(I));
+            if (EEst != EEst || bad) { ret = RET_UNSTABLE; break; }
+            // ---- loopfooter!: PI controller ----
+            const double q = pi_q(EEst, qold, q11);
+            accept = EEst <= 1.0;
+            if (accept) {
+                ++naccept;
+                qold = fmax(EEst, Ctrl::qoldinit);
+                const double dtnew = dt / q;
+                double tnew = t + dt;
+                if (fabs(tnew - t1) < 100.0 * eps_of(fmax(fabs(t), fabs(t1)))) tnew = t1;
+                dtpropose = fmax(fmin(dtmax, fabs(dtnew)), fmax(eps_of(tnew), dtmin0));
+                if (DENSE) {
+                    if (nrec >= a.cap) { ret = RET_OVERFLOW; break; }
+                    a.rec_t[(int64_t)nrec * B + b] = t;
+                    T* r = a.rec + (int64_t)nrec * (1 + 8 * I) * B + b;
+                    r[0] = h;
+#pragma unroll
+                    for (int i = 0; i < I; ++i) r[(int64_t)(1 + i) * B] = uprev[i];
+#pragma unroll
+                    for (int j = 0; j < 7; ++j)
+#pragma unroll
+                        for (int i = 0; i < I; ++i) r[(int64_t)(1 + I + j * I + i) * B] = k[j][i];
+                    ++nrec;
+                }
+                // saveat: dense output inside (t, tnew]  (and t0 itself on the first step)
+                while (sidx < a.nsave && a.saveat[sidx] <= tnew) {
+                    const T th = (T)((a.saveat[sidx] - t) / dt);
+                    T bw[7]; interp_weights(th, bw);
+#pragma unroll
+                    for (int i = 0; i < I; ++i) {
+                        T acc = T(0);
+#pragma unroll
+                        for (int j = 0; j < 7; ++j) acc += bw[j] * k[j][i];
+                        const T v = uprev[i] + h * acc;
+                        if (a.out) a.out[(b * a.nsave + sidx) * I + i] = v;
+                        if (DENSE) {
+                            const T e = v - a.target[(b * a.nsave + sidx) * I + i];
+                            lsum += (double)e * (double)e;
+                            a.dg[((int64_t)sidx * I + i) * B + b] = (T(2) / (T)((double)I * a.nsave)) * e;
+                        }
+                    }
+                    ++sidx;
+                }
+                t = tnew;
+#pragma unroll
+                for (int i = 0; i < I; ++i) { uprev[i] = unew[i]; u[i] = unew[i]; k[0][i] = k[6][i]; }
+            } else {
+                ++nreject;
+            }
+        }
+        if (ret != RET_SUCCESS) {   // leave NaN in the unsaved outputs of a failed trajectory
+            for (; sidx < a.nsave; ++sidx)
+#pragma unroll
+                for (int i = 0; i < I; ++i) {
+                    if (a.out) a.out[(b * a.nsave + sidx) * I + i] = T(NAN);
+                    if (DENSE) a.dg[((int64_t)sidx * I + i) * B + b] = T(0);
+                }
+        }
+        if (a.stats) a.stats[b] = kanode_stats{naccept, nreject, nf, ret};
+        if (DENSE) { a.nsteps[b] = nrec; a.retcode[b] = ret; }
+    }
+    if (DENSE) {   // block-level loss reduction, one atomic per warp
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+        if ((threadIdx.x & 31) == 0 && lsum != 0.0) atomicAdd(a.loss_sum, lsum);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward: interpolating adjoint on z = [lambda(I); g(NP)], T -> t0, tstops + jumps at the save times
+// ------------------------------------------------------------------------------------------------------
+template <class T, class P> struct GPhase {
+    // visit every parameter-gradient component j with the per-stage derivative factors a_s (by o) and c_s (by q):
+    // k_s[j] = -(a_s[o] * c_s[q]).  fn(j, av[NS], cv[NS]) for the NS stage slots starting at slot0.
+    template <int NS, class Fn>
+    static __device__ __forceinline__ void for_each(const T* fac, int64_t B, int slot0, Fn&& fn) {
+        constexpr int H = P::H, I = P::I;
+        // block A: a = hbar (H), c = [b1; sw1] (QA), j = OC1 + q*H + o   (C1 then W1 are contiguous)
+#pragma unroll 1
+        for (int o = 0; o < H; ++o) {
+            T av[NS];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) av[s] = fac[((int64_t)(slot0 + s) * P::NF + P::F_HBAR + o) * B];
+#pragma unroll 1
+            for (int q = 0; q < P::QA; ++q) {
+                T cv[NS];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) cv[s] = fac[((int64_t)(slot0 + s) * P::NF + P::F_CA + q) * B];
+                fn(P::OC1 + q * H + o, av, cv);
+            }
+        }
+        // block B: a = lam (I), c = [b2; sw2] (QB), j = OC2 + q*I + o   (C2 then W2 are contiguous)
+        T aw[I][NS];
+#pragma unroll
+        for (int o = 0; o < I; ++o)
+#pragma unroll
+            for (int s = 0; s < NS; ++s) aw[o][s] = fac[((int64_t)(slot0 + s) * P::NF + P::F_LAM + o) * B];
+#pragma unroll 1
+        for (int q = 0; q < P::QB; ++q) {
+            T cv[NS];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) cv[s] = fac[((int64_t)(slot0 + s) * P::NF + P::F_CB + q) * B];
+#pragma unroll
+            for (int o = 0; o < I; ++o) fn(P::OC2 + q * I + o, aw[o], cv);
+        }
+    }
+};
+
+template <class T, class P, int NORM>
+__global__ void __launch_bounds__(64) small_backward_kernel(const __grid_constant__ P prm, const SmallBwdArgs<T> a) {
+    constexpr int I = P::I, NP = P::NP, NF = P::NF, NZ = I + NP, RS = 1 + 8 * I;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int64_t B = a.B;
+    T* fac = a.fac + b;          // element (slot, f) at fac[(slot*NF + f)*B]
+    T* gbuf = a.g + b;           // element (buf, j) at gbuf[(buf*NP + j)*B]
+#pragma unroll 1
+    for (int j = 0; j < NP; ++j) gbuf[(int64_t)j * B] = T(0);
+    T lam[I], lprev[I], kl[7][I];
+#pragma unroll
+    for (int i = 0; i < I; ++i) { lam[i] = T(0); lprev[i] = T(0); }
+    int nf = 0, naccept = 0, nreject = 0, ret = a.retcode[b];
+    const int nsteps = a.nsteps[b];
+    if (ret != RET_SUCCESS || nsteps <= 0) {
+        if (a.stats) a.stats[b] = kanode_stats{0, 0, 0, ret};
+        if (a.du0) for (int i = 0; i < I; ++i) a.du0[b * I + i] = T(0);
+        return;
+    }
+    // cached forward record (dense output of the forward solve)
+    int ridx = nsteps - 1;
+    double rt, rt_next;           // record covers [rt, rt_next]
+    T rdt, ru[I], rk[7][I];
+    auto load_rec = [&](int idx) {
+        rt = a.rec_t[(int64_t)idx * B + b];
+        const T* r = a.rec + (int64_t)idx * RS * B + b;
+        rdt = r[0];
+#pragma unroll
+        for (int i = 0; i < I; ++i) ru[i] = r[(int64_t)(1 + i) * B];
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+#pragma unroll
+            for (int i = 0; i < I; ++i) rk[j][i] = r[(int64_t)(1 + I + j * I + i) * B];
+        rt_next = (idx + 1 < nsteps) ? a.rec_t[(int64_t)(idx + 1) * B + b] : a.t1;
+        ridx = idx;
+    };
+    load_rec(ridx);
+    auto eval_y = [&](double t, T (&y)[I]) {      // y = sol(t), right-continuous at step boundaries
+        while (t < rt && ridx > 0) load_rec(ridx - 1);
+        while (t >= rt_next && ridx + 1 < nsteps) load_rec(ridx + 1);
+        const T th = (T)((t - rt) / (double)rdt);
+        T bw[7]; interp_weights(th, bw);
+#pragma unroll
+        for (int i = 0; i < I; ++i) {
+            T acc = T(0);
+#pragma unroll
+            for (int j = 0; j < 7; ++j) acc += bw[j] * rk[j][i];
+            y[i] = ru[i] + rdt * acc;
+        }
+    };
+    // one adjoint RHS evaluation at (t, l): dl = -(df/du)^T l, factors of dg -> slot
+    auto adj_eval = [&](double t, const T (&l)[I], T (&dl)[I], int slot) {
+        T y[I], ub[I];
+        eval_y(t, y);
+        T* f = fac + (int64_t)slot * NF * B;
+        small_vjp<NORM>(prm, y, l, ub, [&](int idx, T v) { f[(int64_t)idx * B] = v; });
+#pragma unroll
+        for (int i = 0; i < I; ++i) dl[i] = -ub[i];
+        ++nf;
+    };
+
+    const double t0 = a.t0, t1 = a.t1, dtmax = fabs(t1 - t0);
+    const double dtmin0 = fmax(eps_of(t0), eps_of(t1));
+    const T abstol = a.abstol, reltol = a.reltol;
+    double t = t1;
+    int sp = a.nsave - 1;                        // next preset (save) time, descending
+    auto apply_jumps = [&](double tt) {
+        bool mod = false;
+        while (sp >= 0 && a.saveat[sp] == tt) {
+#pragma unroll
+            for (int i = 0; i < I; ++i) lam[i] += a.dg[((int64_t)sp * I + i) * B + b];
+            --sp; mod = true;
+        }
+        return mod;
+    };
+    apply_jumps(t1);                              // PresetTimeCallback fires at init when t_end is a save time
+    adj_eval(t, lam, kl[0], 0);                   // FSAL
+    double dt;                                    // |dt|; integration runs in -t
+    {   // ---- initdt on the augmented state (g(T) = 0 so its scale is abstol) ----
+        T sk[I], s0 = T(0), s1 = T(0);
+#pragma unroll
+        for (int i = 0; i < I; ++i) {
+            sk[i] = abstol + kabs(lam[i]) * reltol;
+            const T x0 = lam[i] / sk[i], x1 = kl[0][i] / sk[i];
+            s0 += x0 * x0; s1 += x1 * x1;
+        }
+        GPhase<T, P>::template for_each<1>(fac, B, 0, [&](int, const T (&av)[1], const T (&cv)[1]) {
+            const T x = (av[0] * cv[0]) / abstol; s1 += x * x;
+        });
+        const double d0 = sqrt((double)s0 / NZ), d1 = sqrt((double)s1 / NZ);
+        double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
+        dt0 = fmin(dt0, dtmax);
+        T l1[I], f1[I];
+#pragma unroll
+        for (int i = 0; i < I; ++i) l1[i] = lam[i] - (T)dt0 * kl[0][i];
+        adj_eval(t - dt0, l1, f1, 1);
+        ++nf;                                     // the package evaluates f0 again; counted like the package does
+        T s2 = T(0);
+#pragma unroll
+        for (int i = 0; i < I; ++i) { const T x = (f1[i] - kl[0][i]) / sk[i]; s2 += x * x; }
+        GPhase<T, P>::template for_each<2>(fac, B, 0, [&](int, const T (&av)[2], const T (&cv)[2]) {
+            const T x = (av[1] * cv[1] - av[0] * cv[0]) / abstol; s2 += x * x;
+        });
+        const double d2 = sqrt((double)s2 / NZ) / dt0;
+        const double mx = fmax(d1, d2);
+        const double dt1 = (mx <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / 5.0);
+        dt = fmax(dtmin0, fmin(fmin(100.0 * dt0, dt1), dtmax));
+    }
+    double qold = Ctrl::qoldinit, q11 = 1.0, dtpropose = dt;
+    bool accept = false, modified = false;
+    int iter = 0, cur = 0;
+    while (t > t0) {
+        // ---- loopheader! ----
+        if (iter > 0) {
+            if (!accept) dt = dt / fmin(1.0 / Ctrl::qmin, q11 / Ctrl::gamma);
+            else {
+                dt = dtpropose;
+                if (modified) { adj_eval(t, lam, kl[0], 0); modified = false; }   // FSAL re-evaluation after a jump
+                else {
+#pragma unroll
+                    for (int i = 0; i < I; ++i) kl[0][i] = kl[6][i];
+#pragma unroll 1
+                    for (int f = 0; f < NF; ++f) fac[(int64_t)f * B] = fac[((int64_t)6 * NF + f) * B];
+                }
+            }
+        }
+        ++iter;
+        const double tstop = (sp >= 0) ? fmax(a.saveat[sp], t0) : t0;
+        const double dtmin_t = fmax(eps_of(t), dtmin0);
+        dt = fmin(fmax(fmin(fabs(dt), dtmax), dtmin_t), t - tstop);
+        if (iter > a.maxiters) { ret = RET_MAXITERS; break; }
+        if (!(dt > dtmin_t) && (t - dt > tstop || !accept) && iter > 1) { ret = RET_DTMIN; break; }
+        if (dt != dt) { ret = RET_UNSTABLE; break; }
+        // ---- perform_step! on lambda (registers); g stages exist only as factors ----
+        const T h = (T)(-dt);
+        T lnew[I];
+#pragma unroll 1
+        for (int s = 1; s < 7; ++s) {
+            T ls[I], ks[I];
+#pragma unroll
+            for (int i = 0; i < I; ++i) {
+                T acc = T(0);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) acc += Tab<T>::a(s, j) * kl[j][i];
+                ls[i] = lprev[i] + h * acc;
+            }
+            adj_eval(t - tab_c(s) * dt, ls, ks, s);
+#pragma unroll
+            for (int j = 1; j < 7; ++j)
+                if (j == s) {
+#pragma unroll
+                    for (int i = 0; i < I; ++i) kl[j][i] = ks[i];
+                }
+            if (s == 6) {
+#pragma unroll
+                for (int i = 0; i < I; ++i) lnew[i] = ls[i];
+            }
+        }
+        // ---- error estimate over all I + NP components; g_new goes to the other buffer ----
+        T es = T(0);
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < I; ++i) {
+            T ut = T(0);
+#pragma unroll
+            for (int j = 0; j < 7; ++j) ut += Tab<T>::bt(j) * kl[j][i];
+            ut *= h;
+            const T sc = abstol + kmax(kabs(lprev[i]), kabs(lnew[i])) * reltol;
+            const T r = ut / sc;
+            es += r * r;
+            bad |= (lnew[i] != lnew[i]);
+        }
+        {
+            T wb[7], wbt[7];
+#pragma unroll
+            for (int s = 0; s < 7; ++s) { wb[s] = -Tab<T>::b(s); wbt[s] = -Tab<T>::bt(s); }   // k = -(a*c)
+            const T* gold = gbuf + (int64_t)cur * NP * B;
+            T* gnew = gbuf + (int64_t)(cur ^ 1) * NP * B;
+            GPhase<T, P>::template for_each<7>(fac, B, 0, [&](int j, const T (&av)[7], const T (&cv)[7]) {
+                T vb = T(0), vt = T(0);
+#pragma unroll
+                for (int s = 0; s < 7; ++s) { const T kk = av[s] * cv[s]; vb += wb[s] * kk; vt += wbt[s] * kk; }
+                const T g0 = gold[(int64_t)j * B];
+                const T g1 = g0 + h * vb;
+                const T sc = abstol + kmax(kabs(g0), kabs(g1)) * reltol;
+                const T r = (h * vt) / sc;
+                es += r * r;
+                gnew[(int64_t)j * B] = g1;
+            });
+        }
+        const double EEst = (double)ksqrt(es / T(NZ));
+        if (EEst != EEst || bad) { ret = RET_UNSTABLE; break; }
+        const double q = pi_q(EEst, qold, q11);
+        accept = EEst <= 1.0;
+        if (accept) {
+            ++naccept;
+            qold = fmax(EEst, Ctrl::qoldinit);
+            const double dtnew = dt / q;
+            double tnew = t - dt;
+            if (fabs(tnew - tstop) < 100.0 * eps_of(fmax(fabs(t), fabs(tstop)))) tnew = tstop;
+            dtpropose = fmax(fmin(dtmax, fabs(dtnew)), fmax(eps_of(tnew), dtmin0));
+            t = tnew;
+            cur ^= 1;
+#pragma unroll
+            for (int i = 0; i < I; ++i) lam[i] = lnew[i];
+            modified = apply_jumps(t);
+#pragma unroll
+            for (int i = 0; i < I; ++i) lprev[i] = lam[i];
+        } else {
+            ++nreject;
+        }
+    }
+    if (cur == 1) {   // result always in buffer 0
+#pragma unroll 1
+        for (int j = 0; j < NP; ++j) gbuf[(int64_t)j * B] = gbuf[((int64_t)NP + j) * B];
+    }
+    if (ret != RET_SUCCESS) {
+#pragma unroll 1
+        for (int j = 0; j < NP; ++j) gbuf[(int64_t)j * B] = T(0);
+    }
+    if (a.du0)
+#pragma unroll
+        for (int i = 0; i < I; ++i) a.du0[b * I + i] = lam[i];
+    if (a.stats) a.stats[b] = kanode_stats{naccept, nreject, nf, ret};
+}
+
+// ------------------------------------------------------------------------------------------------------
+// batch RHS / VJP (kanode_rhs, kanode_vjp)
+// ------------------------------------------------------------------------------------------------------
+template <class T, class P, int NORM>
+__global__ void __launch_bounds__(128) small_rhs_kernel(const __grid_constant__ P prm, const T* u, T* du, int64_t B) {
+    constexpr int I = P::I;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    T x[I], y[I];
+#pragma unroll
+    for (int i = 0; i < I; ++i) x[i] = u[b * I + i];
+    small_rhs<NORM>(prm, x, y);
+#pragma unroll
+    for (int i = 0; i < I; ++i) du[b * I + i] = y[i];
+}
+
+// pbar_rows[j][b] = ((df/dp)^T lam_b)[j]; reduced over b by reduce_rows_kernel
+template <class T, class P, int NORM>
+__global__ void __launch_bounds__(64) small_vjp_kernel(const __grid_constant__ P prm, const T* u, const T* lam, T* ubar,
+                                                       T* fac /*[1][NF][B]*/, T* pbar_rows /*[NP][B]*/, int64_t B) {
+    constexpr int I = P::I;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    T x[I], l[I], ub[I];
+#pragma unroll
+    for (int i = 0; i < I; ++i) { x[i] = u[b * I + i]; l[i] = lam[b * I + i]; }
+    T* f = fac + b;
+    small_vjp<NORM>(prm, x, l, ub, [&](int idx, T v) { f[(int64_t)idx * B] = v; });
+#pragma unroll
+    for (int i = 0; i < I; ++i) ubar[b * I + i] = ub[i];
+    GPhase<T, P>::template for_each<1>(f, B, 0, [&](int j, const T (&av)[1], const T (&cv)[1]) {
+        pbar_rows[(int64_t)j * B + b] = av[0] * cv[0];
+    });
+}
+
+// out[r] = scale * sum_b rows[r][b]   (double accumulation, one block per row)
+template <class T, class OutT>
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const T* rows, int64_t B, OutT* out, double scale) {
+    const T* src = rows + (int64_t)blockIdx.x * B;
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < B; i += blockDim.x) acc += (double)src[i];
+    __shared__ double sh[8];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
+        out[blockIdx.x] = (OutT)(s * scale);
+    }
+}
+
+}  // namespace kanode

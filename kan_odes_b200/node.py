@@ -1,0 +1,204 @@
+"""Host-side mirror of the reference's ODE / gradient surface over the C ABI (include/kanode.h).
+
+Mirrors the three call shapes the reference drivers use:
+  NeuralODE(chain, tspan, Tsit5(); saveat)(u0, p, st) -> (sol, st)        LV/LV_driver_KANODE.jl:180-184
+  ODEProblem(rc_kanode, u0, tspan, p; saveat) + solve(prob, Tsit5())      PDE/Allen-Cahn_Source.jl:96-99
+  Zygote.gradient(loss, p)[1],  loss(p) = mean(abs2, X .- predict(p))     LV/LV_driver_KANODE.jl:197-203,284
+
+All compute happens in libkanode_b200.so (CUDA, sm_100a).  There is no CPU fallback: if the library is missing or no
+B200-class device is usable the constructors raise KanodeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+
+from . import abi
+from .layers import Chain
+
+
+class Tsit5:
+    """Marker for the integrator argument of NeuralODE / solve (the only one on the hot path)."""
+
+
+@dataclass
+class Stats:
+    naccept: np.ndarray
+    nreject: np.ndarray
+    nf: np.ndarray
+    retcode: np.ndarray
+
+    @classmethod
+    def from_raw(cls, raw) -> "Stats":
+        a = np.frombuffer(raw, dtype=np.int32).reshape(-1, 4)
+        return cls(a[:, 0].copy(), a[:, 1].copy(), a[:, 2].copy(), a[:, 3].copy())
+
+
+@dataclass
+class ODESolution:
+    """What `node(u0, p, st)[1]` gives in the reference: `.t`, `.u`, `Array(sol)`, `.stats`, `.retcode`."""
+    t: np.ndarray              # save times
+    array: np.ndarray          # [batch, nsave, n]
+    stats: Stats
+
+    @property
+    def u(self):
+        return [self.array[:, i, :] for i in range(self.array.shape[1])]
+
+    @property
+    def retcode(self):
+        return [abi.RETCODE_NAMES[int(r)] for r in self.stats.retcode]
+
+    def __array__(self, dtype=None, copy=None):
+        """Array(sol): [n, nsave] for a single trajectory (Julia layout), else [batch, nsave, n]."""
+        a = self.array[0].T if self.array.shape[0] == 1 else self.array
+        return a.astype(dtype) if dtype is not None else a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class KanOde:
+    """Owns one kanode_handle: a KDense chain as an ODE right-hand side on one GPU."""
+
+    def __init__(self, chain: Chain, rhs_kind: int = abi.RHS_CHAIN, n_state: int | None = None,
+                 lap_coef: float = 0.0, dx: float = 1.0, device: int = 0, stream: int | None = None,
+                 dtype=np.float32):
+        self.lib = abi.load_library()
+        self.chain = chain
+        self.desc = chain.desc(rhs_kind, n_state, lap_coef, dx)
+        self.n = int(self.desc.n_state)
+        self.np_ = int(self.lib.kanode_param_count(C.byref(self.desc)))
+        if self.np_ == 0:
+            raise abi.KanodeError("invalid model descriptor")
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise ValueError("dtype must be float32 or float64")
+        self._suf = "" if self.dtype == np.float32 else "_f64"
+        self._real = C.c_float if self.dtype == np.float32 else C.c_double
+        h = C.c_void_p()
+        rc = self.lib.kanode_create(C.byref(self.desc), int(device), C.c_void_p(stream), C.byref(h))
+        abi.check(self.lib, None, rc, "kanode_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.kanode_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _fn(self, name):
+        f = getattr(self.lib, name + self._suf)
+        if self._suf:   # the _f64 variants take double tolerances; declare lazily
+            f.restype = C.c_int
+        return f
+
+    def _arr(self, x, shape=None):
+        a = np.ascontiguousarray(x, dtype=self.dtype)
+        return a if shape is None else a.reshape(shape)
+
+    # ---- parameters ----------------------------------------------------------------------------------
+    def set_params(self, p) -> None:
+        p = self._arr(p).reshape(-1)
+        rc = self._fn("kanode_set_params")(self.h, _ptr(p), C.c_size_t(p.size))
+        abi.check(self.lib, self.h, rc, "kanode_set_params")
+
+    # ---- RHS / VJP -----------------------------------------------------------------------------------
+    def rhs(self, u):
+        u = self._arr(u).reshape(-1, self.n)
+        du = np.empty_like(u)
+        rc = self._fn("kanode_rhs")(self.h, _ptr(u), _ptr(du), C.c_int64(u.shape[0]))
+        abi.check(self.lib, self.h, rc, "kanode_rhs")
+        return du
+
+    def vjp(self, u, lam):
+        u = self._arr(u).reshape(-1, self.n)
+        lam = self._arr(lam).reshape(-1, self.n)
+        ubar = np.empty_like(u); pbar = np.empty(self.np_, self.dtype)
+        rc = self._fn("kanode_vjp")(self.h, _ptr(u), _ptr(lam), _ptr(ubar), _ptr(pbar), C.c_int64(u.shape[0]))
+        abi.check(self.lib, self.h, rc, "kanode_vjp")
+        return ubar, pbar
+
+    # ---- solve / loss+gradient -------------------------------------------------------------------------
+    def solve(self, u0, tspan, saveat, abstol=1e-6, reltol=1e-3) -> ODESolution:
+        u0 = self._arr(u0).reshape(-1, self.n)
+        B = u0.shape[0]
+        sa = np.ascontiguousarray(saveat, dtype=np.float64).reshape(-1)
+        out = np.empty((B, sa.size, self.n), self.dtype)
+        stats = (abi.Stats * max(B, 1))()
+        f = self._fn("kanode_solve")
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_int32,
+                      self._real, self._real, C.c_void_p, C.c_void_p]
+        rc = f(self.h, _ptr(u0), B, float(tspan[0]), float(tspan[1]), _ptr(sa), sa.size, abstol, reltol,
+               _ptr(out), stats)
+        abi.check(self.lib, self.h, rc, "kanode_solve")
+        return ODESolution(sa, out, Stats.from_raw(stats))
+
+    def loss_grad(self, u0, tspan, saveat, target, abstol=1e-6, reltol=1e-3):
+        u0 = self._arr(u0).reshape(-1, self.n)
+        B = u0.shape[0]
+        sa = np.ascontiguousarray(saveat, dtype=np.float64).reshape(-1)
+        target = self._arr(target).reshape(B, sa.size, self.n)
+        loss = self._real(0)
+        grad = np.empty(self.np_, self.dtype); du0 = np.empty_like(u0)
+        fst = (abi.Stats * B)(); bst = (abi.Stats * B)()
+        f = self._fn("kanode_loss_grad")
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_void_p,
+                      self._real, self._real, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = f(self.h, _ptr(u0), B, float(tspan[0]), float(tspan[1]), _ptr(sa), sa.size, _ptr(target), abstol, reltol,
+               C.byref(loss), _ptr(grad), _ptr(du0), fst, bst)
+        abi.check(self.lib, self.h, rc, "kanode_loss_grad")
+        return dict(loss=float(loss.value), grad=grad, du0=du0, fwd_stats=Stats.from_raw(fst),
+                    bwd_stats=Stats.from_raw(bst))
+
+    def launch_count(self) -> int:
+        return int(self.lib.kanode_launch_count(self.h))
+
+
+class NeuralODE:
+    """NeuralODE(model, tspan, Tsit5(); saveat, abstol, reltol) — [EXT DiffEqFlux 4.0.0] call surface.
+
+    `node(u0, p, st)` returns `(sol, st)` like the reference (LV_driver_KANODE.jl:183); `node.loss_and_grad(u0, p, X)`
+    is `loss(p)` and `Zygote.gradient(loss, p)[1]` of LV_driver_KANODE.jl:197-203,284 in one call.
+    """
+
+    def __init__(self, model: Chain, tspan: Sequence[float], alg: Tsit5 | None = None, *, saveat=(),
+                 abstol: float = 1e-6, reltol: float = 1e-3, device: int = 0, dtype=np.float32):
+        if alg is not None and not isinstance(alg, Tsit5):
+            raise NotImplementedError("only Tsit5() is on the hot path")
+        self.model, self.tspan = model, (float(tspan[0]), float(tspan[1]))
+        self.saveat = np.asarray(saveat, dtype=np.float64)
+        self.abstol, self.reltol = abstol, reltol
+        self.ode = KanOde(model, device=device, dtype=dtype)
+
+    def __call__(self, u0, p, st=None):
+        self.ode.set_params(p)
+        return self.ode.solve(u0, self.tspan, self.saveat, self.abstol, self.reltol), st
+
+    def loss_and_grad(self, u0, p, target):
+        self.ode.set_params(p)
+        r = self.ode.loss_grad(u0, self.tspan, self.saveat, target, self.abstol, self.reltol)
+        return r["loss"], r["grad"], r
+
+
+class SourceODE(NeuralODE):
+    """`rc_kanode(u,p,t) = s*D*lap*u + kan1_.(u)` + `solve(prob, Tsit5())`  (PDE/Allen-Cahn_Source.jl:90-99,
+    PDE/Fisher-KPP_Source.jl:95-104): periodic 3-point Laplacian plus a pointwise 1->1 KAN."""
+
+    def __init__(self, model: Chain, n_state: int, lap_coef: float, dx: float, tspan, alg=None, *, saveat=(),
+                 abstol: float = 1e-6, reltol: float = 1e-3, device: int = 0, dtype=np.float32):
+        if alg is not None and not isinstance(alg, Tsit5):
+            raise NotImplementedError("only Tsit5() is on the hot path")
+        self.model, self.tspan = model, (float(tspan[0]), float(tspan[1]))
+        self.saveat = np.asarray(saveat, dtype=np.float64)
+        self.abstol, self.reltol = abstol, reltol
+        self.ode = KanOde(model, abi.RHS_SOURCE_LAPLACIAN, n_state, lap_coef, dx, device=device, dtype=dtype)

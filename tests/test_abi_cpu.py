@@ -1,0 +1,76 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/kanode.h declares,
+validates descriptors, and refuses to compute without a GPU (there is no CPU fallback)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import kan_odes_b200 as K
+from conftest import lv_chain, source_chain
+from kan_odes_b200 import abi
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    return abi.load_library()
+
+
+def test_header_symbols_all_exported(lib):
+    hdr = (ROOT / "include" / "kanode.h").read_text()
+    declared = set(re.findall(r"\b(kanode_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"kanode_handle"}
+    assert declared == set(abi.EXPORTED_SYMBOLS), declared ^ set(abi.EXPORTED_SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert b"sm_100a" in lib.kanode_version()
+
+
+def test_param_count_matches_parameterlength(lib):
+    for chain, kw in [(lv_chain(), {}), (lv_chain(40, 5), {}),
+                      (source_chain(10), dict(rhs_kind=abi.RHS_SOURCE_LAPLACIAN, n_state=41, lap_coef=-1e-4, dx=0.05))]:
+        d = chain.desc(**kw)
+        assert lib.kanode_param_count(C.byref(d)) == chain.parameterlength()
+    bad = lv_chain().desc(); bad.n_state = 3
+    assert lib.kanode_param_count(C.byref(bad)) == 0
+    bad = lv_chain().desc(); bad.layers[0].grid_len = 1
+    assert lib.kanode_param_count(C.byref(bad)) == 0
+
+
+def test_desc_struct_layout_matches_header():
+    assert C.sizeof(abi.LayerDesc) == 36
+    assert C.sizeof(abi.Desc) == 4 + 8 * 36 + 4 + 4 + 4 + 8 + 8   # with 4 bytes padding before the doubles
+    assert C.sizeof(abi.Stats) == 16
+
+
+def test_create_without_gpu_fails_loudly(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    d = lv_chain().desc()
+    h = C.c_void_p()
+    rc = lib.kanode_create(C.byref(d), 0, None, C.byref(h))
+    assert rc == -2 and not h.value
+    assert b"no CPU fallback" in lib.kanode_last_error(None)
+    with pytest.raises(K.KanodeError):
+        K.NeuralODE(lv_chain(), (0.0, 3.5), K.Tsit5(), saveat=[0.0])
+
+
+def test_flat_parameter_layout_roundtrip():
+    chain = lv_chain()
+    ps, st = K.setup(np.random.default_rng(0), chain)
+    p = K.flatten_params(ps)
+    assert p.dtype == np.float32 and p.size == 240
+    back = K.unflatten_params(chain, p)
+    for name in ps:
+        for key in ps[name]:
+            assert np.array_equal(back[name][key], ps[name][key])
+    # column (i-1)*G+g of C belongs to input i (Activation_getter.jl:9-10)
+    assert np.array_equal(back["layer_1"]["C"][:, :5], ps["layer_1"]["C"][:, :5])
+    assert np.allclose(st["layer_1"]["grid"], [-1, -0.5, 0, 0.5, 1])
+    assert chain.layers[0].denominator == 0.5 and chain.layers[0].statelength() == 5
