@@ -74,7 +74,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = Path(path) if path else LIB_PATH
+    p = Path(path) if path else Path(os.environ.get("KANODE_B200_LIB", LIB_PATH))
     if not p.exists():
         raise KanodeError(
             f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

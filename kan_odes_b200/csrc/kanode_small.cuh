@@ -196,6 +196,12 @@ __global__ void __launch_bounds__(64) small_forward_kernel(const __grid_constant
         T u[I], uprev[I], k[7][I];
 #pragma unroll
         for (int i = 0; i < I; ++i) { u[i] = a.u0[b * I + i]; uprev[i] = u[i]; }
+        // stages 2..7 are multiplied by zero tableau entries before they are first written: they must not hold
+        // NaN/Inf bit patterns
+#pragma unroll
+        for (int j = 1; j < 7; ++j)
+#pragma unroll
+            for (int i = 0; i < I; ++i) k[j][i] = T(0);
         small_rhs<NORM>(prm, u, k[0]);
         int nf = 1, naccept = 0, nreject = 0, ret = RET_SUCCESS;
         const double t0 = a.t0, t1 = a.t1, dtmax = fabs(t1 - t0);
@@ -248,6 +254,8 @@ __global__ void __launch_bounds__(64) small_forward_kernel(const __grid_constant
             // ---- perform_step! ----
             const T h = (T)dt;
             T unew[I];
+#pragma unroll
+            for (int i = 0; i < I; ++i) unew[i] = uprev[i];
 #pragma unroll 1
             for (int s = 1; s < 7; ++s) {
                 T us[I], ks[I];
@@ -285,6 +293,9 @@ __global__ void __launch_bounds__(64) small_forward_kernel(const __grid_constant
                 bad |= (unew[i] != unew[i]);
             }
             const double EEst = (double)ksqrt(es / T(I));
+#ifdef KANODE_DEBUG
+            if (b == 0) printf("fwd iter %d t %g dt %g es %g EEst %g unew %g %g k0 %g k6 %g abstol %g reltol %g\n", iter, t, dt, (double)es, EEst, (double)unew[0], (double)unew[1], (double)k[0][0], (double)k[6][0], (double)abstol, (double)reltol);
+#endif
             if (EEst != EEst || bad) { ret = RET_UNSTABLE; break; }
             // ---- loopfooter!: PI controller ----
             const double q = pi_q(EEst, qold, q11);
@@ -406,6 +417,10 @@ __global__ void __launch_bounds__(64) small_backward_kernel(const __grid_constan
     T lam[I], lprev[I], kl[7][I];
 #pragma unroll
     for (int i = 0; i < I; ++i) { lam[i] = T(0); lprev[i] = T(0); }
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+#pragma unroll
+        for (int i = 0; i < I; ++i) kl[j][i] = T(0);   // see the forward kernel: zero-weighted stages must be finite
     int nf = 0, naccept = 0, nreject = 0, ret = a.retcode[b];
     const int nsteps = a.nsteps[b];
     if (ret != RET_SUCCESS || nsteps <= 0) {
@@ -530,6 +545,8 @@ __global__ void __launch_bounds__(64) small_backward_kernel(const __grid_constan
         // ---- perform_step! on lambda (registers); g stages exist only as factors ----
         const T h = (T)(-dt);
         T lnew[I];
+#pragma unroll
+        for (int i = 0; i < I; ++i) lnew[i] = lprev[i];
 #pragma unroll 1
         for (int s = 1; s < 7; ++s) {
             T ls[I], ks[I];
@@ -585,6 +602,9 @@ __global__ void __launch_bounds__(64) small_backward_kernel(const __grid_constan
             });
         }
         const double EEst = (double)ksqrt(es / T(NZ));
+#ifdef KANODE_DEBUG
+        if (b == 0) printf("bwd iter %d t %g dt %g es %g EEst %g lnew %g %g kl0 %g kl6 %g abstol %g reltol %g\n", iter, t, dt, (double)es, EEst, (double)lnew[0], (double)lnew[1], (double)kl[0][0], (double)kl[6][0], (double)abstol, (double)reltol);
+#endif
         if (EEst != EEst || bad) { ret = RET_UNSTABLE; break; }
         const double q = pi_q(EEst, qold, q11);
         accept = EEst <= 1.0;
