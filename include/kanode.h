@@ -206,6 +206,11 @@ int kanode_loss_grad_dev_f64(kanode_handle* h, const double* d_u0, int64_t batch
  * it automatically on overflow; *_dev entry points report KANODE_RET_RECORD_OVERFLOW in the stats instead. */
 int kanode_set_record_capacity(kanode_handle* h, int32_t max_steps);
 
+/* device time of the kernels of the LAST kanode_loss_grad*() call, measured with CUDA events recorded on the
+ * handle's stream around each launch: ms[0] = forward (Tsit5 + dense record + loss), ms[1] = backward (adjoint),
+ * ms[2] = gradient reduction.  Blocks until that call has finished. */
+int kanode_last_timing(kanode_handle* h, float* ms3);
+
 /* number of kernel launches issued by this handle since creation (for bench accounting) */
 int64_t kanode_launch_count(const kanode_handle* h);
 

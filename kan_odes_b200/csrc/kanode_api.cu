@@ -165,21 +165,28 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
         ENSURE(h, W_NSTEPS, sizeof(int) * (size_t)B, nsteps);
         ENSURE(h, W_RET, sizeof(int) * (size_t)B, retc);
         ENSURE(h, W_DG, sizeof(T) * (size_t)nsave * I * B, dg);
-        ENSURE(h, W_FAC, sizeof(T) * (size_t)7 * P::NF * B, fac);
         ENSURE(h, W_G, sizeof(T) * (size_t)2 * P::NP * B, g);
         SmallFwdArgs<T> a{};
         a.u0 = d_u0; a.B = B; a.t0 = t0; a.t1 = t1; a.saveat = d_saveat; a.nsave = nsave;
         a.abstol = (T)abstol; a.reltol = (T)reltol; a.maxiters = 100000; a.out = d_out_opt; a.stats = d_fst;
         a.rec_t = rec_t; a.rec = rec; a.cap = cap; a.nsteps = nsteps; a.retcode = retc;
         a.target = d_target; a.dg = dg; a.loss_sum = d_loss_sum;
+        cudaEventRecord(h->ev[0], h->stream);
         small_forward_kernel<T, P, NORM, true><<<blocks_for(B, 64), 64, 0, h->stream>>>(prm, a);
+        cudaEventRecord(h->ev[1], h->stream);
         SmallBwdArgs<T> bw{};
         bw.B = B; bw.t0 = t0; bw.t1 = t1; bw.saveat = d_saveat; bw.nsave = nsave;
         bw.abstol = (T)abstol; bw.reltol = (T)reltol; bw.maxiters = 100000;
         bw.rec_t = rec_t; bw.rec = rec; bw.cap = cap; bw.nsteps = nsteps; bw.retcode = retc; bw.dg = dg;
-        bw.fac = fac; bw.g = g; bw.du0 = d_du0; bw.stats = d_bst;
-        small_backward_kernel<T, P, NORM><<<blocks_for(B, 64), 64, 0, h->stream>>>(prm, bw);
+        bw.fac = nullptr; bw.g = g; bw.du0 = d_du0; bw.stats = d_bst;
+        constexpr int BT = 128;                                        // threads (= trajectories) per block
+        const size_t smem = sizeof(T) * 7 * StageRec<P>::N * BT;       // 7 stage records per trajectory
+        CK(h, cudaFuncSetAttribute(small_backward_kernel<T, P, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        small_backward_kernel<T, P, NORM><<<blocks_for(B, BT), BT, smem, h->stream>>>(prm, bw);
+        cudaEventRecord(h->ev[2], h->stream);
         reduce_rows_kernel<T, T><<<P::NP, 256, 0, h->stream>>>(g, B, d_grad_sum, 1.0);
+        cudaEventRecord(h->ev[3], h->stream);
+        h->ev_valid = true;
         h->launches += 3;
         CK(h, cudaGetLastError());
         return 0;
@@ -327,6 +334,8 @@ int kanode_create(const kanode_desc* desc, int device, void* stream, kanode_hand
         if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, KANODE_ERR_CUDA, "cudaStreamCreate failed"); }
         h->own_stream = true;
     }
+    for (auto& e : h->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) { kanode_destroy(h); return fail(nullptr, KANODE_ERR_CUDA, "cudaEventCreate failed"); }
     if (int rc = generic_init(h)) { g_create_error = h->err; kanode_destroy(h); return rc; }
     *out = h;
     return 0;
@@ -337,6 +346,7 @@ int kanode_destroy(kanode_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (auto& b : h->ws) if (b.p) cudaFree(b.p);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -355,6 +365,14 @@ int kanode_set_record_capacity(kanode_handle* h, int32_t max_steps) {
 }
 
 int64_t kanode_launch_count(const kanode_handle* h) { return h ? h->launches : 0; }
+
+int kanode_last_timing(kanode_handle* h, float* ms3) {
+    if (int rc = enter(h)) return rc;
+    if (!ms3 || !h->ev_valid) return fail(h, KANODE_ERR_INVALID, "no timed loss_grad call yet");
+    CK(h, cudaEventSynchronize(h->ev[3]));
+    for (int i = 0; i < 3; ++i) CK(h, cudaEventElapsedTime(&ms3[i], h->ev[i], h->ev[i + 1]));
+    return 0;
+}
 
 int kanode_set_params(kanode_handle* h, const float* p, size_t np) { return set_params_host<float>(h, p, np); }
 int kanode_set_params_f64(kanode_handle* h, const double* p, size_t np) { return set_params_host<double>(h, p, np); }

@@ -15,6 +15,8 @@
 //   NeuralODE / loss / grad   Lotka-Volterra/LV_driver_KANODE.jl:180-184,197-203,284
 #pragma once
 #include "../../include/kanode.h"
+#include <type_traits>
+
 #include "kanode_math.cuh"
 
 namespace kanode {
@@ -404,13 +406,92 @@ template <class T, class P> struct GPhase {
     }
 };
 
+// Stage record kept in SHARED memory for the 7 Tsit5 stages of one backward step (per trajectory):
+//   [ y(I) | h(H) | hbar(H) | lam(I) ]  — the forward state, the hidden pre-activations, the hidden cotangent and
+// the stage adjoint.  Every rank-1 factor of dg/dt is a cheap function of these: the step-end pass recomputes the
+// activations (tanh/RBF/SiLU) per unit instead of storing the 84 factors per stage in memory.
+template <class P> struct StageRec {
+    static constexpr int Y = 0, HH = P::I, HBAR = P::I + P::H, LAM = P::I + 2 * P::H, N = 2 * P::I + 2 * P::H;
+};
+
+// fused forward-recompute + VJP returning the hidden pre-activation h and its cotangent hbar (registers)
+template <int NORM, class T, class P>
+__device__ __forceinline__ void small_vjp_h(const P& p, const T (&y)[P::I], const T (&lam)[P::I], T (&ubar)[P::I],
+                                            T (&h)[P::H], T (&hbar)[P::H]) {
+    constexpr int I = P::I, H = P::H, G = P::G;
+    T xn1[I], db1[I * G], dsw1[I];
+#pragma unroll
+    for (int o = 0; o < H; ++o) h[o] = T(0);
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+        xn1[i] = normalize<NORM>(y[i]);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const T a = (xn1[i] - p.grid[g]) * p.inv_h;
+            const T b = kexp(-a * a);
+            db1[i * G + g] = T(-2) * a * b * p.inv_h;
+#pragma unroll
+            for (int o = 0; o < H; ++o) h[o] += p.w[P::OC1 + (i * G + g) * H + o] * b;
+        }
+        T s; swish_both(y[i], s, dsw1[i]);
+#pragma unroll
+        for (int o = 0; o < H; ++o) h[o] += p.w[P::OW1 + i * H + o] * s;
+    }
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const T xn = normalize<NORM>(h[i]);
+        T xnbar = T(0);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const T a = (xn - p.grid[g]) * p.inv_h;
+            const T b = kexp(-a * a);
+            T bbar = T(0);
+#pragma unroll
+            for (int o = 0; o < I; ++o) bbar += p.w[P::OC2 + (i * G + g) * I + o] * lam[o];
+            xnbar += (T(-2) * a * b * p.inv_h) * bbar;
+        }
+        T s, ds; swish_both(h[i], s, ds);
+        T sbar = T(0);
+#pragma unroll
+        for (int o = 0; o < I; ++o) sbar += p.w[P::OW2 + i * I + o] * lam[o];
+        hbar[i] = xnbar * normalize_deriv<NORM>(xn) + sbar * ds;
+    }
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+        T xnbar = T(0);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            T bbar = T(0);
+#pragma unroll
+            for (int o = 0; o < H; ++o) bbar += p.w[P::OC1 + (i * G + g) * H + o] * hbar[o];
+            xnbar += db1[i * G + g] * bbar;
+        }
+        T sbar = T(0);
+#pragma unroll
+        for (int o = 0; o < H; ++o) sbar += p.w[P::OW1 + i * H + o] * hbar[o];
+        ubar[i] = xnbar * normalize_deriv<NORM>(xn1[i]) + sbar * dsw1[i];
+    }
+}
+
+// c-vector of one KDense input unit: [basis(G); swish]  (the rank-1 factor shared by all outputs of that unit)
+template <int NORM, class T, class P>
+__device__ __forceinline__ void unit_features(const P& p, T x, T (&c)[P::G + 1]) {
+    const T xn = normalize<NORM>(x);
+#pragma unroll
+    for (int g = 0; g < P::G; ++g) { const T a = (xn - p.grid[g]) * p.inv_h; c[g] = kexp(-a * a); }
+    swish_fwd(x, c[P::G]);
+}
+
 template <class T, class P, int NORM>
-__global__ void __launch_bounds__(64) small_backward_kernel(const __grid_constant__ P prm, const SmallBwdArgs<T> a) {
-    constexpr int I = P::I, NP = P::NP, NF = P::NF, NZ = I + NP, RS = 1 + 8 * I;
+__global__ void __launch_bounds__(128, 2) small_backward_kernel(const __grid_constant__ P prm, const SmallBwdArgs<T> a) {
+    constexpr int I = P::I, H = P::H, G = P::G, NP = P::NP, NZ = I + NP, RS = 1 + 8 * I;
+    using SR = StageRec<P>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* sm = reinterpret_cast<T*>(smem_raw) + threadIdx.x;          // element (slot, f) at sm[(slot*SR::N + f)*nthr]
+    const int nthr = blockDim.x;
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
     const int64_t B = a.B;
-    T* fac = a.fac + b;          // element (slot, f) at fac[(slot*NF + f)*B]
     T* gbuf = a.g + b;           // element (buf, j) at gbuf[(buf*NP + j)*B]
 #pragma unroll 1
     for (int j = 0; j < NP; ++j) gbuf[(int64_t)j * B] = T(0);
@@ -420,7 +501,7 @@ __global__ void __launch_bounds__(64) small_backward_kernel(const __grid_constan
 #pragma unroll
     for (int j = 0; j < 7; ++j)
 #pragma unroll
-        for (int i = 0; i < I; ++i) kl[j][i] = T(0);   // see the forward kernel: zero-weighted stages must be finite
+        for (int i = 0; i < I; ++i) kl[j][i] = T(0);   // zero-weighted stages must be finite (see forward kernel)
     int nf = 0, naccept = 0, nreject = 0, ret = a.retcode[b];
     const int nsteps = a.nsteps[b];
     if (ret != RET_SUCCESS || nsteps <= 0) {
@@ -459,15 +540,63 @@ __global__ void __launch_bounds__(64) small_backward_kernel(const __grid_constan
             y[i] = ru[i] + rdt * acc;
         }
     };
-    // one adjoint RHS evaluation at (t, l): dl = -(df/du)^T l, factors of dg -> slot
+    // one adjoint RHS evaluation at (t, l): dl = -(df/du)^T l; stage record -> shared-memory slot
     auto adj_eval = [&](double t, const T (&l)[I], T (&dl)[I], int slot) {
-        T y[I], ub[I];
+        T y[I], ub[I], hh[H], hb[H];
         eval_y(t, y);
-        T* f = fac + (int64_t)slot * NF * B;
-        small_vjp<NORM>(prm, y, l, ub, [&](int idx, T v) { f[(int64_t)idx * B] = v; });
+        small_vjp_h<NORM>(prm, y, l, ub, hh, hb);
+        T* s = sm + slot * SR::N * nthr;
 #pragma unroll
-        for (int i = 0; i < I; ++i) dl[i] = -ub[i];
+        for (int i = 0; i < I; ++i) { s[(SR::Y + i) * nthr] = y[i]; s[(SR::LAM + i) * nthr] = l[i]; dl[i] = -ub[i]; }
+#pragma unroll
+        for (int o = 0; o < H; ++o) { s[(SR::HH + o) * nthr] = hh[o]; s[(SR::HBAR + o) * nthr] = hb[o]; }
         ++nf;
+    };
+    // Visit every parameter-gradient component of the NS stage slots: fn(j, kv[NS]) with kv[s] = (df/dp)^T lam
+    // of stage s at component j (dg/dt = -kv).  Activations are recomputed per unit from the stage records.
+    auto for_each_g = [&](auto ns_tag, auto&& fn) {
+        constexpr int NS = decltype(ns_tag)::value;
+        // layer 1: unit = state component i; a = hbar (H outputs), c = features(y_i); C1 then W1
+#pragma unroll 1
+        for (int i = 0; i < I; ++i) {
+            T c[NS][G + 1];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) unit_features<NORM>(prm, sm[(s * SR::N + SR::Y + i) * nthr], c[s]);
+#pragma unroll 1
+            for (int o = 0; o < H; ++o) {
+                T av[NS];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) av[s] = sm[(s * SR::N + SR::HBAR + o) * nthr];
+#pragma unroll
+                for (int q = 0; q <= G; ++q) {
+                    T kv[NS];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) kv[s] = av[s] * c[s][q];
+                    fn(q < G ? P::OC1 + (i * G + q) * H + o : P::OW1 + i * H + o, kv);
+                }
+            }
+        }
+        // layer 2: unit = hidden unit i; a = lam (I outputs), c = features(h_i); C2 then W2
+        T al[NS][I];
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int o = 0; o < I; ++o) al[s][o] = sm[(s * SR::N + SR::LAM + o) * nthr];
+#pragma unroll 1
+        for (int i = 0; i < H; ++i) {
+            T c[NS][G + 1];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) unit_features<NORM>(prm, sm[(s * SR::N + SR::HH + i) * nthr], c[s]);
+#pragma unroll
+            for (int q = 0; q <= G; ++q)
+#pragma unroll
+                for (int o = 0; o < I; ++o) {
+                    T kv[NS];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) kv[s] = al[s][o] * c[s][q];
+                    fn(q < G ? P::OC2 + (i * G + q) * I + o : P::OW2 + i * I + o, kv);
+                }
+        }
     };
 
     const double t0 = a.t0, t1 = a.t1, dtmax = fabs(t1 - t0);
@@ -495,8 +624,8 @@ __global__ void __launch_bounds__(64) small_backward_kernel(const __grid_constan
             const T x0 = lam[i] / sk[i], x1 = kl[0][i] / sk[i];
             s0 += x0 * x0; s1 += x1 * x1;
         }
-        GPhase<T, P>::template for_each<1>(fac, B, 0, [&](int, const T (&av)[1], const T (&cv)[1]) {
-            const T x = (av[0] * cv[0]) / abstol; s1 += x * x;
+        for_each_g(std::integral_constant<int, 1>{}, [&](int, const T (&kv)[1]) {
+            const T x = kv[0] / abstol; s1 += x * x;
         });
         const double d0 = sqrt((double)s0 / NZ), d1 = sqrt((double)s1 / NZ);
         double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
@@ -509,8 +638,8 @@ __global__ void __launch_bounds__(64) small_backward_kernel(const __grid_constan
         T s2 = T(0);
 #pragma unroll
         for (int i = 0; i < I; ++i) { const T x = (f1[i] - kl[0][i]) / sk[i]; s2 += x * x; }
-        GPhase<T, P>::template for_each<2>(fac, B, 0, [&](int, const T (&av)[2], const T (&cv)[2]) {
-            const T x = (av[1] * cv[1] - av[0] * cv[0]) / abstol; s2 += x * x;
+        for_each_g(std::integral_constant<int, 2>{}, [&](int, const T (&kv)[2]) {
+            const T x = (kv[1] - kv[0]) / abstol; s2 += x * x;
         });
         const double d2 = sqrt((double)s2 / NZ) / dt0;
         const double mx = fmax(d1, d2);
@@ -526,12 +655,11 @@ __global__ void __launch_bounds__(64) small_backward_kernel(const __grid_constan
             if (!accept) dt = dt / fmin(1.0 / Ctrl::qmin, q11 / Ctrl::gamma);
             else {
                 dt = dtpropose;
-                if (modified) { adj_eval(t, lam, kl[0], 0); modified = false; }   // FSAL re-evaluation after a jump
-                else {
+                if (!modified) {                                   // FSAL: stage 7 of the last step is stage 1
 #pragma unroll
                     for (int i = 0; i < I; ++i) kl[0][i] = kl[6][i];
-#pragma unroll 1
-                    for (int f = 0; f < NF; ++f) fac[(int64_t)f * B] = fac[((int64_t)6 * NF + f) * B];
+#pragma unroll
+                    for (int f = 0; f < SR::N; ++f) sm[f * nthr] = sm[(6 * SR::N + f) * nthr];
                 }
             }
         }
@@ -542,13 +670,15 @@ __global__ void __launch_bounds__(64) small_backward_kernel(const __grid_constan
         if (iter > a.maxiters) { ret = RET_MAXITERS; break; }
         if (!(dt > dtmin_t) && (t - dt > tstop || !accept) && iter > 1) { ret = RET_DTMIN; break; }
         if (dt != dt) { ret = RET_UNSTABLE; break; }
-        // ---- perform_step! on lambda (registers); g stages exist only as factors ----
+        // ---- perform_step! on lambda (registers); g stages exist only as stage records ----
         const T h = (T)(-dt);
         T lnew[I];
 #pragma unroll
         for (int i = 0; i < I; ++i) lnew[i] = lprev[i];
+        // after a jump the FSAL stage is re-evaluated: that is stage 0 of the same loop (row 0 of the tableau is
+        // zero, c[0] = 0), so the hot loop contains exactly one copy of the fused forward+VJP code
 #pragma unroll 1
-        for (int s = 1; s < 7; ++s) {
+        for (int s = modified ? 0 : 1; s < 7; ++s) {
             T ls[I], ks[I];
 #pragma unroll
             for (int i = 0; i < I; ++i) {
@@ -559,7 +689,7 @@ __global__ void __launch_bounds__(64) small_backward_kernel(const __grid_constan
             }
             adj_eval(t - tab_c(s) * dt, ls, ks, s);
 #pragma unroll
-            for (int j = 1; j < 7; ++j)
+            for (int j = 0; j < 7; ++j)
                 if (j == s) {
 #pragma unroll
                     for (int i = 0; i < I; ++i) kl[j][i] = ks[i];
@@ -569,6 +699,7 @@ __global__ void __launch_bounds__(64) small_backward_kernel(const __grid_constan
                 for (int i = 0; i < I; ++i) lnew[i] = ls[i];
             }
         }
+        modified = false;
         // ---- error estimate over all I + NP components; g_new goes to the other buffer ----
         T es = T(0);
         bool bad = false;
@@ -583,28 +714,84 @@ __global__ void __launch_bounds__(64) small_backward_kernel(const __grid_constan
             es += r * r;
             bad |= (lnew[i] != lnew[i]);
         }
-        {
+        {   // step-end pass over the NP gradient components: g1 = g0 - h*sum_s b_s kv_s, error term with btilde.
+            // Per unit: prefetch its g values, recompute the unit's features for the 7 stages, accumulate, finalise.
             T wb[7], wbt[7];
 #pragma unroll
-            for (int s = 0; s < 7; ++s) { wb[s] = -Tab<T>::b(s); wbt[s] = -Tab<T>::bt(s); }   // k = -(a*c)
+            for (int s = 0; s < 7; ++s) { wb[s] = -h * Tab<T>::b(s); wbt[s] = -h * Tab<T>::bt(s); }   // dg/dt = -kv
             const T* gold = gbuf + (int64_t)cur * NP * B;
             T* gnew = gbuf + (int64_t)(cur ^ 1) * NP * B;
-            GPhase<T, P>::template for_each<7>(fac, B, 0, [&](int j, const T (&av)[7], const T (&cv)[7]) {
-                T vb = T(0), vt = T(0);
-#pragma unroll
-                for (int s = 0; s < 7; ++s) { const T kk = av[s] * cv[s]; vb += wb[s] * kk; vt += wbt[s] * kk; }
-                const T g0 = gold[(int64_t)j * B];
-                const T g1 = g0 + h * vb;
+            auto finalize = [&](int j, T g0, T vb, T vt) {
+                const T g1 = g0 + vb;
                 const T sc = abstol + kmax(kabs(g0), kabs(g1)) * reltol;
-                const T r = (h * vt) / sc;
+                const T r = kdiv(vt, sc);
                 es += r * r;
                 gnew[(int64_t)j * B] = g1;
-            });
+            };
+            // layer 2: unit = hidden unit i, outputs o < I, features q <= G (C2 rows then the W2 row)
+            {
+                T awb[7][I], awt[7][I];
+#pragma unroll
+                for (int s = 0; s < 7; ++s)
+#pragma unroll
+                    for (int o = 0; o < I; ++o) {
+                        const T l = sm[(s * SR::N + SR::LAM + o) * nthr];
+                        awb[s][o] = wb[s] * l; awt[s][o] = wbt[s] * l;
+                    }
+#pragma unroll 1
+                for (int i = 0; i < H; ++i) {
+                    T g0[G + 1][I], vb[G + 1][I], vt[G + 1][I];
+#pragma unroll
+                    for (int q = 0; q <= G; ++q)
+#pragma unroll
+                        for (int o = 0; o < I; ++o) {
+                            const int j = q < G ? P::OC2 + (i * G + q) * I + o : P::OW2 + i * I + o;
+                            g0[q][o] = gold[(int64_t)j * B]; vb[q][o] = T(0); vt[q][o] = T(0);
+                        }
+#pragma unroll
+                    for (int s = 0; s < 7; ++s) {
+                        T c[G + 1];
+                        unit_features<NORM>(prm, sm[(s * SR::N + SR::HH + i) * nthr], c);
+#pragma unroll
+                        for (int q = 0; q <= G; ++q)
+#pragma unroll
+                            for (int o = 0; o < I; ++o) { vb[q][o] += awb[s][o] * c[q]; vt[q][o] += awt[s][o] * c[q]; }
+                    }
+#pragma unroll
+                    for (int q = 0; q <= G; ++q)
+#pragma unroll
+                        for (int o = 0; o < I; ++o)
+                            finalize(q < G ? P::OC2 + (i * G + q) * I + o : P::OW2 + i * I + o, g0[q][o], vb[q][o], vt[q][o]);
+                }
+            }
+            // layer 1: unit = state component i, outputs o < H, features q <= G (C1 rows then the W1 row)
+#pragma unroll 1
+            for (int i = 0; i < I; ++i) {
+                T c[7][G + 1];
+#pragma unroll
+                for (int s = 0; s < 7; ++s) unit_features<NORM>(prm, sm[(s * SR::N + SR::Y + i) * nthr], c[s]);
+#pragma unroll 1
+                for (int o = 0; o < H; ++o) {
+                    T g0[G + 1], vb[G + 1], vt[G + 1];
+#pragma unroll
+                    for (int q = 0; q <= G; ++q) {
+                        const int j = q < G ? P::OC1 + (i * G + q) * H + o : P::OW1 + i * H + o;
+                        g0[q] = gold[(int64_t)j * B]; vb[q] = T(0); vt[q] = T(0);
+                    }
+#pragma unroll
+                    for (int s = 0; s < 7; ++s) {
+                        const T hb = sm[(s * SR::N + SR::HBAR + o) * nthr];
+                        const T ab = wb[s] * hb, at = wbt[s] * hb;
+#pragma unroll
+                        for (int q = 0; q <= G; ++q) { vb[q] += ab * c[s][q]; vt[q] += at * c[s][q]; }
+                    }
+#pragma unroll
+                    for (int q = 0; q <= G; ++q)
+                        finalize(q < G ? P::OC1 + (i * G + q) * H + o : P::OW1 + i * H + o, g0[q], vb[q], vt[q]);
+                }
+            }
         }
         const double EEst = (double)ksqrt(es / T(NZ));
-#ifdef KANODE_DEBUG
-        if (b == 0) printf("bwd iter %d t %g dt %g es %g EEst %g lnew %g %g kl0 %g kl6 %g abstol %g reltol %g\n", iter, t, dt, (double)es, EEst, (double)lnew[0], (double)lnew[1], (double)kl[0][0], (double)kl[6][0], (double)abstol, (double)reltol);
-#endif
         if (EEst != EEst || bad) { ret = RET_UNSTABLE; break; }
         const double q = pi_q(EEst, qold, q11);
         accept = EEst <= 1.0;
