@@ -52,8 +52,11 @@ bool small_match(const kanode_desc& d, SmallKey& k) {
 template <class T, class P> void fill_small(const kanode_handle* h, P& p) {
     for (int i = 0; i < P::NP; ++i) p.w[i] = (T)h->params[i];
     const kanode_layer_desc& s = h->desc.layers[0];
-    for (int g = 0; g < P::G; ++g) p.grid[g] = (T)grid_point(s, g);
-    p.inv_h = (T)(1.0f / s.denominator);                               // Float32 1/h (utils.jl:9)
+    const double inv_h = (double)(1.0f / s.denominator);               // Float32 1/h (utils.jl:9)
+    const double sc = KRbfScale<T>::value;
+    p.hs = (T)(inv_h * sc);
+    for (int g = 0; g < P::G; ++g) p.gs[g] = (T)((double)grid_point(s, g) * inv_h * sc);
+    p.dk = (T)(-2.0 * inv_h / sc);
 }
 
 // Visitor: calls fn.template operator()<P, NORM>() for the instantiation matching the descriptor.

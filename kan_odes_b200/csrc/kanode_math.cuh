@@ -71,14 +71,26 @@ __device__ __forceinline__ double kmax(double a, double b) { return fmax(a, b); 
 __device__ __forceinline__ float ksqrt(float a) { return sqrtf(a); }
 __device__ __forceinline__ double ksqrt(double a) { return sqrt(a); }
 
-// tanh: fp32 uses NNlib's tanh_fast(::Float32) rational (|rel err| ~ 5 eps); fp64 uses libdevice tanh
-// (the reference's Float64 tanh_fast is exp-based and agrees with tanh to ~2 eps).
+// ex2.approx: one MUFU, 2 ulp
+__device__ __forceinline__ float kex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// Gaussian RBF on a pre-scaled argument: exp(-a^2) with t = a*KRbfScale<T>.  fp32 folds sqrt(log2 e) into the
+// argument so the basis is FFMA + FMUL + MUFU.EX2; fp64 uses libdevice exp (scale 1).
+template <class T> struct KRbfScale;
+template <> struct KRbfScale<float> { static constexpr double value = 1.2011224087864498; };   // sqrt(log2(e))
+template <> struct KRbfScale<double> { static constexpr double value = 1.0; };
+__device__ __forceinline__ float krbf_scaled(float t) { return kex2(-t * t); }
+__device__ __forceinline__ double krbf_scaled(double t) { return exp(-t * t); }
+
+// tanh.  The reference's tanh_fast(::Float64) is exp-based ((e-1)/(e+1), e = exp(2x)); fp32 here uses the same form
+// with two MUFU ops, 1 - 2/(1+e): absolute error <= ~2e-7 (what matters: the result feeds (xn - grid)/h), never NaN
+// (e=inf -> 1, e=0 -> -1).  NNlib's Float32 rational tanh_fast (3e-7) costs 3x the instructions.  fp64: libdevice.
 __device__ __forceinline__ float ktanh(float x) {
-    const float x2 = x * x;
-    const float n = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 1.587199e-8f, 2.2332108e-5f), 0.0035974074f), 0.1346604f), 1.0f);
-    const float d = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 8.7767893e-7f, 0.0003453992f), 0.026262015f), 0.4679937f), 1.0f);
-    const float r = x * __fdividef(n, d);
-    return x2 < 66.0f ? r : copysignf(1.0f, x);
+    const float e = kex2(x * 2.8853900817779268f);                     // exp(2x)
+    return 1.0f - __fdividef(2.0f, 1.0f + e);
 }
 __device__ __forceinline__ double ktanh(double x) { return tanh(x); }
 

@@ -29,8 +29,9 @@ struct SmallParams {
     static constexpr int F_HBAR = 0, F_CA = H, QA = I * G + I, F_LAM = F_CA + QA, F_CB = F_LAM + I, QB = H * G + H,
                          NF = F_CB + QB;
     T w[NP];
-    T grid[G];
-    T inv_h;
+    T gs[G];      // grid[g] * hs
+    T hs;         // Float32(1/h) * KRbfScale<T>  : basis = krbf_scaled(xn*hs - gs[g])
+    T dk;         // d(basis)/d(xn) = dk * t * basis,  dk = -2*hs/KRbfScale^2   (utils.jl:18 times 1/h)
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -47,8 +48,7 @@ __device__ __forceinline__ void small_rhs(const P& p, const T (&u)[P::I], T (&du
         const T xn = normalize<NORM>(u[i]);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const T a = (xn - p.grid[g]) * p.inv_h;
-            const T y = kexp(-a * a);
+            const T y = krbf_scaled(xn * p.hs - p.gs[g]);
 #pragma unroll
             for (int o = 0; o < H; ++o) h[o] += p.w[P::OC1 + (i * G + g) * H + o] * y;
         }
@@ -63,8 +63,7 @@ __device__ __forceinline__ void small_rhs(const P& p, const T (&u)[P::I], T (&du
         const T xn = normalize<NORM>(h[i]);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const T a = (xn - p.grid[g]) * p.inv_h;
-            const T y = kexp(-a * a);
+            const T y = krbf_scaled(xn * p.hs - p.gs[g]);
 #pragma unroll
             for (int o = 0; o < I; ++o) du[o] += p.w[P::OC2 + (i * G + g) * I + o] * y;
         }
@@ -90,9 +89,9 @@ __device__ __forceinline__ void small_vjp(const P& p, const T (&y)[P::I], const 
         xn1[i] = normalize<NORM>(y[i]);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const T a = (xn1[i] - p.grid[g]) * p.inv_h;
-            const T b = kexp(-a * a);
-            db1[i * G + g] = T(-2) * a * b * p.inv_h;                    // utils.jl:18 times d(arg)/d(xn)
+            const T a = xn1[i] * p.hs - p.gs[g];
+            const T b = krbf_scaled(a);
+            db1[i * G + g] = p.dk * a * b;                               // utils.jl:18 times d(arg)/d(xn)
             st(P::F_CA + i * G + g, b);
 #pragma unroll
             for (int o = 0; o < H; ++o) h[o] += p.w[P::OC1 + (i * G + g) * H + o] * b;
@@ -109,13 +108,13 @@ __device__ __forceinline__ void small_vjp(const P& p, const T (&y)[P::I], const 
         T xnbar = T(0);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const T a = (xn - p.grid[g]) * p.inv_h;
-            const T b = kexp(-a * a);
+            const T a = xn * p.hs - p.gs[g];
+            const T b = krbf_scaled(a);
             st(P::F_CB + i * G + g, b);
             T bbar = T(0);
 #pragma unroll
             for (int o = 0; o < I; ++o) bbar += p.w[P::OC2 + (i * G + g) * I + o] * lam[o];
-            xnbar += (T(-2) * a * b * p.inv_h) * bbar;
+            xnbar += (p.dk * a * b) * bbar;
         }
         T s, ds; swish_both(h[i], s, ds);
         st(P::F_CB + H * G + i, s);
@@ -427,9 +426,9 @@ __device__ __forceinline__ void small_vjp_h(const P& p, const T (&y)[P::I], cons
         xn1[i] = normalize<NORM>(y[i]);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const T a = (xn1[i] - p.grid[g]) * p.inv_h;
-            const T b = kexp(-a * a);
-            db1[i * G + g] = T(-2) * a * b * p.inv_h;
+            const T a = xn1[i] * p.hs - p.gs[g];
+            const T b = krbf_scaled(a);
+            db1[i * G + g] = p.dk * a * b;
 #pragma unroll
             for (int o = 0; o < H; ++o) h[o] += p.w[P::OC1 + (i * G + g) * H + o] * b;
         }
@@ -443,12 +442,12 @@ __device__ __forceinline__ void small_vjp_h(const P& p, const T (&y)[P::I], cons
         T xnbar = T(0);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const T a = (xn - p.grid[g]) * p.inv_h;
-            const T b = kexp(-a * a);
+            const T a = xn * p.hs - p.gs[g];
+            const T b = krbf_scaled(a);
             T bbar = T(0);
 #pragma unroll
             for (int o = 0; o < I; ++o) bbar += p.w[P::OC2 + (i * G + g) * I + o] * lam[o];
-            xnbar += (T(-2) * a * b * p.inv_h) * bbar;
+            xnbar += (p.dk * a * b) * bbar;
         }
         T s, ds; swish_both(h[i], s, ds);
         T sbar = T(0);
@@ -478,7 +477,7 @@ template <int NORM, class T, class P>
 __device__ __forceinline__ void unit_features(const P& p, T x, T (&c)[P::G + 1]) {
     const T xn = normalize<NORM>(x);
 #pragma unroll
-    for (int g = 0; g < P::G; ++g) { const T a = (xn - p.grid[g]) * p.inv_h; c[g] = kexp(-a * a); }
+    for (int g = 0; g < P::G; ++g) c[g] = krbf_scaled(xn * p.hs - p.gs[g]);
     swish_fwd(x, c[P::G]);
 }
 
@@ -715,10 +714,8 @@ __global__ void __launch_bounds__(128, 2) small_backward_kernel(const __grid_con
             bad |= (lnew[i] != lnew[i]);
         }
         {   // step-end pass over the NP gradient components: g1 = g0 - h*sum_s b_s kv_s, error term with btilde.
-            // Per unit: prefetch its g values, recompute the unit's features for the 7 stages, accumulate, finalise.
-            T wb[7], wbt[7];
-#pragma unroll
-            for (int s = 0; s < 7; ++s) { wb[s] = -h * Tab<T>::b(s); wbt[s] = -h * Tab<T>::bt(s); }   // dg/dt = -kv
+            // Per unit: prefetch its g values, then a ROLLED loop over the 7 stages recomputes the unit's features
+            // from the stage record and accumulates (small code: the hot loop must stay inside the I-cache).
             const T* gold = gbuf + (int64_t)cur * NP * B;
             T* gnew = gbuf + (int64_t)(cur ^ 1) * NP * B;
             auto finalize = [&](int j, T g0, T vb, T vt) {
@@ -729,66 +726,68 @@ __global__ void __launch_bounds__(128, 2) small_backward_kernel(const __grid_con
                 gnew[(int64_t)j * B] = g1;
             };
             // layer 2: unit = hidden unit i, outputs o < I, features q <= G (C2 rows then the W2 row)
-            {
-                T awb[7][I], awt[7][I];
+#pragma unroll 1
+            for (int i = 0; i < H; ++i) {
+                T g0[G + 1][I], vb[G + 1][I], vt[G + 1][I];
 #pragma unroll
-                for (int s = 0; s < 7; ++s)
+                for (int q = 0; q <= G; ++q)
 #pragma unroll
                     for (int o = 0; o < I; ++o) {
-                        const T l = sm[(s * SR::N + SR::LAM + o) * nthr];
-                        awb[s][o] = wb[s] * l; awt[s][o] = wbt[s] * l;
+                        const int j = q < G ? P::OC2 + (i * G + q) * I + o : P::OW2 + i * I + o;
+                        g0[q][o] = gold[(int64_t)j * B]; vb[q][o] = T(0); vt[q][o] = T(0);
                     }
 #pragma unroll 1
-                for (int i = 0; i < H; ++i) {
-                    T g0[G + 1][I], vb[G + 1][I], vt[G + 1][I];
+                for (int s = 0; s < 7; ++s) {
+                    const T* rec = sm + s * SR::N * nthr;
+                    T c[G + 1];
+                    unit_features<NORM>(prm, rec[(SR::HH + i) * nthr], c);
+                    const T wb = -h * Tab<T>::b(s), wt = -h * Tab<T>::bt(s);       // dg/dt = -kv
 #pragma unroll
-                    for (int q = 0; q <= G; ++q)
+                    for (int o = 0; o < I; ++o) {
+                        const T l = rec[(SR::LAM + o) * nthr];
+                        const T ab = wb * l, at = wt * l;
 #pragma unroll
-                        for (int o = 0; o < I; ++o) {
-                            const int j = q < G ? P::OC2 + (i * G + q) * I + o : P::OW2 + i * I + o;
-                            g0[q][o] = gold[(int64_t)j * B]; vb[q][o] = T(0); vt[q][o] = T(0);
-                        }
-#pragma unroll
-                    for (int s = 0; s < 7; ++s) {
-                        T c[G + 1];
-                        unit_features<NORM>(prm, sm[(s * SR::N + SR::HH + i) * nthr], c);
-#pragma unroll
-                        for (int q = 0; q <= G; ++q)
-#pragma unroll
-                            for (int o = 0; o < I; ++o) { vb[q][o] += awb[s][o] * c[q]; vt[q][o] += awt[s][o] * c[q]; }
+                        for (int q = 0; q <= G; ++q) { vb[q][o] += ab * c[q]; vt[q][o] += at * c[q]; }
                     }
-#pragma unroll
-                    for (int q = 0; q <= G; ++q)
-#pragma unroll
-                        for (int o = 0; o < I; ++o)
-                            finalize(q < G ? P::OC2 + (i * G + q) * I + o : P::OW2 + i * I + o, g0[q][o], vb[q][o], vt[q][o]);
                 }
+#pragma unroll
+                for (int q = 0; q <= G; ++q)
+#pragma unroll
+                    for (int o = 0; o < I; ++o)
+                        finalize(q < G ? P::OC2 + (i * G + q) * I + o : P::OW2 + i * I + o, g0[q][o], vb[q][o], vt[q][o]);
             }
-            // layer 1: unit = state component i, outputs o < H, features q <= G (C1 rows then the W1 row)
+            // layer 1: unit = state component i, outputs o < H in chunks of OC, features q <= G (C1 rows, W1 row)
+            constexpr int OC = (H % 5 == 0) ? 5 : (H % 4 == 0 ? 4 : (H % 2 == 0 ? 2 : 1));
 #pragma unroll 1
-            for (int i = 0; i < I; ++i) {
-                T c[7][G + 1];
+            for (int io = 0; io < I * (H / OC); ++io) {
+                const int i = io / (H / OC), o0 = (io % (H / OC)) * OC;
+                T g0[G + 1][OC], vb[G + 1][OC], vt[G + 1][OC];
 #pragma unroll
-                for (int s = 0; s < 7; ++s) unit_features<NORM>(prm, sm[(s * SR::N + SR::Y + i) * nthr], c[s]);
+                for (int q = 0; q <= G; ++q)
+#pragma unroll
+                    for (int oo = 0; oo < OC; ++oo) {
+                        const int j = (q < G ? P::OC1 + (i * G + q) * H : P::OW1 + i * H) + o0 + oo;
+                        g0[q][oo] = gold[(int64_t)j * B]; vb[q][oo] = T(0); vt[q][oo] = T(0);
+                    }
 #pragma unroll 1
-                for (int o = 0; o < H; ++o) {
-                    T g0[G + 1], vb[G + 1], vt[G + 1];
+                for (int s = 0; s < 7; ++s) {
+                    const T* rec = sm + s * SR::N * nthr;
+                    T c[G + 1];
+                    unit_features<NORM>(prm, rec[(SR::Y + i) * nthr], c);
+                    const T wb = -h * Tab<T>::b(s), wt = -h * Tab<T>::bt(s);
 #pragma unroll
-                    for (int q = 0; q <= G; ++q) {
-                        const int j = q < G ? P::OC1 + (i * G + q) * H + o : P::OW1 + i * H + o;
-                        g0[q] = gold[(int64_t)j * B]; vb[q] = T(0); vt[q] = T(0);
+                    for (int oo = 0; oo < OC; ++oo) {
+                        const T hb = rec[(SR::HBAR + o0 + oo) * nthr];
+                        const T ab = wb * hb, at = wt * hb;
+#pragma unroll
+                        for (int q = 0; q <= G; ++q) { vb[q][oo] += ab * c[q]; vt[q][oo] += at * c[q]; }
                     }
-#pragma unroll
-                    for (int s = 0; s < 7; ++s) {
-                        const T hb = sm[(s * SR::N + SR::HBAR + o) * nthr];
-                        const T ab = wb[s] * hb, at = wbt[s] * hb;
-#pragma unroll
-                        for (int q = 0; q <= G; ++q) { vb[q] += ab * c[s][q]; vt[q] += at * c[s][q]; }
-                    }
-#pragma unroll
-                    for (int q = 0; q <= G; ++q)
-                        finalize(q < G ? P::OC1 + (i * G + q) * H + o : P::OW1 + i * H + o, g0[q], vb[q], vt[q]);
                 }
+#pragma unroll
+                for (int q = 0; q <= G; ++q)
+#pragma unroll
+                    for (int oo = 0; oo < OC; ++oo)
+                        finalize((q < G ? P::OC1 + (i * G + q) * H : P::OW1 + i * H) + o0 + oo, g0[q][oo], vb[q][oo], vt[q][oo]);
             }
         }
         const double EEst = (double)ksqrt(es / T(NZ));
