@@ -10,22 +10,22 @@
 #include "../../include/kanode.h"
 
 namespace kanode {
-// layer table for the generic kernels (device-friendly POD)
+// layer table for the generic (block-per-trajectory) kernels: device-friendly POD, passed as a kernel parameter
+constexpr int GEN_MAX_G = 32;
 struct GenericLayer {
     int I, O, G, norm, basis, use_base;
-    float grid_lo, grid_step_unused;
-    float inv_h;
-    long long offC, offW;     // offsets into the flat parameter vector
-    long long offGrid;        // offset into the grid table
+    float inv_h;               // Float32 1/h (utils.jl:9)
+    int goff;                  // offset of this layer's grid points in GenericModel::grid
+    long long offC, offW;      // offsets into the flat parameter vector
+    long long rx, ry;          // offsets of x_l (layer input) and ybar_l (output cotangent) in a backward stage record
 };
 struct GenericModel {
     int n_layers, rhs_kind, n;
     long long np;
     double lap_scale;          // lap_coef / dx^2
+    long long rec_len;         // length of one backward stage record
     GenericLayer L[KANODE_MAX_LAYERS];
-    float grid[KANODE_MAX_LAYERS * 64];   // Float32 LinRange points per layer (G <= 64)
-    int max_width;             // widest layer interface
-    long long nfac;            // factor floats per backward stage
+    float grid[KANODE_MAX_LAYERS * GEN_MAX_G];   // Float32 LinRange points per layer
 };
 }  // namespace kanode
 
@@ -52,7 +52,7 @@ struct kanode_handle {
     std::string err;
     // grow-only device workspace, keyed by purpose
     enum { W_U0, W_OUT, W_TARGET, W_STATS_F, W_STATS_B, W_SAVEAT, W_REC_T, W_REC, W_NSTEPS, W_RET, W_DG, W_FAC, W_G,
-           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_LAM, W_GEN, W_COUNT };
+           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_LAM, W_GEN, W_GEN2, W_COUNT };
     DevBuf ws[W_COUNT];
     kanode::GenericModel gm{};               // layer table for the generic kernels
 };

@@ -613,6 +613,8 @@ __global__ void __launch_bounds__(128, 2) small_backward_kernel(const __grid_con
         return mod;
     };
     apply_jumps(t1);                              // PresetTimeCallback fires at init when t_end is a save time
+#pragma unroll
+    for (int i = 0; i < I; ++i) lprev[i] = lam[i];
     adj_eval(t, lam, kl[0], 0);                   // FSAL
     double dt;                                    // |dt|; integration runs in -t
     {   // ---- initdt on the augmented state (g(T) = 0 so its scale is abstol) ----

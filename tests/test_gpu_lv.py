@@ -115,6 +115,20 @@ def test_single_trajectory_reference_config(lv_saveat):
     assert _relmax(grad, ref["grad"]) < 1e-8
 
 
+def test_save_time_at_both_ends_of_tspan(setup_lv):
+    """saveat containing t0 and T: the adjoint jump at T fires at initialisation (PresetTimeCallback), the one at
+    t0 after the last step (Allen-Cahn_Source.jl:97 uses saveat=dt, which includes both ends)."""
+    chain, p, u0, _ = setup_lv
+    sa = np.linspace(0.0, 3.5, 8)
+    tg = np.random.default_rng(5).uniform(0, 3, (6, 8, 2))
+    ref = Oracle(chain.desc(), np.float64).loss_grad(p, u0[:6], TSPAN, sa, tg)
+    node = K.NeuralODE(chain, TSPAN, K.Tsit5(), saveat=sa, dtype=np.float64)
+    loss, grad, info = node.loss_and_grad(u0[:6], p, tg)
+    assert (info["bwd_stats"].naccept == ref["bwd_stats"][:, 0]).all()
+    assert (info["bwd_stats"].nf == ref["bwd_stats"][:, 2]).all()
+    assert _relmax(grad, ref["grad"]) < 1e-8 and _relmax(info["du0"], ref["du0"]) < 1e-8
+
+
 def test_edge_cases(setup_lv, lv_saveat):
     chain, p, u0, tg = setup_lv
     node = K.NeuralODE(chain, TSPAN, K.Tsit5(), saveat=[3.5], dtype=np.float64)
