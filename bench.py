@@ -162,6 +162,7 @@ def run_ours(args):
 
     import kan_odes_b200 as K
     from kan_odes_b200 import abi
+    from kan_odes_b200.dist import combine_loss_grad
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -201,8 +202,7 @@ def run_ours(args):
                 d_fst.data_ptr() if with_stats else None, d_bst.data_ptr() if with_stats else None)
         abi.check(lib, ode.h, rc, "kanode_loss_grad_dev")
         if world > 1:                                              # the only collective: gradient + loss sums
-            dist.all_reduce(d_grad)
-            dist.all_reduce(d_loss)
+            combine_loss_grad(d_loss, d_grad, B, SAVEAT.size, 2)
 
     ms3 = (C.c_float * 3)()
     with torch.cuda.stream(stream):
