@@ -59,6 +59,31 @@ template <class T, class P> void fill_small(const kanode_handle* h, P& p) {
     p.dk = (T)(-2.0 * inv_h / sc);
 }
 
+// packed per-hidden-unit weights for the shared-memory kernels (layout: SmallParams::UW), uploaded on demand
+template <class T, class P> int upload_packed(kanode_handle* h, const T** out) {
+    std::vector<T> pk((size_t)P::WPK, T(0));
+    constexpr int I = P::I, H = P::H, G = P::G, NQ = P::NQ;
+    for (int j = 0; j < H; ++j) {
+        T* w = pk.data() + (size_t)j * P::UW;
+        for (int i = 0; i < I; ++i) {
+            for (int g = 0; g < G; ++g) w[i * G + g] = (T)h->params[P::OC1 + (i * G + g) * H + j];
+            w[I * G + i] = (T)h->params[P::OW1 + i * H + j];
+        }
+        for (int g = 0; g < G; ++g)
+            for (int o = 0; o < I; ++o) w[NQ + g * I + o] = (T)h->params[P::OC2 + (j * G + g) * I + o];
+        for (int o = 0; o < I; ++o) w[NQ + G * I + o] = (T)h->params[P::OW2 + j * I + o];
+    }
+    T* d = nullptr;
+    if (sizeof(T) == 4) ENSURE(h, W_WPK32, sizeof(T) * pk.size(), d); else ENSURE(h, W_WPK64, sizeof(T) * pk.size(), d);
+    if (h->wpk_version[sizeof(T) == 4 ? 0 : 1] != h->params_version) {
+        CK(h, cudaMemcpyAsync(d, pk.data(), sizeof(T) * pk.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));                       // pk is a stack-lifetime staging buffer
+        h->wpk_version[sizeof(T) == 4 ? 0 : 1] = h->params_version;
+    }
+    *out = d;
+    return 0;
+}
+
 // Visitor: calls fn.template operator()<P, NORM>() for the instantiation matching the descriptor.
 #define KANODE_SMALL_CASES(X) X(2, 10, 5, NORM_TANH)
 
@@ -134,6 +159,7 @@ int solve_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double t1, 
     auto run = [&]<class P, int NORM>() -> int {
         P prm; fill_small<T>(h, prm);
         SmallFwdArgs<T> a{};
+        if (int rcw = upload_packed<T, P>(h, &a.wpk)) return rcw;
         a.u0 = d_u0; a.B = B; a.t0 = t0; a.t1 = t1; a.saveat = d_saveat; a.nsave = nsave;
         a.abstol = (T)abstol; a.reltol = (T)reltol; a.maxiters = 100000; a.out = d_out; a.stats = d_stats;
         small_forward_kernel<T, P, NORM, false><<<blocks_for(B, 64), 64, 0, h->stream>>>(prm, a);
@@ -170,6 +196,7 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
         ENSURE(h, W_DG, sizeof(T) * (size_t)nsave * I * B, dg);
         ENSURE(h, W_G, sizeof(T) * (size_t)2 * P::NP * B, g);
         SmallFwdArgs<T> a{};
+        if (int rcw = upload_packed<T, P>(h, &a.wpk)) return rcw;
         a.u0 = d_u0; a.B = B; a.t0 = t0; a.t1 = t1; a.saveat = d_saveat; a.nsave = nsave;
         a.abstol = (T)abstol; a.reltol = (T)reltol; a.maxiters = 100000; a.out = d_out_opt; a.stats = d_fst;
         a.rec_t = rec_t; a.rec = rec; a.cap = cap; a.nsteps = nsteps; a.retcode = retc;
@@ -178,12 +205,12 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
         small_forward_kernel<T, P, NORM, true><<<blocks_for(B, 64), 64, 0, h->stream>>>(prm, a);
         cudaEventRecord(h->ev[1], h->stream);
         SmallBwdArgs<T> bw{};
-        bw.B = B; bw.t0 = t0; bw.t1 = t1; bw.saveat = d_saveat; bw.nsave = nsave;
+        bw.wpk = a.wpk; bw.B = B; bw.t0 = t0; bw.t1 = t1; bw.saveat = d_saveat; bw.nsave = nsave;
         bw.abstol = (T)abstol; bw.reltol = (T)reltol; bw.maxiters = 100000;
         bw.rec_t = rec_t; bw.rec = rec; bw.cap = cap; bw.nsteps = nsteps; bw.retcode = retc; bw.dg = dg;
         bw.fac = nullptr; bw.g = g; bw.du0 = d_du0; bw.stats = d_bst;
         constexpr int BT = 128;                                        // threads (= trajectories) per block
-        const size_t smem = sizeof(T) * 7 * StageRec<P>::N * BT;       // 7 stage records per trajectory
+        const size_t smem = sizeof(T) * (7 * StageRec<P>::N * BT + P::WPK) + 16;   // stage records + packed weights + mbarrier
         CK(h, cudaFuncSetAttribute(small_backward_kernel<T, P, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         small_backward_kernel<T, P, NORM><<<blocks_for(B, BT), BT, smem, h->stream>>>(prm, bw);
         cudaEventRecord(h->ev[2], h->stream);
@@ -205,6 +232,7 @@ template <class T> int set_params_host(kanode_handle* h, const T* p, size_t np) 
     if (!p || np != h->np) return fail(h, KANODE_ERR_INVALID, "expected %zu parameters, got %zu", h->np, np);
     for (size_t i = 0; i < np; ++i) h->params[i] = (double)p[i];
     h->have_params = true;
+    ++h->params_version;
     return generic_upload_params(h);
 }
 

@@ -45,6 +45,8 @@ struct kanode_handle {
     int n = 0;
     std::vector<double> params;      // host copy (drives the __grid_constant__ parameter blocks)
     bool have_params = false;
+    uint64_t params_version = 0;     // bumped by set_params; derived device copies are refreshed lazily
+    uint64_t wpk_version[2] = {~0ull, ~0ull};
     int rec_cap = 32;
     int64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fwd start / bwd start / reduce start / end
@@ -52,7 +54,7 @@ struct kanode_handle {
     std::string err;
     // grow-only device workspace, keyed by purpose
     enum { W_U0, W_OUT, W_TARGET, W_STATS_F, W_STATS_B, W_SAVEAT, W_REC_T, W_REC, W_NSTEPS, W_RET, W_DG, W_FAC, W_G,
-           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_LAM, W_GEN, W_GEN2, W_COUNT };
+           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_WPK32, W_WPK64, W_LAM, W_GEN, W_GEN2, W_COUNT };
     DevBuf ws[W_COUNT];
     kanode::GenericModel gm{};               // layer table for the generic kernels
 };

@@ -28,6 +28,9 @@ struct SmallParams {
     // rank-1 factor record of one backward stage: [hbar(H) | b1(I*G) sw1(I) | lam(I) | b2(H*G) sw2(H)]
     static constexpr int F_HBAR = 0, F_CA = H, QA = I * G + I, F_LAM = F_CA + QA, F_CB = F_LAM + I, QB = H * G + H,
                          NF = F_CB + QB;
+    // per-hidden-unit packed weights (shared-memory copy used by the hot kernels):
+    //   [C1[(i,g),o] (I*G) | W1[i,o] (I) | C2[(o,g),oo] (G*I, index g*I+oo) | W2[o,oo] (I)]
+    static constexpr int NQ = I * (G + 1), UW = ((2 * NQ + 3) / 4) * 4, WPK = UW * H;
     T w[NP];
     T gs[G];      // grid[g] * hs
     T hs;         // Float32(1/h) * KRbfScale<T>  : basis = krbf_scaled(xn*hs - gs[g])
@@ -143,9 +146,145 @@ __device__ __forceinline__ void small_vjp(const P& p, const T (&y)[P::I], const 
 }
 
 // ------------------------------------------------------------------------------------------------------
+// TMA (1-D bulk async copy) staging of the packed weights into shared memory + mbarrier completion
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// all threads of the block call this once; afterwards wsm holds the WPK packed weights
+template <class T, int WPK>
+__device__ __forceinline__ void stage_weights(T* wsm, uint64_t* bar, const T* __restrict__ wpk) {
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, (uint32_t)(sizeof(T) * WPK));
+        tma_load_1d(wsm, wpk, (uint32_t)(sizeof(T) * WPK), bar);
+    }
+    mbar_wait(bar, 0);
+}
+
+// features of the state components: f[i*G+g] = basis_g(norm(u_i)), f[I*G+i] = swish(u_i)  (layout of the packed C1|W1)
+template <int NORM, class T, class P>
+__device__ __forceinline__ void input_features(const P& p, const T (&u)[P::I], T (&f)[P::NQ]) {
+    constexpr int I = P::I, G = P::G;
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+        const T xn = normalize<NORM>(u[i]);
+#pragma unroll
+        for (int g = 0; g < G; ++g) f[i * G + g] = krbf_scaled(xn * p.hs - p.gs[g]);
+        swish_fwd(u[i], f[I * G + i]);
+    }
+}
+
+// KAN right-hand side with the weights in shared memory: one ROLLED loop over the hidden units (small code)
+template <int NORM, class T, class P>
+__device__ __forceinline__ void small_rhs_sm(const P& p, const T* __restrict__ wsm, const T (&u)[P::I], T (&du)[P::I]) {
+    constexpr int I = P::I, H = P::H, G = P::G, NQ = P::NQ;
+    T f[NQ];
+    input_features<NORM>(p, u, f);
+#pragma unroll
+    for (int o = 0; o < I; ++o) du[o] = T(0);
+#pragma unroll 1
+    for (int j = 0; j < H; ++j) {
+        const T* w = wsm + j * P::UW;
+        T h = T(0);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) h += w[q] * f[q];
+        const T xn = normalize<NORM>(h);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const T b = krbf_scaled(xn * p.hs - p.gs[g]);
+#pragma unroll
+            for (int o = 0; o < I; ++o) du[o] += w[NQ + g * I + o] * b;
+        }
+        T s; swish_fwd(h, s);
+#pragma unroll
+        for (int o = 0; o < I; ++o) du[o] += w[NQ + G * I + o] * s;
+    }
+}
+
+// fused forward-recompute + VJP with shared-memory weights; h_j and hbar_j go straight to the stage record
+// (rec = this thread's slot base, element f at rec[f*nthr])
+template <int NORM, class T, class P>
+__device__ __forceinline__ void small_vjp_sm(const P& p, const T* __restrict__ wsm, const T (&y)[P::I], const T (&lam)[P::I],
+                                             T (&ubar)[P::I], T* rec, int nthr, int off_h, int off_hbar) {
+    constexpr int I = P::I, H = P::H, G = P::G, NQ = P::NQ;
+    T f[NQ], df[NQ], bb[NQ];                  // features, their derivatives wrt the input, and sum_j w1[q][j]*hbar_j
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+        const T xn = normalize<NORM>(y[i]);
+        const T dn = normalize_deriv<NORM>(xn);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const T a = xn * p.hs - p.gs[g];
+            const T b = krbf_scaled(a);
+            f[i * G + g] = b;
+            df[i * G + g] = p.dk * a * b * dn;                           // utils.jl:18 * d(arg)/d(xn) * norm'
+        }
+        swish_both(y[i], f[I * G + i], df[I * G + i]);
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) bb[q] = T(0);
+#pragma unroll 1
+    for (int j = 0; j < H; ++j) {
+        const T* w = wsm + j * P::UW;
+        T wl[NQ];
+        T h = T(0);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) { wl[q] = w[q]; h += wl[q] * f[q]; }
+        const T xn = normalize<NORM>(h);
+        T xnbar = T(0);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const T a = xn * p.hs - p.gs[g];
+            const T b = krbf_scaled(a);
+            T bbar = T(0);
+#pragma unroll
+            for (int o = 0; o < I; ++o) bbar += w[NQ + g * I + o] * lam[o];
+            xnbar += (p.dk * a * b) * bbar;
+        }
+        T s, ds; swish_both(h, s, ds);
+        T sbar = T(0);
+#pragma unroll
+        for (int o = 0; o < I; ++o) sbar += w[NQ + G * I + o] * lam[o];
+        const T hb = xnbar * normalize_deriv<NORM>(xn) + sbar * ds;
+        rec[(off_h + j) * nthr] = h;
+        rec[(off_hbar + j) * nthr] = hb;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) bb[q] += wl[q] * hb;
+    }
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+        T xb = bb[I * G + i] * df[I * G + i];
+#pragma unroll
+        for (int g = 0; g < G; ++g) xb += bb[i * G + g] * df[i * G + g];
+        ubar[i] = xb;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // argument blocks
 // ------------------------------------------------------------------------------------------------------
 template <class T> struct SmallFwdArgs {
+    const T* wpk;           // packed per-unit weights (global), staged to smem by TMA
     const T* u0;            // [B][I]
     int64_t B;
     double t0, t1;
@@ -168,6 +307,7 @@ template <class T> struct SmallFwdArgs {
 };
 
 template <class T> struct SmallBwdArgs {
+    const T* wpk;           // packed per-unit weights (global), staged to smem by TMA
     int64_t B;
     double t0, t1;
     const double* saveat;
@@ -189,6 +329,9 @@ template <class T> struct SmallBwdArgs {
 template <class T, class P, int NORM, bool DENSE>
 __global__ void __launch_bounds__(64) small_forward_kernel(const __grid_constant__ P prm, const SmallFwdArgs<T> a) {
     constexpr int I = P::I;
+    __shared__ __align__(16) T wsm[P::WPK];
+    __shared__ uint64_t wbar;
+    stage_weights<T, P::WPK>(wsm, &wbar, a.wpk);
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = b < a.B;
     double lsum = 0.0;
@@ -203,7 +346,7 @@ __global__ void __launch_bounds__(64) small_forward_kernel(const __grid_constant
         for (int j = 1; j < 7; ++j)
 #pragma unroll
             for (int i = 0; i < I; ++i) k[j][i] = T(0);
-        small_rhs<NORM>(prm, u, k[0]);
+        small_rhs_sm<NORM>(prm, wsm, u, k[0]);
         int nf = 1, naccept = 0, nreject = 0, ret = RET_SUCCESS;
         const double t0 = a.t0, t1 = a.t1, dtmax = fabs(t1 - t0);
         const double dtmin0 = fmax(eps_of(t0), eps_of(t1));
@@ -222,7 +365,7 @@ __global__ void __launch_bounds__(64) small_forward_kernel(const __grid_constant
             dt0 = fmin(dt0, dtmax);
 #pragma unroll
             for (int i = 0; i < I; ++i) u1[i] = u[i] + (T)dt0 * k[0][i];
-            small_rhs<NORM>(prm, u1, f1);
+            small_rhs_sm<NORM>(prm, wsm, u1, f1);
             nf += 2;
             T s2 = T(0);
 #pragma unroll
@@ -267,7 +410,7 @@ __global__ void __launch_bounds__(64) small_forward_kernel(const __grid_constant
                     for (int j = 0; j < 6; ++j) acc += Tab<T>::a(s, j) * k[j][i];
                     us[i] = uprev[i] + h * acc;
                 }
-                small_rhs<NORM>(prm, us, ks);
+                small_rhs_sm<NORM>(prm, wsm, us, ks);
 #pragma unroll
                 for (int j = 1; j < 7; ++j)
                     if (j == s) {
@@ -488,6 +631,9 @@ __global__ void __launch_bounds__(128, 2) small_backward_kernel(const __grid_con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* sm = reinterpret_cast<T*>(smem_raw) + threadIdx.x;          // element (slot, f) at sm[(slot*SR::N + f)*nthr]
     const int nthr = blockDim.x;
+    T* wsm = reinterpret_cast<T*>(smem_raw) + 7 * SR::N * nthr;    // packed weights behind the stage records
+    uint64_t* wbar = reinterpret_cast<uint64_t*>(wsm + P::WPK);
+    stage_weights<T, P::WPK>(wsm, wbar, a.wpk);
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
     const int64_t B = a.B;
@@ -541,14 +687,12 @@ __global__ void __launch_bounds__(128, 2) small_backward_kernel(const __grid_con
     };
     // one adjoint RHS evaluation at (t, l): dl = -(df/du)^T l; stage record -> shared-memory slot
     auto adj_eval = [&](double t, const T (&l)[I], T (&dl)[I], int slot) {
-        T y[I], ub[I], hh[H], hb[H];
+        T y[I], ub[I];
         eval_y(t, y);
-        small_vjp_h<NORM>(prm, y, l, ub, hh, hb);
         T* s = sm + slot * SR::N * nthr;
+        small_vjp_sm<NORM>(prm, wsm, y, l, ub, s, nthr, SR::HH, SR::HBAR);
 #pragma unroll
         for (int i = 0; i < I; ++i) { s[(SR::Y + i) * nthr] = y[i]; s[(SR::LAM + i) * nthr] = l[i]; dl[i] = -ub[i]; }
-#pragma unroll
-        for (int o = 0; o < H; ++o) { s[(SR::HH + o) * nthr] = hh[o]; s[(SR::HBAR + o) * nthr] = hb[o]; }
         ++nf;
     };
     // Visit every parameter-gradient component of the NS stage slots: fn(j, kv[NS]) with kv[s] = (df/dp)^T lam
