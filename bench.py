@@ -153,7 +153,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "trajectories/s", "cores": cores, "kind": "port",
                              "sample": "8192 trajectories per step, fp64 C++ oracle (OpenMP); Julia absent"},
             "e2e": {"value": val, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -316,12 +316,28 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(chain, p, u0, tg)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter) was sent to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)          # keep stdout for the JSON line only
+    os.dup2(2, 1)                     # native-library prints to fd 1 (e.g. "NCCL version ...") go to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -209,7 +209,7 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
         bw.abstol = (T)abstol; bw.reltol = (T)reltol; bw.maxiters = 100000;
         bw.rec_t = rec_t; bw.rec = rec; bw.cap = cap; bw.nsteps = nsteps; bw.retcode = retc; bw.dg = dg;
         bw.fac = nullptr; bw.g = g; bw.du0 = d_du0; bw.stats = d_bst;
-        constexpr int BT = 128;                                        // threads (= trajectories) per block
+        constexpr int BT = KANODE_BWD_BT;                              // threads (= trajectories) per block
         const size_t smem = sizeof(T) * (7 * StageRec<P>::N * BT + P::WPK) + 16;   // stage records + packed weights + mbarrier
         CK(h, cudaFuncSetAttribute(small_backward_kernel<T, P, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         small_backward_kernel<T, P, NORM><<<blocks_for(B, BT), BT, smem, h->stream>>>(prm, bw);

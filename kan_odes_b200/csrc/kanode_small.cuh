@@ -19,6 +19,19 @@
 
 #include "kanode_math.cuh"
 
+// tuning knobs (defaults chosen from B200 measurements, see profiles/)
+#ifndef KANODE_UNROLL_J
+#define KANODE_UNROLL_J 2      // hidden units processed per iteration of the rolled unit loops
+#endif
+#ifndef KANODE_BWD_BT
+#define KANODE_BWD_BT 64       // trajectories (threads) per block of the backward kernel
+#endif
+#ifndef KANODE_BWD_MINB
+#define KANODE_BWD_MINB 4      // resident blocks per SM the backward kernel is compiled for
+#endif
+#define KANODE_PRAGMA(x) _Pragma(#x)
+#define KANODE_UNROLL(n) KANODE_PRAGMA(unroll n)
+
 namespace kanode {
 
 template <class T, int I_, int H_, int G_>
@@ -202,7 +215,7 @@ __device__ __forceinline__ void small_rhs_sm(const P& p, const T* __restrict__ w
     input_features<NORM>(p, u, f);
 #pragma unroll
     for (int o = 0; o < I; ++o) du[o] = T(0);
-#pragma unroll 1
+    KANODE_UNROLL(KANODE_UNROLL_J)
     for (int j = 0; j < H; ++j) {
         const T* w = wsm + j * P::UW;
         T h = T(0);
@@ -243,7 +256,7 @@ __device__ __forceinline__ void small_vjp_sm(const P& p, const T* __restrict__ w
     }
 #pragma unroll
     for (int q = 0; q < NQ; ++q) bb[q] = T(0);
-#pragma unroll 1
+    KANODE_UNROLL(KANODE_UNROLL_J)
     for (int j = 0; j < H; ++j) {
         const T* w = wsm + j * P::UW;
         T wl[NQ];
@@ -625,7 +638,7 @@ __device__ __forceinline__ void unit_features(const P& p, T x, T (&c)[P::G + 1])
 }
 
 template <class T, class P, int NORM>
-__global__ void __launch_bounds__(128, 2) small_backward_kernel(const __grid_constant__ P prm, const SmallBwdArgs<T> a) {
+__global__ void __launch_bounds__(KANODE_BWD_BT, KANODE_BWD_MINB) small_backward_kernel(const __grid_constant__ P prm, const SmallBwdArgs<T> a) {
     constexpr int I = P::I, H = P::H, G = P::G, NP = P::NP, NZ = I + NP, RS = 1 + 8 * I;
     using SR = StageRec<P>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
