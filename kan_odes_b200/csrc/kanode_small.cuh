@@ -29,6 +29,9 @@
 #ifndef KANODE_BWD_MINB
 #define KANODE_BWD_MINB 4      // resident blocks per SM the backward kernel is compiled for
 #endif
+#ifndef KANODE_UNROLL_S
+#define KANODE_UNROLL_S 1      // stages per iteration of the rolled stage loops of the step-end gradient pass
+#endif
 #define KANODE_PRAGMA(x) _Pragma(#x)
 #define KANODE_UNROLL(n) KANODE_PRAGMA(unroll n)
 
@@ -895,7 +898,7 @@ __global__ void __launch_bounds__(KANODE_BWD_BT, KANODE_BWD_MINB) small_backward
                         const int j = q < G ? P::OC2 + (i * G + q) * I + o : P::OW2 + i * I + o;
                         g0[q][o] = gold[(int64_t)j * B]; vb[q][o] = T(0); vt[q][o] = T(0);
                     }
-#pragma unroll 1
+                KANODE_UNROLL(KANODE_UNROLL_S)
                 for (int s = 0; s < 7; ++s) {
                     const T* rec = sm + s * SR::N * nthr;
                     T c[G + 1];
@@ -928,7 +931,7 @@ __global__ void __launch_bounds__(KANODE_BWD_BT, KANODE_BWD_MINB) small_backward
                         const int j = (q < G ? P::OC1 + (i * G + q) * H : P::OW1 + i * H) + o0 + oo;
                         g0[q][oo] = gold[(int64_t)j * B]; vb[q][oo] = T(0); vt[q][oo] = T(0);
                     }
-#pragma unroll 1
+                KANODE_UNROLL(KANODE_UNROLL_S)
                 for (int s = 0; s < 7; ++s) {
                     const T* rec = sm + s * SR::N * nthr;
                     T c[G + 1];

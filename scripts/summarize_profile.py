@@ -30,21 +30,35 @@ for r in rows[2:]:
     lines.append("")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 srows = list(csv.reader(src.splitlines()))
-if len(srows) > 3:
-    h = srows[1]; data = srows[2:]
+sections, cur = [], None
+for r in srows:
+    if r and r[0] == "Kernel Name":
+        cur = {"name": r[1], "hdr": None, "data": []}; sections.append(cur)
+    elif cur is not None and cur["hdr"] is None:
+        cur["hdr"] = r
+    elif cur is not None and len(r) == len(cur["hdr"]):
+        cur["data"].append(r)
+for sec in sections:
+    h, data = sec["hdr"], sec["data"]
     ix = {k: i for i, k in enumerate(h)}
-    f = lambda r, k: float(r[ix[k]]) if r[ix[k]] not in ("", None) else 0.0
-    tot = sum(f(r, "Instructions Executed") for r in data)
+
+    def f(r, k):
+        try:
+            return float(r[ix[k]])
+        except (ValueError, IndexError):
+            return 0.0
+    tot = sum(f(r, "Instructions Executed") for r in data) or 1.0
     ops = collections.Counter()
     for r in data:
         m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[ix["Source"]])
         ops[m.group(2).split(".")[0] if m else "?"] += f(r, "Instructions Executed")
-    lines += [f"## SASS: {len(data)} instructions, {tot:.4g} warp-instructions executed", "opcode mix: " +
-              ", ".join(f"{k} {v / tot * 100:.1f}%" for k, v in ops.most_common(12))]
+    lines += [f"## SASS of {sec['name'][:90]}: {len(data)} instructions, {tot:.4g} warp-instructions executed",
+              "opcode mix: " + ", ".join(f"{k} {v / tot * 100:.1f}%" for k, v in ops.most_common(12))]
     stalls = [k for k in h if k.startswith("stall_") and "Not Issued" not in k]
-    st = collections.Counter({s: sum(f(r, s) for r in data) for s in stalls})
+    st = collections.Counter({s_: sum(f(r, s_) for r in data) for s_ in stalls})
     ts = sum(st.values()) or 1
     lines.append("stall samples: " + ", ".join(f"{k[6:]} {v / ts * 100:.1f}%" for k, v in st.most_common(8)))
+    lines.append("")
 (out / f"{tag}_ncu_summary.md").write_text("\n".join(lines) + "\n")
 if launches:
     r = list(csv.reader(l for l in open(launches) if not l.startswith("==")))

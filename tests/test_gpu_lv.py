@@ -147,3 +147,36 @@ def test_edge_cases(setup_lv, lv_saveat):
     r = ode.loss_grad(u0[:5], TSPAN, lv_saveat, tg[:5])
     ref = Oracle(chain.desc()).loss_grad(p, u0[:5], TSPAN, lv_saveat, tg[:5])
     assert _relmax(r["grad"], ref["grad"]) < 1e-8
+
+
+def test_full_size_ensemble_properties(lv_saveat):
+    """BASELINE configs[1] at full size (65,536 trajectories, fp32): size-independent properties.
+    (a) trajectories are independent: a permuted batch gives the permuted outputs bit for bit;
+    (b) sharding: per-shard unnormalised sums add up to the full-batch result (what the multi-GPU path relies on);
+    (c) a random sample of trajectories agrees with the fp64 oracle within solver accuracy;
+    (d) duplicated initial conditions give identical trajectories and step counts."""
+    chain = lv_chain()
+    p = glorot_params(chain, seed=0)
+    B = 65536
+    rng = np.random.default_rng(1234)
+    u0 = rng.uniform(0.5, 2.0, (B, 2)).astype(np.float32)
+    u0[B // 2:B // 2 + 64] = u0[:64]                                   # (d) duplicates
+    tg = rng.uniform(0.0, 3.0, (B, 35, 2)).astype(np.float32)
+    ode = K.KanOde(chain, dtype=np.float32); ode.set_params(p)
+    sol = ode.solve(u0, TSPAN, lv_saveat)
+    assert (sol.stats.retcode == 0).all() and np.isfinite(sol.array).all()
+    assert np.array_equal(sol.array[:64], sol.array[B // 2:B // 2 + 64])
+    assert np.array_equal(sol.stats.naccept[:64], sol.stats.naccept[B // 2:B // 2 + 64])
+    perm = rng.permutation(B)
+    sol_p = ode.solve(u0[perm], TSPAN, lv_saveat)
+    assert np.array_equal(sol_p.array, sol.array[perm])                 # (a)
+    full = ode.loss_grad(u0, TSPAN, lv_saveat, tg)
+    halves = [ode.loss_grad(u0[s], TSPAN, lv_saveat, tg[s]) for s in (slice(0, 40000), slice(40000, B))]
+    g = (halves[0]["grad"].astype(np.float64) * 40000 + halves[1]["grad"].astype(np.float64) * (B - 40000)) / B
+    l = (halves[0]["loss"] * 40000 + halves[1]["loss"] * (B - 40000)) / B
+    assert _relmax(g, full["grad"].astype(np.float64)) < 2e-6 and abs(l - full["loss"]) < 2e-6 * full["loss"]   # (b)
+    idx = rng.choice(B, 256, replace=False)
+    ref = Oracle(chain.desc(), np.float64).loss_grad(p, u0[idx], TSPAN, lv_saveat, tg[idx], want_out=True)
+    assert _relmax(sol.array[idx], ref["out"]) < 5e-3                    # (c)
+    sub = ode.loss_grad(u0[idx], TSPAN, lv_saveat, tg[idx])
+    assert _relmax(sub["grad"], ref["grad"]) < 5e-3 and _relmax(sub["du0"], ref["du0"]) < 2e-2

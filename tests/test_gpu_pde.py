@@ -151,3 +151,65 @@ def test_burgers_1024_batch_runs_and_matches_oracle_fp64():
     ref = Oracle(chain.desc(), np.float64).loss_grad(p, u0, (0.0, 1.0), saveat, tg)
     assert (r["bwd_stats"].naccept == ref["bwd_stats"][:, 0]).all()
     assert _relmax(r["grad"], ref["grad"]) < 1e-8
+
+
+def test_allen_cahn_surrogate_4096_wide_layer_fp64():
+    """BASELINE configs[3] shape: [4096,10,4096] G=10 (the 'wide layer'), one IC, fp64 parity with the oracle."""
+    n = 4096
+    chain = surrogate_chain(n, 10, 10)
+    p = glorot_params(chain, seed=1)
+    x = np.linspace(-1, 1, n)
+    u0 = (x**2 * np.cos(np.pi * x))[None, :]
+    saveat = np.array([0.1, 0.3, 0.5, 0.7, 0.9])
+    tg = u0[:, None, :] * (1 - 0.5 * saveat)[None, :, None]
+    ode = K.KanOde(chain, dtype=np.float64); ode.set_params(p)
+    r = ode.loss_grad(u0, (0.0, 1.0), saveat, tg)
+    ref = Oracle(chain.desc(), np.float64).loss_grad(p, u0, (0.0, 1.0), saveat, tg)
+    assert (r["fwd_stats"].naccept == ref["fwd_stats"][:, 0]).all()
+    assert (r["bwd_stats"].naccept == ref["bwd_stats"][:, 0]).all() and (r["bwd_stats"].nf == ref["bwd_stats"][:, 2]).all()
+    assert abs(r["loss"] - ref["loss"]) < 1e-9 * abs(ref["loss"])
+    assert _relmax(r["grad"], ref["grad"]) < 1e-7
+
+
+def test_schrodinger_16384_fp64():
+    """BASELINE configs[4] shape: [32768,10,32768] G=10 (Re/Im split on a 16,384-point grid), one IC, fp64 parity."""
+    n = 32768
+    chain = surrogate_chain(n, 10, 10)
+    p = glorot_params(chain, seed=2)
+    x = np.linspace(-5, 5, 16384)
+    u0 = np.concatenate([2 / np.cosh(x), np.zeros_like(x)])[None, :]
+    saveat = np.array([0.1, 0.3, 0.5, 0.7, 0.9, 1.1, 1.3, 1.5])
+    tg = u0[:, None, :] * np.cos(saveat)[None, :, None]
+    ode = K.KanOde(chain, dtype=np.float64); ode.set_params(p)
+    r = ode.loss_grad(u0, (0.0, np.pi / 2), saveat, tg)
+    ref = Oracle(chain.desc(), np.float64).loss_grad(p, u0, (0.0, np.pi / 2), saveat, tg)
+    assert (r["fwd_stats"].naccept == ref["fwd_stats"][:, 0]).all()
+    assert (r["bwd_stats"].naccept == ref["bwd_stats"][:, 0]).all()
+    assert abs(r["loss"] - ref["loss"]) < 1e-9 * abs(ref["loss"])
+    assert _relmax(r["grad"], ref["grad"]) < 1e-7
+
+
+def test_hidden_source_4096_fp64():
+    """BASELINE configs[3] hidden-source shape at N=4096 (periodic Laplacian + 1->1 KAN).  The Allen-Cahn script's sign
+    (-1e-4*lap, Allen-Cahn_Source.jl:92) is anti-diffusive and blows up at dx=2/4095 (growth rate 4*419/s), so the
+    stable Fisher-KPP sign (+D*lap, Fisher-KPP_Source.jl:97) is used with D/dx^2 = 419."""
+    n = 4096
+    chain = source_chain(10)
+    kw = dict(rhs_kind=abi.RHS_SOURCE_LAPLACIAN, n_state=n, lap_coef=1e-4, dx=2.0 / (n - 1))
+    p = glorot_params(chain, seed=3)
+    x = np.linspace(-1, 1, n)
+    u0 = (x**2 * np.cos(np.pi * x))[None, :]
+    saveat = np.linspace(0, 0.2, 21)
+    tg = u0[:, None, :] * np.exp(0.5 * saveat)[None, :, None]
+    ode = K.KanOde(chain, kw["rhs_kind"], n, kw["lap_coef"], kw["dx"], dtype=np.float64); ode.set_params(p)
+    r = ode.loss_grad(u0, (0.0, 0.2), saveat, tg)
+    ref = Oracle(chain.desc(**kw), np.float64).loss_grad(p, u0, (0.0, 0.2), saveat, tg)
+    assert (r["fwd_stats"].naccept == ref["fwd_stats"][:, 0]).all() and (r["fwd_stats"].retcode == 0).all()
+    assert (r["bwd_stats"].naccept == ref["bwd_stats"][:, 0]).all()
+    assert _relmax(r["grad"], ref["grad"]) < 1e-7
+    # the reference's anti-diffusive sign at this resolution: both sides report the blow-up instead of a number
+    bad = dict(kw, lap_coef=-1e-4)
+    ode2 = K.KanOde(chain, bad["rhs_kind"], n, bad["lap_coef"], bad["dx"], dtype=np.float64); ode2.set_params(p)
+    sol = ode2.solve(u0, (0.0, 1.0), [1.0])
+    _, st = Oracle(chain.desc(**bad), np.float64).solve(p, u0, (0.0, 1.0), [1.0])
+    assert sol.stats.retcode[0] != 0 and st[0, 3] != 0
