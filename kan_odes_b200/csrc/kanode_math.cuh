@@ -88,9 +88,14 @@ __device__ __forceinline__ double krbf_scaled(double t) { return exp(-t * t); }
 // tanh.  The reference's tanh_fast(::Float64) is exp-based ((e-1)/(e+1), e = exp(2x)); fp32 here uses the same form
 // with two MUFU ops, 1 - 2/(1+e): absolute error <= ~2e-7 (what matters: the result feeds (xn - grid)/h), never NaN
 // (e=inf -> 1, e=0 -> -1).  NNlib's Float32 rational tanh_fast (3e-7) costs 3x the instructions.  fp64: libdevice.
+__device__ __forceinline__ float krcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float ktanh(float x) {
     const float e = kex2(x * 2.8853900817779268f);                     // exp(2x)
-    return 1.0f - __fdividef(2.0f, 1.0f + e);
+    return fmaf(-2.0f, krcp(1.0f + e), 1.0f);
 }
 __device__ __forceinline__ double ktanh(double x) { return tanh(x); }
 
@@ -98,6 +103,12 @@ template <class T> __device__ __forceinline__ T ksigmoid(T x) {
     const T t = kexp(-kabs(x));
     const T r = kdiv(T(1), T(1) + t);
     return x >= T(0) ? r : t * r;
+}
+// fp32: exp(-|x|) as one ex2.approx.ftz (no denormal fix-up code) and one rcp.approx
+template <> __device__ __forceinline__ float ksigmoid<float>(float x) {
+    const float t = kex2(-1.4426950408889634f * fabsf(x));
+    const float r = krcp(1.0f + t);
+    return x >= 0.0f ? r : t * r;
 }
 
 template <int NORM, class T> __device__ __forceinline__ T normalize(T x) {

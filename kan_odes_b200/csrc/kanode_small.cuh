@@ -880,10 +880,11 @@ __global__ void __launch_bounds__(KANODE_BWD_BT, KANODE_BWD_MINB) small_backward
             // from the stage record and accumulates (small code: the hot loop must stay inside the I-cache).
             const T* gold = gbuf + (int64_t)cur * NP * B;
             T* gnew = gbuf + (int64_t)(cur ^ 1) * NP * B;
+            const T mh = -h;                                               // dg/dt = -kv
             auto finalize = [&](int j, T g0, T vb, T vt) {
-                const T g1 = g0 + vb;
+                const T g1 = g0 + mh * vb;
                 const T sc = abstol + kmax(kabs(g0), kabs(g1)) * reltol;
-                const T r = kdiv(vt, sc);
+                const T r = kdiv(mh * vt, sc);
                 es += r * r;
                 gnew[(int64_t)j * B] = g1;
             };
@@ -903,7 +904,7 @@ __global__ void __launch_bounds__(KANODE_BWD_BT, KANODE_BWD_MINB) small_backward
                     const T* rec = sm + s * SR::N * nthr;
                     T c[G + 1];
                     unit_features<NORM>(prm, rec[(SR::HH + i) * nthr], c);
-                    const T wb = -h * Tab<T>::b(s), wt = -h * Tab<T>::bt(s);       // dg/dt = -kv
+                    const T wb = Tab<T>::b(s), wt = Tab<T>::bt(s);
 #pragma unroll
                     for (int o = 0; o < I; ++o) {
                         const T l = rec[(SR::LAM + o) * nthr];
@@ -936,7 +937,7 @@ __global__ void __launch_bounds__(KANODE_BWD_BT, KANODE_BWD_MINB) small_backward
                     const T* rec = sm + s * SR::N * nthr;
                     T c[G + 1];
                     unit_features<NORM>(prm, rec[(SR::Y + i) * nthr], c);
-                    const T wb = -h * Tab<T>::b(s), wt = -h * Tab<T>::bt(s);
+                    const T wb = Tab<T>::b(s), wt = Tab<T>::bt(s);
 #pragma unroll
                     for (int oo = 0; oo < OC; ++oo) {
                         const T hb = rec[(SR::HBAR + o0 + oo) * nthr];
