@@ -202,6 +202,14 @@ int kanode_loss_grad_dev_f64(kanode_handle* h, const double* d_u0, int64_t batch
                              double* d_loss_sum, double* d_grad_sum, double* d_du0,
                              kanode_stats* d_fwd_stats, kanode_stats* d_bwd_stats);
 
+/* Flux.Adam(eta, (beta1, beta2), eps) + update!(opt, p, grad)  (LV_driver_KANODE.jl:219,287; [EXT Flux 0.14.22]):
+ *   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g^2;  p -= eta * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps),  g = grad_scale*d_grad.
+ * All pointers are device pointers of np floats; t is the 1-based iteration count.  grad_scale lets a data-parallel
+ * caller pass the all-reduced gradient SUM and divide by the global trajectory count in the same kernel.
+ * The handle's parameters are NOT changed: call kanode_set_params_dev(h, d_p, np) afterwards. */
+int kanode_adam_step_dev(kanode_handle* h, float* d_p, const float* d_grad, float* d_m, float* d_v, int64_t t,
+                         float eta, float beta1, float beta2, float eps, float grad_scale);
+
 /* dense-record capacity (accepted forward steps kept per trajectory for the adjoint).  Host entry points grow
  * it automatically on overflow; *_dev entry points report KANODE_RET_RECORD_OVERFLOW in the stats instead. */
 int kanode_set_record_capacity(kanode_handle* h, int32_t max_steps);

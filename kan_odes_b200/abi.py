@@ -59,7 +59,7 @@ EXPORTED_SYMBOLS = (
     "kanode_vjp", "kanode_solve", "kanode_solve_dev", "kanode_loss_grad", "kanode_loss_grad_dev",
     "kanode_launch_count", "kanode_set_record_capacity",
     "kanode_set_params_f64", "kanode_rhs_f64", "kanode_vjp_f64", "kanode_solve_f64", "kanode_loss_grad_f64",
-    "kanode_loss_grad_dev_f64", "kanode_last_timing",
+    "kanode_loss_grad_dev_f64", "kanode_last_timing", "kanode_adam_step_dev",
 )
 
 _lib = None
@@ -105,6 +105,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lg64 = [vp, vp, i64, C.c_double, C.c_double, vp, C.c_int32, vp, C.c_double, C.c_double, vp, vp, vp, vp, vp]
     lib.kanode_loss_grad_dev_f64.argtypes = lg64
     lib.kanode_loss_grad_dev_f64.restype = C.c_int
+    lib.kanode_adam_step_dev.argtypes = [vp, vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]
+    lib.kanode_adam_step_dev.restype = C.c_int
     lib.kanode_last_timing.argtypes = [vp, vp]
     lib.kanode_last_timing.restype = C.c_int
     lib.kanode_launch_count.restype = C.c_int64

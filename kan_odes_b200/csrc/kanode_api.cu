@@ -100,6 +100,18 @@ template <class T, class Fn> bool small_dispatch(const kanode_handle* h, Fn&& fn
     return false;
 }
 
+__global__ void __launch_bounds__(256) adam_update_kernel(float* __restrict__ p, const float* __restrict__ grad, float* __restrict__ m,
+                                                          float* __restrict__ v, size_t n, float eta, float b1, float b2,
+                                                          float eps, float c1, float c2, float gs) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float g = gs * grad[i];
+    const float mi = b1 * m[i] + (1.0f - b1) * g;
+    const float vi = b2 * v[i] + (1.0f - b2) * g * g;
+    m[i] = mi; v[i] = vi;
+    p[i] -= eta * (mi * c1) / (sqrtf(vi * c2) + eps);
+}
+
 inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -396,6 +408,19 @@ int kanode_set_record_capacity(kanode_handle* h, int32_t max_steps) {
 }
 
 int64_t kanode_launch_count(const kanode_handle* h) { return h ? h->launches : 0; }
+
+int kanode_adam_step_dev(kanode_handle* h, float* d_p, const float* d_grad, float* d_m, float* d_v, int64_t t, float eta,
+                         float beta1, float beta2, float eps, float grad_scale) {
+    if (int rc = enter(h)) return rc;
+    if (!d_p || !d_grad || !d_m || !d_v || t < 1) return fail(h, KANODE_ERR_INVALID, "bad arguments");
+    const float c1 = (float)(1.0 / (1.0 - std::pow((double)beta1, (double)t)));
+    const float c2 = (float)(1.0 / (1.0 - std::pow((double)beta2, (double)t)));
+    adam_update_kernel<<<blocks_for((int64_t)h->np, 256), 256, 0, h->stream>>>(d_p, d_grad, d_m, d_v, h->np, eta, beta1, beta2, eps,
+                                                                                c1, c2, grad_scale);
+    ++h->launches;
+    CK(h, cudaGetLastError());
+    return 0;
+}
 
 int kanode_last_timing(kanode_handle* h, float* ms3) {
     if (int rc = enter(h)) return rc;

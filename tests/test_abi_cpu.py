@@ -74,3 +74,17 @@ def test_flat_parameter_layout_roundtrip():
     assert np.array_equal(back["layer_1"]["C"][:, :5], ps["layer_1"]["C"][:, :5])
     assert np.allclose(st["layer_1"]["grid"], [-1, -0.5, 0, 0.5, 1])
     assert chain.layers[0].denominator == 0.5 and chain.layers[0].statelength() == 5
+
+
+def test_adam_matches_flux_formula():
+    """[EXT Flux 0.14.22] Adam: m,v moments with bias correction."""
+    rng = np.random.default_rng(0)
+    p = rng.normal(size=7); g1, g2 = rng.normal(size=7), rng.normal(size=7)
+    opt = K.Adam(5e-4)
+    q = p.copy()
+    opt.update(q, g1); opt.update(q, g2)
+    m = 0.1 * g1; v = 0.001 * g1**2
+    ref = p - 5e-4 * (m / (1 - 0.9)) / (np.sqrt(v / (1 - 0.999)) + 1e-8)
+    m = 0.9 * m + 0.1 * g2; v = 0.999 * v + 0.001 * g2**2
+    ref = ref - 5e-4 * (m / (1 - 0.9**2)) / (np.sqrt(v / (1 - 0.999**2)) + 1e-8)
+    assert np.allclose(q, ref, rtol=1e-13)
