@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -13,6 +14,7 @@
 
 #include "kanode_host.h"
 #include "kanode_small.cuh"
+#include "kanode_small_ls.cuh"
 #include "kanode_generic.cuh"
 
 using namespace kanode;
@@ -221,15 +223,92 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
         bw.abstol = (T)abstol; bw.reltol = (T)reltol; bw.maxiters = 100000;
         bw.rec_t = rec_t; bw.rec = rec; bw.cap = cap; bw.nsteps = nsteps; bw.retcode = retc; bw.dg = dg;
         bw.fac = nullptr; bw.g = g; bw.du0 = d_du0; bw.stats = d_bst;
-        constexpr int BT = KANODE_BWD_BT;                              // threads (= trajectories) per block
-        const size_t smem = sizeof(T) * (7 * StageRec<P>::N * BT + P::WPK) + 16;   // stage records + packed weights + mbarrier
-        CK(h, cudaFuncSetAttribute(small_backward_kernel<T, P, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        small_backward_kernel<T, P, NORM><<<blocks_for(B, BT), BT, smem, h->stream>>>(prm, bw);
-        cudaEventRecord(h->ev[2], h->stream);
-        reduce_rows_kernel<T, T><<<P::NP, 256, 0, h->stream>>>(g, B, d_grad_sum, 1.0);
-        cudaEventRecord(h->ev[3], h->stream);
+        if (const char* e = std::getenv("KANODE_BWD_MAXIT")) bw.maxiters = std::atoi(e);   // timing experiments only
+        // the lockstep engine is opt-in (KANODE_LOCKSTEP=1): measured slower than the monolithic kernel on B200 because its
+        // stage records and per-trajectory state round-trip through L2/HBM every step
+        const bool lockstep = h->lockstep > 0 && (int64_t)B * 7 * StageRec<P>::N < (1ll << 31);
+        if (!lockstep) {
+            // launch order from the previous call's per-trajectory step counts (same batch size, same dtype)
+            int *att = nullptr, *order = nullptr;
+            const int slot = sizeof(T) == 4 ? 0 : 1;
+            if (h->schedule && B >= 4096) {
+                ENSURE(h, W_ATT, sizeof(int) * (size_t)B * 2, att);
+                ENSURE(h, W_ORDER, sizeof(int) * (size_t)B * 2, order);
+                att += (size_t)slot * B; order += (size_t)slot * B;
+                if (h->order_B[slot] == B) { build_order_kernel<<<1, 1024, 0, h->stream>>>(att, B, order); bw.order = order; ++h->launches; }
+                bw.attempts = att;
+                h->order_B[slot] = B;
+            }
+            constexpr int BT = KANODE_BWD_BT;                              // threads (= trajectories) per block
+            const size_t smem = sizeof(T) * (7 * StageRec<P>::N * BT + P::WPK) + 16;   // stage records + packed weights + mbarrier
+            constexpr size_t kExclusiveSmem = 200 * 1024;                  // a block asking for this much owns its SM
+            CK(h, cudaFuncSetAttribute(small_backward_kernel<T, P, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExclusiveSmem));
+            int64_t n_long = 0;
+            if (bw.order) {
+                // The first kLongSlots launch positions hold the trajectories predicted to need the most steps.  They run
+                // as one-warp blocks that each own an SM (exclusive shared-memory request), so their serial chain of steps
+                // proceeds at lone-warp latency while the other SMs chew through the bulk, which is launched on a second
+                // stream right behind them (the long blocks must be resident before the bulk fills the machine).
+                constexpr int kLongBT = 32;
+                int kLongSlots = 256;
+                if (const char* e = std::getenv("KANODE_LONG_SLOTS")) kLongSlots = std::atoi(e);   // tuning experiments
+                n_long = B < kLongSlots ? B : kLongSlots;
+                CK(h, cudaEventRecord(h->aux_ev[0], h->stream));
+                SmallBwdArgs<T> lg = bw; lg.gid0 = 0; lg.gidn = n_long;
+                small_backward_kernel<T, P, NORM><<<blocks_for(n_long, kLongBT), kLongBT, kExclusiveSmem, h->stream>>>(prm, lg);
+                ++h->launches;
+            }
+            bw.gid0 = n_long; bw.gidn = B - n_long;
+            if (bw.gidn > 0) {
+                cudaStream_t bulk = n_long > 0 ? h->aux_stream : h->stream;
+                if (n_long > 0) CK(h, cudaStreamWaitEvent(bulk, h->aux_ev[0], 0));
+                small_backward_kernel<T, P, NORM><<<blocks_for(bw.gidn, BT), BT, smem, bulk>>>(prm, bw);
+                if (n_long > 0) { CK(h, cudaEventRecord(h->aux_ev[1], bulk)); CK(h, cudaStreamWaitEvent(h->stream, h->aux_ev[1], 0)); }
+            }
+            cudaEventRecord(h->ev[2], h->stream);
+            reduce_rows_kernel<T, T><<<P::NP, 256, 0, h->stream>>>(g, B, d_grad_sum, 1.0);
+            cudaEventRecord(h->ev[3], h->stream);
+            h->launches += 3;
+        } else {
+            // lockstep engine: one (stage kernel, gradient-pass kernel) pair per step attempt of all trajectories
+            constexpr int NITEM = LsItems<P>::NITEM;
+            const size_t nd = 5, ni = 9, nT = (size_t)(3 * I + 7 * I + 1 + NITEM + 7 * StageRec<P>::N);
+            const size_t bytes = sizeof(double) * nd * B + sizeof(int) * (ni * B + 4) + sizeof(T) * nT * B + 64;
+            char* base = nullptr;
+            ENSURE(h, W_LS, bytes, base);
+            LsState<T> st{};
+            double* pd = reinterpret_cast<double*>(base);
+            st.t = pd; st.dt = pd + B; st.dtpropose = pd + 2 * B; st.qold = pd + 3 * B; st.q11 = pd + 4 * B;
+            T* pt = reinterpret_cast<T*>(pd + nd * B);
+            st.lam = pt; pt += (size_t)I * B; st.lprev = pt; pt += (size_t)I * B; st.lnew = pt; pt += (size_t)I * B;
+            st.kl = pt; pt += (size_t)7 * I * B; st.es_l = pt; pt += B; st.es_part = pt; pt += (size_t)NITEM * B;
+            st.rec = pt; pt += (size_t)7 * StageRec<P>::N * B;
+            int* pi = reinterpret_cast<int*>(pt);
+            st.iter = pi; st.sp = pi + B; st.cur = pi + 2 * B; st.naccept = pi + 3 * B; st.nreject = pi + 4 * B;
+            st.nf = pi + 5 * B; st.ret = pi + 6 * B; st.flags = pi + 7 * B; st.ridx = pi + 8 * B; st.active = pi + 9 * B;
+            CK(h, cudaMemsetAsync(st.active, 0, sizeof(int), h->stream));
+            const unsigned nb = blocks_for(B, 128);
+            ls_init_kernel<T, P, NORM><<<nb, 128, 0, h->stream>>>(prm, bw, st);
+            int launches = 4, active = 1, iters = 0;
+            int chunk = nsave + 8;                                         // every save time is a tstop: >= nsave attempts
+            const char* cap_env = std::getenv("KANODE_LS_MAXIT");      // timing experiments only
+            const int it_cap = cap_env ? std::atoi(cap_env) : bw.maxiters + 8;
+            while (active > 0 && iters < it_cap) {
+                for (int k = 0; k < chunk; ++k) {
+                    ls_step_kernel<T, P, NORM><<<blocks_for(B, KANODE_LS_BT), KANODE_LS_BT, 0, h->stream>>>(prm, bw, st);
+                    ls_gphase_kernel<T, P, NORM><<<dim3(nb, NITEM), 128, 0, h->stream>>>(prm, bw, st);
+                }
+                iters += chunk; launches += 2 * chunk;
+                CK(h, cudaMemcpyAsync(&active, st.active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+                CK(h, cudaStreamSynchronize(h->stream));
+                chunk = 4;
+            }
+            cudaEventRecord(h->ev[2], h->stream);
+            ls_reduce_kernel<T><<<P::NP, 256, 0, h->stream>>>(g, st.cur, st.ret, P::NP, B, d_grad_sum);
+            cudaEventRecord(h->ev[3], h->stream);
+            h->launches += launches;
+        }
         h->ev_valid = true;
-        h->launches += 3;
         CK(h, cudaGetLastError());
         return 0;
     };
@@ -371,11 +450,18 @@ int kanode_create(const kanode_desc* desc, int device, void* stream, kanode_hand
     if (!h) return fail(nullptr, KANODE_ERR_NOMEM, "out of host memory");
     h->desc = *desc; h->device = device; h->np = np; h->n = desc->n_state;
     h->params.assign(np, 0.0);
+    if (const char* e = std::getenv("KANODE_LOCKSTEP")) h->lockstep = std::atoi(e);
+    if (const char* e = std::getenv("KANODE_SCHEDULE")) h->schedule = std::atoi(e);
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, KANODE_ERR_CUDA, "cudaSetDevice failed"); }
     if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
     else {
         if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, KANODE_ERR_CUDA, "cudaStreamCreate failed"); }
         h->own_stream = true;
+    }
+    if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->aux_ev[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->aux_ev[1], cudaEventDisableTiming) != cudaSuccess) {
+        kanode_destroy(h); return fail(nullptr, KANODE_ERR_CUDA, "aux stream/event creation failed");
     }
     for (auto& e : h->ev)
         if (cudaEventCreate(&e) != cudaSuccess) { kanode_destroy(h); return fail(nullptr, KANODE_ERR_CUDA, "cudaEventCreate failed"); }
@@ -390,6 +476,8 @@ int kanode_destroy(kanode_handle* h) {
     cudaStreamSynchronize(h->stream);
     for (auto& b : h->ws) if (b.p) cudaFree(b.p);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : h->aux_ev) if (e) cudaEventDestroy(e);
+    if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;

@@ -48,13 +48,18 @@ struct kanode_handle {
     uint64_t params_version = 0;     // bumped by set_params; derived device copies are refreshed lazily
     uint64_t wpk_version[2] = {~0ull, ~0ull};
     int rec_cap = 32;
+    int64_t order_B[2] = {0, 0};     // batch size the cached launch order (per dtype) was built for; 0 = none
+    int schedule = 1;                // 1: reuse last call's step counts to launch long backward solves first
+    int lockstep = -1;               // backward engine for the small path: -1 auto (by batch), 0 monolithic, 1 lockstep
     int64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fwd start / bwd start / reduce start / end
+    cudaStream_t aux_stream = nullptr;                           // concurrent launch of the predicted-long trajectories
+    cudaEvent_t aux_ev[2] = {nullptr, nullptr};
     bool ev_valid = false;
     std::string err;
     // grow-only device workspace, keyed by purpose
     enum { W_U0, W_OUT, W_TARGET, W_STATS_F, W_STATS_B, W_SAVEAT, W_REC_T, W_REC, W_NSTEPS, W_RET, W_DG, W_FAC, W_G,
-           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_WPK32, W_WPK64, W_LAM, W_GEN, W_GEN2, W_COUNT };
+           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_WPK32, W_WPK64, W_LAM, W_GEN, W_GEN2, W_LS, W_ATT, W_ORDER, W_COUNT };
     DevBuf ws[W_COUNT];
     kanode::GenericModel gm{};               // layer table for the generic kernels
 };
