@@ -228,42 +228,56 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
         // stage records and per-trajectory state round-trip through L2/HBM every step
         const bool lockstep = h->lockstep > 0 && (int64_t)B * 7 * StageRec<P>::N < (1ll << 31);
         if (!lockstep) {
-            // launch order from the previous call's per-trajectory step counts (same batch size, same dtype)
-            int *att = nullptr, *order = nullptr;
-            const int slot = sizeof(T) == 4 ? 0 : 1;
-            if (h->schedule && B >= 4096) {
-                ENSURE(h, W_ATT, sizeof(int) * (size_t)B * 2, att);
-                ENSURE(h, W_ORDER, sizeof(int) * (size_t)B * 2, order);
-                att += (size_t)slot * B; order += (size_t)slot * B;
-                if (h->order_B[slot] == B) { build_order_kernel<<<1, 1024, 0, h->stream>>>(att, B, order); bw.order = order; ++h->launches; }
-                bw.attempts = att;
-                h->order_B[slot] = B;
-            }
+            // Scheduling from the previous call's per-trajectory step counts (same batch size, same dtype): the
+            // trajectories predicted to need the most steps run as one-warp blocks that each own an SM (exclusive
+            // shared-memory request), so their serial chain of steps proceeds at lone-warp latency while the other SMs
+            // chew through the bulk, which is launched on a second stream right behind them.
             constexpr int BT = KANODE_BWD_BT;                              // threads (= trajectories) per block
+            constexpr int kLongBT = 32;
+            int kLongSlots = 256;
+            if (const char* e = std::getenv("KANODE_LONG_SLOTS")) kLongSlots = std::atoi(e);   // tuning experiments
             const size_t smem = sizeof(T) * (7 * StageRec<P>::N * BT + P::WPK) + 16;   // stage records + packed weights + mbarrier
             constexpr size_t kExclusiveSmem = 200 * 1024;                  // a block asking for this much owns its SM
             CK(h, cudaFuncSetAttribute(small_backward_kernel<T, P, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExclusiveSmem));
-            int64_t n_long = 0;
-            if (bw.order) {
-                // The first kLongSlots launch positions hold the trajectories predicted to need the most steps.  They run
-                // as one-warp blocks that each own an SM (exclusive shared-memory request), so their serial chain of steps
-                // proceeds at lone-warp latency while the other SMs chew through the bulk, which is launched on a second
-                // stream right behind them (the long blocks must be resident before the bulk fills the machine).
-                constexpr int kLongBT = 32;
-                int kLongSlots = 256;
-                if (const char* e = std::getenv("KANODE_LONG_SLOTS")) kLongSlots = std::atoi(e);   // tuning experiments
-                n_long = B < kLongSlots ? B : kLongSlots;
-                CK(h, cudaEventRecord(h->aux_ev[0], h->stream));
-                SmallBwdArgs<T> lg = bw; lg.gid0 = 0; lg.gidn = n_long;
-                small_backward_kernel<T, P, NORM><<<blocks_for(n_long, kLongBT), kLongBT, kExclusiveSmem, h->stream>>>(prm, lg);
-                ++h->launches;
+            const int slot = sizeof(T) == 4 ? 0 : 1;
+            bool have_long = false;
+            if (h->schedule && B >= 4096 && kLongSlots > 0) {
+                // W_ATT: [2 dtypes][ attempts[B] ], W_ORDER: [2 dtypes][ sched (4 x u64) | long_list[cap] | flag[B] ]
+                int* att = nullptr; char* ob = nullptr;
+                const size_t per = 64 + sizeof(int) * (size_t)kLongSlots + (size_t)B;
+                ENSURE(h, W_ATT, sizeof(int) * (size_t)B * 2, att);
+                ENSURE(h, W_ORDER, 2 * ((per + 63) / 64 * 64), ob);
+                att += (size_t)slot * B; ob += (size_t)slot * ((per + 63) / 64 * 64);
+                unsigned long long* sched = reinterpret_cast<unsigned long long*>(ob);     // [0] prev sum, [1] running sum
+                int* long_count = reinterpret_cast<int*>(sched + 2);
+                int* long_list = reinterpret_cast<int*>(ob + 64);
+                unsigned char* long_flag = reinterpret_cast<unsigned char*>(long_list + kLongSlots);
+                if (h->order_B[slot] == B) {
+                    CK(h, cudaMemcpyAsync(&sched[0], &sched[1], sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
+                    CK(h, cudaMemsetAsync(&sched[1], 0, sizeof(unsigned long long) + sizeof(int), h->stream));   // running sum, long_count
+                    mark_long_kernel<<<blocks_for(B, 256), 256, 0, h->stream>>>(att, B, &sched[0], long_count, kLongSlots, long_list, long_flag);
+                    clamp_count_kernel<<<1, 1, 0, h->stream>>>(long_count, kLongSlots);
+                    h->launches += 2;
+                    have_long = true;
+                    CK(h, cudaEventRecord(h->aux_ev[0], h->stream));
+                    SmallBwdArgs<T> lg = bw;
+                    lg.long_list = long_list; lg.long_count = long_count; lg.gidn = kLongSlots;
+                    lg.attempts = att; lg.attempts_sum = &sched[1];
+                    small_backward_kernel<T, P, NORM><<<blocks_for(kLongSlots, kLongBT), kLongBT, kExclusiveSmem, h->stream>>>(prm, lg);
+                    ++h->launches;
+                    bw.long_flag = long_flag;
+                } else {
+                    CK(h, cudaMemsetAsync(ob, 0, 64, h->stream));
+                }
+                bw.attempts = att; bw.attempts_sum = &sched[1];
+                h->order_B[slot] = B;
             }
-            bw.gid0 = n_long; bw.gidn = B - n_long;
-            if (bw.gidn > 0) {
-                cudaStream_t bulk = n_long > 0 ? h->aux_stream : h->stream;
-                if (n_long > 0) CK(h, cudaStreamWaitEvent(bulk, h->aux_ev[0], 0));
-                small_backward_kernel<T, P, NORM><<<blocks_for(bw.gidn, BT), BT, smem, bulk>>>(prm, bw);
-                if (n_long > 0) { CK(h, cudaEventRecord(h->aux_ev[1], bulk)); CK(h, cudaStreamWaitEvent(h->stream, h->aux_ev[1], 0)); }
+            bw.gidn = B;
+            {
+                cudaStream_t bulk = have_long ? h->aux_stream : h->stream;
+                if (have_long) CK(h, cudaStreamWaitEvent(bulk, h->aux_ev[0], 0));
+                small_backward_kernel<T, P, NORM><<<blocks_for(B, BT), BT, smem, bulk>>>(prm, bw);
+                if (have_long) { CK(h, cudaEventRecord(h->aux_ev[1], bulk)); CK(h, cudaStreamWaitEvent(h->stream, h->aux_ev[1], 0)); }
             }
             cudaEventRecord(h->ev[2], h->stream);
             reduce_rows_kernel<T, T><<<P::NP, 256, 0, h->stream>>>(g, B, d_grad_sum, 1.0);

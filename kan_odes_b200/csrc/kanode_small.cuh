@@ -336,9 +336,13 @@ template <class T> struct SmallBwdArgs {
     T* g;                   // [2][NP][B]  double-buffered gradient state; result ends in buffer 0
     T* du0;                 // [B][I] or null
     kanode_stats* stats;    // [B] or null
-    const int* order;       // launch position -> trajectory (long solves first), or null for identity
-    int* attempts;          // [B] step attempts of this backward solve (feeds the next call's order), or null
-    int64_t gid0, gidn;     // this launch covers launch positions [gid0, gid0 + gidn)
+    // scheduling (optional): trajectories predicted to be long are listed in long_list and run in a separate launch
+    const int* long_list;   // launch of the long ones: position -> trajectory; null in the bulk launch
+    const int* long_count;  // device scalar: entries of long_list (clamped to the launch size by the kernel)
+    const unsigned char* long_flag;   // bulk launch: [B] 1 = handled by the long launch (skip), or null
+    int* attempts;          // [B] step attempts of this backward solve (feeds the next call's prediction), or null
+    unsigned long long* attempts_sum; // device scalar accumulating sum of attempts, or null
+    int64_t gidn;           // launch positions of this launch
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -653,9 +657,13 @@ __global__ void __launch_bounds__(KANODE_BWD_BT, KANODE_BWD_MINB) small_backward
     T* wsm = reinterpret_cast<T*>(smem_raw) + 7 * SR::N * nthr;    // packed weights behind the stage records
     uint64_t* wbar = reinterpret_cast<uint64_t*>(wsm + P::WPK);
     stage_weights<T, P::WPK>(wsm, wbar, a.wpk);
-    const int64_t gid = a.gid0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= a.gid0 + a.gidn) return;
-    const int64_t b = a.order ? (int64_t)a.order[gid] : gid;      // trajectories predicted to be long run first
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= a.gidn) return;
+    int64_t b = gid;
+    if (a.long_list) {                                            // launch of the predicted-long trajectories
+        if (gid >= *a.long_count) return;
+        b = a.long_list[gid];
+    } else if (a.long_flag && a.long_flag[b]) return;             // bulk launch: that one runs in the long launch
     const int64_t B = a.B;
     T* gbuf = a.g + b;           // element (buf, j) at gbuf[(buf*NP + j)*B]
 #pragma unroll 1
@@ -992,41 +1000,30 @@ __global__ void __launch_bounds__(KANODE_BWD_BT, KANODE_BWD_MINB) small_backward
 #pragma unroll
         for (int i = 0; i < I; ++i) a.du0[b * I + i] = lam[i];
     if (a.stats) a.stats[b] = kanode_stats{naccept, nreject, nf, ret};
-    if (a.attempts) a.attempts[b] = naccept + nreject;
+    if (a.attempts) {
+        a.attempts[b] = naccept + nreject;
+        if (a.attempts_sum) atomicAdd(a.attempts_sum, (unsigned long long)(naccept + nreject));
+    }
 }
 
-// Launch order for the NEXT backward solve from the attempts of the last one (training steps repeat with slowly
-// changing parameters, so the same trajectories are the long ones): trajectories with more than mean+4 attempts go
-// first, everything else keeps its index order (coalescing).  One block; deterministic.
-__global__ void __launch_bounds__(1024) build_order_kernel(const int* __restrict__ attempts, int64_t B, int* __restrict__ order) {
-    __shared__ long long s_sum;
-    __shared__ int s_cnt[1024];
-    __shared__ int s_total;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int64_t per = (B + nt - 1) / nt, lo = tid * per, hi = lo + per < B ? lo + per : B;
-    if (tid == 0) s_sum = 0;
-    __syncthreads();
-    long long sum = 0;
-    for (int64_t i = lo; i < hi; ++i) sum += attempts[i];
-    atomicAdd((unsigned long long*)&s_sum, (unsigned long long)sum);
-    __syncthreads();
-    const int thr = (int)(s_sum / (B > 0 ? B : 1)) + 4;
-    int cnt = 0;
-    for (int64_t i = lo; i < hi; ++i) cnt += attempts[i] > thr;
-    s_cnt[tid] = cnt;
-    __syncthreads();
-    if (tid == 0) {                                   // exclusive scan over 1024 per-thread counts
-        int run = 0;
-        for (int k = 0; k < nt; ++k) { const int c = s_cnt[k]; s_cnt[k] = run; run += c; }
-        s_total = run;
+// Prediction for the NEXT backward solve from the step attempts of the last one (training steps repeat with slowly
+// changing parameters, so the same trajectories are the long ones): a trajectory with more than mean+4 attempts is
+// appended to long_list (up to `cap` of them) and flagged so that the bulk launch skips it.
+// sched[0] = sum of attempts of the previous call, sched[1] = entries in long_list (may exceed cap; clamp when used).
+__global__ void __launch_bounds__(256) mark_long_kernel(const int* __restrict__ attempts, int64_t B, const unsigned long long* sched_sum,
+                                                        int* long_count, int cap, int* __restrict__ long_list,
+                                                        unsigned char* __restrict__ long_flag) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int thr = (int)(*sched_sum / (unsigned long long)B) + 4;
+    unsigned char f = 0;
+    if (attempts[b] > thr) {
+        const int slot = atomicAdd(long_count, 1);
+        if (slot < cap) { long_list[slot] = (int)b; f = 1; }
     }
-    __syncthreads();
-    int pl = s_cnt[tid];                              // next slot among the long trajectories
-    int64_t ps = s_total + (lo - s_cnt[tid]);         // next slot among the others (index order kept)
-    for (int64_t i = lo; i < hi; ++i) {
-        if (attempts[i] > thr) order[pl++] = (int)i; else order[ps++] = (int)i;
-    }
+    long_flag[b] = f;
 }
+__global__ void clamp_count_kernel(int* c, int cap) { if (*c > cap) *c = cap; }
 
 // ------------------------------------------------------------------------------------------------------
 // batch RHS / VJP (kanode_rhs, kanode_vjp)
