@@ -229,16 +229,14 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
         const bool lockstep = h->lockstep > 0 && (int64_t)B * 7 * StageRec<P>::N < (1ll << 31);
         if (!lockstep) {
             // Scheduling from the previous call's per-trajectory step counts (same batch size, same dtype): the
-            // trajectories predicted to need the most steps run as one-warp blocks that each own an SM (exclusive
-            // shared-memory request), so their serial chain of steps proceeds at lone-warp latency while the other SMs
-            // chew through the bulk, which is launched on a second stream right behind them.
+            // trajectories predicted to need the most steps get a warp each (small_backward_warp_kernel: the step-end
+            // gradient pass is spread over the lanes), launched ahead of the bulk, which follows on a second stream.
+            // Their serial chain of steps then finishes well inside the bulk's run time instead of bounding the launch.
             constexpr int BT = KANODE_BWD_BT;                              // threads (= trajectories) per block
-            constexpr int kLongBT = 32;
             int kLongSlots = 256;
             if (const char* e = std::getenv("KANODE_LONG_SLOTS")) kLongSlots = std::atoi(e);   // tuning experiments
             const size_t smem = sizeof(T) * (7 * StageRec<P>::N * BT + P::WPK) + 16;   // stage records + packed weights + mbarrier
-            constexpr size_t kExclusiveSmem = 200 * 1024;                  // a block asking for this much owns its SM
-            CK(h, cudaFuncSetAttribute(small_backward_kernel<T, P, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExclusiveSmem));
+            CK(h, cudaFuncSetAttribute(small_backward_kernel<T, P, NORM, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const int slot = sizeof(T) == 4 ? 0 : 1;
             bool have_long = false;
             if (h->schedule && B >= 4096 && kLongSlots > 0) {
@@ -263,7 +261,13 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
                     SmallBwdArgs<T> lg = bw;
                     lg.long_list = long_list; lg.long_count = long_count; lg.gidn = kLongSlots;
                     lg.attempts = att; lg.attempts_sum = &sched[1];
-                    small_backward_kernel<T, P, NORM><<<blocks_for(kLongSlots, kLongBT), kLongBT, kExclusiveSmem, h->stream>>>(prm, lg);
+                    // one warp per predicted-long trajectory, kLongWarps of them per block; each block asks for enough shared
+                    // memory to own its SM, so the long solves run undisturbed on a few SMs while the bulk gets the rest
+                    constexpr int kLongWarps = 12;
+                    constexpr size_t kExclusiveSmem = 200 * 1024;
+                    static_assert(sizeof(T) * (P::WPK + kLongWarps * (7 * StageRec<P>::N + 2)) + 32 <= kExclusiveSmem, "smem");
+                    CK(h, cudaFuncSetAttribute(small_backward_warp_kernel<T, P, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExclusiveSmem));
+                    small_backward_warp_kernel<T, P, NORM><<<blocks_for(kLongSlots, kLongWarps), kLongWarps * 32, kExclusiveSmem, h->stream>>>(prm, lg);
                     ++h->launches;
                     bw.long_flag = long_flag;
                 } else {
@@ -276,7 +280,7 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
             {
                 cudaStream_t bulk = have_long ? h->aux_stream : h->stream;
                 if (have_long) CK(h, cudaStreamWaitEvent(bulk, h->aux_ev[0], 0));
-                small_backward_kernel<T, P, NORM><<<blocks_for(B, BT), BT, smem, bulk>>>(prm, bw);
+                small_backward_kernel<T, P, NORM, 0><<<blocks_for(B, BT), BT, smem, bulk>>>(prm, bw);
                 if (have_long) { CK(h, cudaEventRecord(h->aux_ev[1], bulk)); CK(h, cudaStreamWaitEvent(h->stream, h->aux_ev[1], 0)); }
             }
             cudaEventRecord(h->ev[2], h->stream);

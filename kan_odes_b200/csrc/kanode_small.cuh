@@ -239,7 +239,7 @@ __device__ __forceinline__ void small_rhs_sm(const P& p, const T* __restrict__ w
 
 // fused forward-recompute + VJP with shared-memory weights; h_j and hbar_j go straight to the stage record
 // (rec = this thread's slot base, element f at rec[f*nthr])
-template <int NORM, class T, class P>
+template <int NORM, int UJ, class T, class P>
 __device__ __forceinline__ void small_vjp_sm(const P& p, const T* __restrict__ wsm, const T (&y)[P::I], const T (&lam)[P::I],
                                              T (&ubar)[P::I], T* rec, int nthr, int off_h, int off_hbar) {
     constexpr int I = P::I, H = P::H, G = P::G, NQ = P::NQ;
@@ -259,7 +259,7 @@ __device__ __forceinline__ void small_vjp_sm(const P& p, const T* __restrict__ w
     }
 #pragma unroll
     for (int q = 0; q < NQ; ++q) bb[q] = T(0);
-    KANODE_UNROLL(KANODE_UNROLL_J)
+#pragma unroll UJ
     for (int j = 0; j < H; ++j) {
         const T* w = wsm + j * P::UW;
         T wl[NQ];
@@ -647,9 +647,12 @@ __device__ __forceinline__ void unit_features(const P& p, T x, T (&c)[P::G + 1])
     swish_fwd(x, c[P::G]);
 }
 
-template <class T, class P, int NORM>
-__global__ void __launch_bounds__(KANODE_BWD_BT, KANODE_BWD_MINB) small_backward_kernel(const __grid_constant__ P prm, const SmallBwdArgs<T> a) {
+// LAT = 0: throughput build (rolled loops, small code, 4 blocks/SM).  LAT = 1: latency build for the launch of the
+// predicted-long trajectories (one warp owns an SM): unit and stage loops fully unrolled for instruction-level parallelism.
+template <class T, class P, int NORM, int LAT = 0>
+__global__ void __launch_bounds__(KANODE_BWD_BT, LAT ? 1 : KANODE_BWD_MINB) small_backward_kernel(const __grid_constant__ P prm, const SmallBwdArgs<T> a) {
     constexpr int I = P::I, H = P::H, G = P::G, NP = P::NP, NZ = I + NP, RS = 1 + 8 * I;
+    constexpr int US = LAT ? 7 : KANODE_UNROLL_S;                  // stage-loop unroll of the gradient pass
     using SR = StageRec<P>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* sm = reinterpret_cast<T*>(smem_raw) + threadIdx.x;          // element (slot, f) at sm[(slot*SR::N + f)*nthr]
@@ -719,7 +722,7 @@ __global__ void __launch_bounds__(KANODE_BWD_BT, KANODE_BWD_MINB) small_backward
         T y[I], ub[I];
         eval_y(t, y);
         T* s = sm + slot * SR::N * nthr;
-        small_vjp_sm<NORM>(prm, wsm, y, l, ub, s, nthr, SR::HH, SR::HBAR);
+        small_vjp_sm<NORM, LAT ? P::H : KANODE_UNROLL_J>(prm, wsm, y, l, ub, s, nthr, SR::HH, SR::HBAR);
 #pragma unroll
         for (int i = 0; i < I; ++i) { s[(SR::Y + i) * nthr] = y[i]; s[(SR::LAM + i) * nthr] = l[i]; dl[i] = -ub[i]; }
         ++nf;
@@ -912,7 +915,7 @@ __global__ void __launch_bounds__(KANODE_BWD_BT, KANODE_BWD_MINB) small_backward
                         const int j = q < G ? P::OC2 + (i * G + q) * I + o : P::OW2 + i * I + o;
                         g0[q][o] = gold[(int64_t)j * B]; vb[q][o] = T(0); vt[q][o] = T(0);
                     }
-                KANODE_UNROLL(KANODE_UNROLL_S)
+#pragma unroll US
                 for (int s = 0; s < 7; ++s) {
                     const T* rec = sm + s * SR::N * nthr;
                     T c[G + 1];
@@ -945,7 +948,7 @@ __global__ void __launch_bounds__(KANODE_BWD_BT, KANODE_BWD_MINB) small_backward
                         const int j = (q < G ? P::OC1 + (i * G + q) * H : P::OW1 + i * H) + o0 + oo;
                         g0[q][oo] = gold[(int64_t)j * B]; vb[q][oo] = T(0); vt[q][oo] = T(0);
                     }
-                KANODE_UNROLL(KANODE_UNROLL_S)
+#pragma unroll US
                 for (int s = 0; s < 7; ++s) {
                     const T* rec = sm + s * SR::N * nthr;
                     T c[G + 1];

@@ -85,7 +85,7 @@ template <class T, class P, int NORM> struct LsEval {
         T y[P::I], ub[P::I];
         eval_y(t, y);
         T* s = rec + (int64_t)slot * SR::N * B;
-        small_vjp_sm<NORM>(prm, wsm, y, l, ub, s, (int)B, SR::HH, SR::HBAR);
+        small_vjp_sm<NORM, KANODE_UNROLL_J>(prm, wsm, y, l, ub, s, (int)B, SR::HH, SR::HBAR);
 #pragma unroll
         for (int i = 0; i < I; ++i) { s[(int64_t)(SR::Y + i) * B] = y[i]; s[(int64_t)(SR::LAM + i) * B] = l[i]; dl[i] = -ub[i]; }
         ++nf;
@@ -360,31 +360,23 @@ __global__ void __launch_bounds__(KANODE_LS_BT, KANODE_LS_MINB) ls_step_kernel(c
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K2: step-end pass over the gradient components; blockIdx.y selects the work item (a hidden unit of layer 2 or an
-// (input, output-chunk) tile of layer 1), so every warp runs one item type
+// One work item of the step-end pass over the gradient components: item < H is hidden unit `item` of layer 2
+// (its C2 rows and W2 row), item >= H is an (input, output-chunk) tile of layer 1.  rec: stage records with element
+// (slot, f) at rec[(slot*SR::N + f)*rs]; gold/gnew: gradient buffers with component j at [j*gs].
+// Returns the item's part of the squared error norm.
 // ---------------------------------------------------------------------------------------------------------
-template <class T, class P, int NORM>
-__global__ void __launch_bounds__(128) ls_gphase_kernel(const __grid_constant__ P prm, const SmallBwdArgs<T> a, const LsState<T> st) {
-    constexpr int I = P::I, H = P::H, G = P::G, NP = P::NP, OC = LsItems<P>::OC;
+template <int NORM, class T, class P>
+__device__ __forceinline__ T gphase_item(const P& prm, int item, const T* rec, int64_t rs, const T* gold, T* gnew, int64_t gs,
+                                         T mh, T abstol, T reltol) {
+    constexpr int I = P::I, H = P::H, G = P::G, OC = LsItems<P>::OC;
     using SR = StageRec<P>;
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.B) return;
-    const int64_t B = a.B;
-    if (!(st.flags[b] & LS_ATTEMPT)) return;
-    const int item = blockIdx.y;
-    const T mh = (T)st.dt[b];                                   // -h = +dt  (dg/dt = -kv, h = -dt)
-    const int cur = st.cur[b];
-    const T* gold = a.g + b + (int64_t)cur * NP * B;
-    T* gnew = a.g + b + (int64_t)(cur ^ 1) * NP * B;
-    const T* rec = st.rec + b;
-    const T abstol = a.abstol, reltol = a.reltol;
     T es = T(0);
     auto finalize = [&](int j, T g0, T vb, T vt) {
         const T g1 = g0 + mh * vb;
         const T sc = abstol + kmax(kabs(g0), kabs(g1)) * reltol;
         const T r = kdiv(mh * vt, sc);
         es += r * r;
-        gnew[(int64_t)j * B] = g1;
+        gnew[(int64_t)j * gs] = g1;
     };
     if (item < H) {                                              // layer 2: hidden unit i, outputs o < I
         const int i = item;
@@ -394,17 +386,17 @@ __global__ void __launch_bounds__(128) ls_gphase_kernel(const __grid_constant__ 
 #pragma unroll
             for (int o = 0; o < I; ++o) {
                 const int j = q < G ? P::OC2 + (i * G + q) * I + o : P::OW2 + i * I + o;
-                g0[q][o] = gold[(int64_t)j * B]; vb[q][o] = T(0); vt[q][o] = T(0);
+                g0[q][o] = gold[(int64_t)j * gs]; vb[q][o] = T(0); vt[q][o] = T(0);
             }
 #pragma unroll
         for (int s = 0; s < 7; ++s) {
-            const T* r = rec + (int64_t)s * SR::N * B;
+            const T* r = rec + (int64_t)s * SR::N * rs;
             T c[G + 1];
-            unit_features<NORM>(prm, r[(int64_t)(SR::HH + i) * B], c);
+            unit_features<NORM>(prm, r[(int64_t)(SR::HH + i) * rs], c);
             const T wb = Tab<T>::b(s), wt = Tab<T>::bt(s);
 #pragma unroll
             for (int o = 0; o < I; ++o) {
-                const T l = r[(int64_t)(SR::LAM + o) * B];
+                const T l = r[(int64_t)(SR::LAM + o) * rs];
                 const T ab = wb * l, at = wt * l;
 #pragma unroll
                 for (int q = 0; q <= G; ++q) { vb[q][o] += ab * c[q]; vt[q][o] += at * c[q]; }
@@ -424,17 +416,17 @@ __global__ void __launch_bounds__(128) ls_gphase_kernel(const __grid_constant__ 
 #pragma unroll
             for (int oo = 0; oo < OC; ++oo) {
                 const int j = (q < G ? P::OC1 + (i * G + q) * H : P::OW1 + i * H) + o0 + oo;
-                g0[q][oo] = gold[(int64_t)j * B]; vb[q][oo] = T(0); vt[q][oo] = T(0);
+                g0[q][oo] = gold[(int64_t)j * gs]; vb[q][oo] = T(0); vt[q][oo] = T(0);
             }
 #pragma unroll
         for (int s = 0; s < 7; ++s) {
-            const T* r = rec + (int64_t)s * SR::N * B;
+            const T* r = rec + (int64_t)s * SR::N * rs;
             T c[G + 1];
-            unit_features<NORM>(prm, r[(int64_t)(SR::Y + i) * B], c);
+            unit_features<NORM>(prm, r[(int64_t)(SR::Y + i) * rs], c);
             const T wb = Tab<T>::b(s), wt = Tab<T>::bt(s);
 #pragma unroll
             for (int oo = 0; oo < OC; ++oo) {
-                const T hb = r[(int64_t)(SR::HBAR + o0 + oo) * B];
+                const T hb = r[(int64_t)(SR::HBAR + o0 + oo) * rs];
                 const T ab = wb * hb, at = wt * hb;
 #pragma unroll
                 for (int q = 0; q <= G; ++q) { vb[q][oo] += ab * c[q]; vt[q][oo] += at * c[q]; }
@@ -446,7 +438,279 @@ __global__ void __launch_bounds__(128) ls_gphase_kernel(const __grid_constant__ 
             for (int oo = 0; oo < OC; ++oo)
                 finalize((q < G ? P::OC1 + (i * G + q) * H : P::OW1 + i * H) + o0 + oo, g0[q][oo], vb[q][oo], vt[q][oo]);
     }
+    return es;
+}
+
+// K2 of the lockstep engine: blockIdx.y selects the work item, so every warp runs one item type
+template <class T, class P, int NORM>
+__global__ void __launch_bounds__(128) ls_gphase_kernel(const __grid_constant__ P prm, const SmallBwdArgs<T> a, const LsState<T> st) {
+    constexpr int NP = P::NP;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int64_t B = a.B;
+    if (!(st.flags[b] & LS_ATTEMPT)) return;
+    const int item = blockIdx.y;
+    const int cur = st.cur[b];
+    const T es = gphase_item<NORM>(prm, item, st.rec + b, B, a.g + b + (int64_t)cur * NP * B, a.g + b + (int64_t)(cur ^ 1) * NP * B, B,
+                                   (T)st.dt[b], a.abstol, a.reltol);                 // -h = +dt  (dg/dt = -kv, h = -dt)
     st.es_part[(int64_t)item * B + b] = es;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// WARP-PER-TRAJECTORY backward solve for the few trajectories predicted to need many steps.  Their serial chain of
+// steps bounds the whole launch, so here one warp owns one trajectory (and, through an exclusive shared-memory
+// request, one SM): lane 0 runs the control flow and the 7 fused forward+VJP stage evaluations exactly like the
+// thread-per-trajectory kernel; the step-end pass over the NP gradient components — 40 % of a step's instructions —
+// is spread over the lanes (one work item per lane).  Same arithmetic, same results.
+// ---------------------------------------------------------------------------------------------------------
+template <class T, class P, int NORM>
+__global__ void __launch_bounds__(384) small_backward_warp_kernel(const __grid_constant__ P prm, const SmallBwdArgs<T> a) {
+    constexpr int I = P::I, NP = P::NP, NZ = I + NP, RS = 1 + 8 * I, NITEM = LsItems<P>::NITEM;
+    using SR = StageRec<P>;
+    static_assert(NITEM <= 32, "one work item per lane");
+    // dynamic shared memory: [packed weights | mbarrier | per warp: 7 stage records, -h, current g buffer]
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* wsm = reinterpret_cast<T*>(smem_raw);
+    uint64_t* wbar = reinterpret_cast<uint64_t*>(wsm + P::WPK);
+    constexpr int PER_WARP = 7 * SR::N + 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    T* rec = reinterpret_cast<T*>(wbar + 2) + warp * PER_WARP;
+    T& s_mh = rec[7 * SR::N];
+    int& s_cur = *reinterpret_cast<int*>(&rec[7 * SR::N + 1]);
+    stage_weights<T, P::WPK>(wsm, wbar, a.wpk);
+    const int slot_id = blockIdx.x * nwarps + warp;
+    if (slot_id >= *a.long_count || slot_id >= a.gidn) return;
+    const int64_t b = a.long_list[slot_id];
+    const int64_t B = a.B;
+    T* gbuf = a.g + b;
+    for (int j = lane; j < NP; j += 32) gbuf[(int64_t)j * B] = T(0);
+    __syncwarp();
+    // ---- everything below mirrors small_backward_kernel; lane 0 holds the solver state ----
+    T lam[I], lprev[I], kl[7][I];
+#pragma unroll
+    for (int i = 0; i < I; ++i) { lam[i] = T(0); lprev[i] = T(0); }
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+#pragma unroll
+        for (int i = 0; i < I; ++i) kl[j][i] = T(0);
+    int nf = 0, naccept = 0, nreject = 0, ret = a.retcode[b];
+    const int nsteps = a.nsteps[b];
+    if (ret != RET_SUCCESS || nsteps <= 0) {
+        if (lane == 0) {
+            if (a.stats) a.stats[b] = kanode_stats{0, 0, 0, ret};
+            if (a.du0) for (int i = 0; i < I; ++i) a.du0[b * I + i] = T(0);
+            if (a.attempts) a.attempts[b] = 0;
+        }
+        return;
+    }
+    int ridx = nsteps - 1;
+    double rt = 0, rt_next = 0;
+    T rdt = T(1), ru[I], rk[7][I];
+    auto load_rec = [&](int idx) {
+        rt = a.rec_t[(int64_t)idx * B + b];
+        const T* r = a.rec + (int64_t)idx * RS * B + b;
+        rdt = r[0];
+#pragma unroll
+        for (int i = 0; i < I; ++i) ru[i] = r[(int64_t)(1 + i) * B];
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+#pragma unroll
+            for (int i = 0; i < I; ++i) rk[j][i] = r[(int64_t)(1 + I + j * I + i) * B];
+        rt_next = (idx + 1 < nsteps) ? a.rec_t[(int64_t)(idx + 1) * B + b] : a.t1;
+        ridx = idx;
+    };
+    auto adj_eval = [&](double t, const T (&l)[I], T (&dl)[I], int slot) {
+        while (t < rt && ridx > 0) load_rec(ridx - 1);
+        while (t >= rt_next && ridx + 1 < nsteps) load_rec(ridx + 1);
+        const T th = (T)((t - rt) / (double)rdt);
+        T bw[7]; interp_weights(th, bw);
+        T y[I], ub[I];
+#pragma unroll
+        for (int i = 0; i < I; ++i) {
+            T acc = T(0);
+#pragma unroll
+            for (int j = 0; j < 7; ++j) acc += bw[j] * rk[j][i];
+            y[i] = ru[i] + rdt * acc;
+        }
+        T* s = rec + slot * SR::N;
+        small_vjp_sm<NORM, KANODE_UNROLL_J>(prm, wsm, y, l, ub, s, 1, SR::HH, SR::HBAR);
+#pragma unroll
+        for (int i = 0; i < I; ++i) { s[SR::Y + i] = y[i]; s[SR::LAM + i] = l[i]; dl[i] = -ub[i]; }
+        ++nf;
+    };
+    const double t0 = a.t0, t1 = a.t1, dtmax = fabs(t1 - t0), dtmin0 = fmax(eps_of(t0), eps_of(t1));
+    const T abstol = a.abstol, reltol = a.reltol;
+    double t = t1, dt = 0, qold = Ctrl::qoldinit, q11 = 1.0, dtpropose = 0;
+    int sp = a.nsave - 1, iter = 0, cur = 0;
+    bool accept = false, modified = false;
+    if (lane == 0) {
+        load_rec(ridx);
+        while (sp >= 0 && a.saveat[sp] == t1) {
+#pragma unroll
+            for (int i = 0; i < I; ++i) lam[i] += a.dg[((int64_t)sp * I + i) * B + b];
+            --sp;
+        }
+#pragma unroll
+        for (int i = 0; i < I; ++i) lprev[i] = lam[i];
+        adj_eval(t, lam, kl[0], 0);
+        T sk[I], s0 = T(0), s1 = T(0);
+#pragma unroll
+        for (int i = 0; i < I; ++i) {
+            sk[i] = abstol + kabs(lam[i]) * reltol;
+            const T x0 = lam[i] / sk[i], x1 = kl[0][i] / sk[i];
+            s0 += x0 * x0; s1 += x1 * x1;
+        }
+        ls_for_each_g<1, NORM>(prm, rec, 1, [&](int, const T (&kv)[1]) { const T x = kv[0] / abstol; s1 += x * x; });
+        const double d0 = sqrt((double)s0 / NZ), d1 = sqrt((double)s1 / NZ);
+        double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
+        dt0 = fmin(dt0, dtmax);
+        T l1[I], f1[I];
+#pragma unroll
+        for (int i = 0; i < I; ++i) l1[i] = lam[i] - (T)dt0 * kl[0][i];
+        adj_eval(t - dt0, l1, f1, 1);
+        ++nf;
+        T s2 = T(0);
+#pragma unroll
+        for (int i = 0; i < I; ++i) { const T x = (f1[i] - kl[0][i]) / sk[i]; s2 += x * x; }
+        ls_for_each_g<2, NORM>(prm, rec, 1, [&](int, const T (&kv)[2]) { const T x = (kv[1] - kv[0]) / abstol; s2 += x * x; });
+        const double d2 = sqrt((double)s2 / NZ) / dt0, mx = fmax(d1, d2);
+        const double dt1 = (mx <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / 5.0);
+        dt = fmax(dtmin0, fmin(fmin(100.0 * dt0, dt1), dtmax));
+        dtpropose = dt;
+    }
+    T es_l = T(0), h = T(0);
+    T lnew[I];
+#pragma unroll
+    for (int i = 0; i < I; ++i) lnew[i] = T(0);
+    double tstop = t0;
+    for (;;) {
+        int go = 0;
+        if (lane == 0) {
+            go = t > t0;
+            if (go) {
+                // ---- loopheader! ----
+                if (iter > 0) {
+                    if (!accept) dt = dt / fmin(1.0 / Ctrl::qmin, q11 / Ctrl::gamma);
+                    else {
+                        dt = dtpropose;
+                        if (!modified) {
+#pragma unroll
+                            for (int i = 0; i < I; ++i) kl[0][i] = kl[6][i];
+#pragma unroll
+                            for (int f = 0; f < SR::N; ++f) rec[f] = rec[6 * SR::N + f];
+                        }
+                    }
+                }
+                ++iter;
+                tstop = (sp >= 0) ? fmax(a.saveat[sp], t0) : t0;
+                const double dtmin_t = fmax(eps_of(t), dtmin0);
+                dt = fmin(fmax(fmin(fabs(dt), dtmax), dtmin_t), t - tstop);
+                if (iter > a.maxiters) { ret = RET_MAXITERS; go = 0; }
+                else if (!(dt > dtmin_t) && (t - dt > tstop || !accept) && iter > 1) { ret = RET_DTMIN; go = 0; }
+                else if (dt != dt) { ret = RET_UNSTABLE; go = 0; }
+            }
+            if (go) {
+                // ---- stage evaluations ----
+                h = (T)(-dt);
+#pragma unroll
+                for (int i = 0; i < I; ++i) lnew[i] = lprev[i];
+#pragma unroll 1
+                for (int s = modified ? 0 : 1; s < 7; ++s) {
+                    T ls[I], ks[I];
+#pragma unroll
+                    for (int i = 0; i < I; ++i) {
+                        T acc = T(0);
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) acc += Tab<T>::a(s, j) * kl[j][i];
+                        ls[i] = lprev[i] + h * acc;
+                    }
+                    adj_eval(t - tab_c(s) * dt, ls, ks, s);
+#pragma unroll
+                    for (int j = 0; j < 7; ++j)
+                        if (j == s) {
+#pragma unroll
+                            for (int i = 0; i < I; ++i) kl[j][i] = ks[i];
+                        }
+                    if (s == 6) {
+#pragma unroll
+                        for (int i = 0; i < I; ++i) lnew[i] = ls[i];
+                    }
+                }
+                modified = false;
+                es_l = T(0);
+#pragma unroll
+                for (int i = 0; i < I; ++i) {
+                    T ut = T(0);
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) ut += Tab<T>::bt(j) * kl[j][i];
+                    ut *= h;
+                    const T sc = abstol + kmax(kabs(lprev[i]), kabs(lnew[i])) * reltol;
+                    const T r = ut / sc;
+                    es_l += r * r;
+                    if (lnew[i] != lnew[i]) es_l = lnew[i];
+                }
+                s_mh = -h; s_cur = cur;
+            }
+        }
+        go = __shfl_sync(0xffffffffu, go, 0);
+        if (!go) break;
+        __syncwarp();
+        // ---- step-end pass over the gradient components: one work item per lane ----
+        T es = T(0);
+        if (lane < NITEM) {
+            const int c = s_cur;
+            es = gphase_item<NORM>(prm, lane, rec, 1, gbuf + (int64_t)c * NP * B, gbuf + (int64_t)(c ^ 1) * NP * B, B, s_mh, abstol, reltol);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) es += __shfl_xor_sync(0xffffffffu, es, off);
+        __syncwarp();
+        if (lane == 0) {
+            // ---- loopfooter! ----
+            const double EEst = (double)ksqrt((es_l + es) / T(NZ));
+            if (EEst != EEst) { ret = RET_UNSTABLE; t = t0; accept = false; }
+            else {
+                const double q = pi_q(EEst, qold, q11);
+                accept = EEst <= 1.0;
+                if (accept) {
+                    ++naccept;
+                    qold = fmax(EEst, Ctrl::qoldinit);
+                    const double dtnew = dt / q;
+                    double tnew = t - dt;
+                    if (fabs(tnew - tstop) < 100.0 * eps_of(fmax(fabs(t), fabs(tstop)))) tnew = tstop;
+                    dtpropose = fmax(fmin(dtmax, fabs(dtnew)), fmax(eps_of(tnew), dtmin0));
+                    t = tnew;
+                    cur ^= 1;
+#pragma unroll
+                    for (int i = 0; i < I; ++i) lam[i] = lnew[i];
+                    while (sp >= 0 && a.saveat[sp] == t) {
+#pragma unroll
+                        for (int i = 0; i < I; ++i) lam[i] += a.dg[((int64_t)sp * I + i) * B + b];
+                        --sp; modified = true;
+                    }
+#pragma unroll
+                    for (int i = 0; i < I; ++i) lprev[i] = lam[i];
+                } else {
+                    ++nreject;
+                }
+            }
+        }
+    }
+    // result always in buffer 0; zero on failure
+    cur = __shfl_sync(0xffffffffu, cur, 0);
+    ret = __shfl_sync(0xffffffffu, ret, 0);
+    __syncwarp();
+    if (ret != RET_SUCCESS) { for (int j = lane; j < NP; j += 32) gbuf[(int64_t)j * B] = T(0); }
+    else if (cur == 1) { for (int j = lane; j < NP; j += 32) gbuf[(int64_t)j * B] = gbuf[((int64_t)NP + j) * B]; }
+    if (lane == 0) {
+        if (a.du0)
+#pragma unroll
+            for (int i = 0; i < I; ++i) a.du0[b * I + i] = lam[i];
+        if (a.stats) a.stats[b] = kanode_stats{naccept, nreject, nf, ret};
+        if (a.attempts) {
+            a.attempts[b] = naccept + nreject;
+            if (a.attempts_sum) atomicAdd(a.attempts_sum, (unsigned long long)(naccept + nreject));
+        }
+    }
 }
 
 // out[j] = sum_b g[cur[b]][j][b] over the trajectories that finished successfully (double accumulation)
