@@ -9,7 +9,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 OUT = HERE / "libkanode_b200.so"
 SOURCES = ["kanode_api.cu"]
-DEPS = ["kanode_api.cu", "kanode_host.h", "kanode_math.cuh", "kanode_small.cuh", "kanode_generic.cuh",
+DEPS = ["kanode_api.cu", "kanode_host.h", "kanode_math.cuh", "kanode_small.cuh", "kanode_generic.cuh", "kanode_small_ls.cuh", "kanode_wide.cuh",
         "../../include/kanode.h"]
 NVCC_FLAGS = ["-std=c++20", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

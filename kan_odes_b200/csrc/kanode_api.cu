@@ -16,6 +16,7 @@
 #include "kanode_small.cuh"
 #include "kanode_small_ls.cuh"
 #include "kanode_generic.cuh"
+#include "kanode_wide.cuh"
 
 using namespace kanode;
 
@@ -182,6 +183,11 @@ int solve_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double t1, 
         return 0;
     };
     if (small_dispatch<T>(h, run, rc)) return rc;
+    WideKey wk;
+    if (h->wide && wide_match(h->desc, wk)) {
+        if (wk.G == 5) return wide_solve_t<T, 10, 5>(h, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);
+        return wide_solve_t<T, 10, 10>(h, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);
+    }
     return generic_solve<T>(h, d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);
 }
 
@@ -331,6 +337,14 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
         return 0;
     };
     if (small_dispatch<T>(h, run, rc)) return rc;
+    WideKey wk;
+    if (h->wide && wide_match(h->desc, wk)) {
+        if (wk.G == 5)
+            return wide_loss_grad_t<T, 10, 5>(h, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol,
+                                              d_loss_sum, d_grad_sum, d_du0, d_fst, d_bst, d_out_opt);
+        return wide_loss_grad_t<T, 10, 10>(h, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol,
+                                           d_loss_sum, d_grad_sum, d_du0, d_fst, d_bst, d_out_opt);
+    }
     return generic_loss_grad<T>(h, d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum, d_grad_sum,
                                 d_du0, d_fst, d_bst, d_out_opt);
 }
@@ -470,6 +484,7 @@ int kanode_create(const kanode_desc* desc, int device, void* stream, kanode_hand
     h->params.assign(np, 0.0);
     if (const char* e = std::getenv("KANODE_LOCKSTEP")) h->lockstep = std::atoi(e);
     if (const char* e = std::getenv("KANODE_SCHEDULE")) h->schedule = std::atoi(e);
+    if (const char* e = std::getenv("KANODE_WIDE")) h->wide = std::atoi(e);
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, KANODE_ERR_CUDA, "cudaSetDevice failed"); }
     if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
     else {

@@ -1,0 +1,1163 @@
+// kanode_wide.cuh — batched LOCKSTEP engine for the wide PDE surrogates: two-layer KDense chains [n, H, n]
+// (Burgers-1024, Allen-Cahn-4096, Schrodinger-32768 of BASELINE.json; H = 10 in every reference script).
+//
+// Why a second engine: the block-per-trajectory kernels (kanode_generic.cuh) stream all np = 2*n*H*(G+1) weights
+// through one block per right-hand-side evaluation, so a batch of B initial conditions re-reads the weights B times
+// from L2 and keeps only B SMs busy.  The RHS is autonomous, so all ICs can evaluate "stage s of their current step
+// attempt" at the same time whatever their own t and dt are: the batch advances in lockstep over step ATTEMPTS,
+// every IC keeps its own PI controller, accept/reject decision, dense record and tstops (identical per-IC
+// arithmetic to the generic path / oracle), and finished ICs are masked.  Every contraction then runs as a kernel
+// over the whole batch with the weights of one input/output unit held in REGISTERS and reused across the ICs:
+//
+//   wide_l1_fwd   thread = input unit i   w1[(G+1)*H] regs   hidden[b][:] += w1 . features(x[b][i])   (reduce over n)
+//   wide_l2_fwd   thread = output unit o  w2[H*(G+1)] regs   k[b][o] = w2 . features(hidden[b][:])    (expand)
+//   wide_l2_vjp   thread = output unit o  w2 regs            hbar[b][j] += lam[b][o] * (w2_j . dfeat_j(hidden[b]))
+//   wide_l1_vjp   thread = input unit i   w1 regs            lambda-dot[b][i] = -dfeat(x[b][i]) . (w1 . hbar[b])
+//
+// The RBF features are produced and consumed in registers / shared memory and never reach HBM.  Cross-block sums
+// (over the n units) are two-level and deterministic: per-block partials, then the last block to finish (device
+// counter) adds them in a fixed order.  The adjoint integrates z = [lambda; g] per IC exactly like the reference's
+// InterpolatingAdjoint: dg/dt is kept as rank-1 stage records (layer inputs x_l, output cotangents ybar_l) and the
+// step-end pass streams g[b] once (read g_old, write g_new, error-norm contribution) — that pass is the HBM-bound
+// part of a wide step (8 bytes per parameter per IC per attempt).
+//
+// Reference semantics: KDense forward Lotka-Volterra/src/kdense.jl:109-130, reverse rules src/utils.jl:15-21;
+// drivers "PDE examples/Burgers_Surrogate.jl":82-107, Allen-Cahn_Surrogate.jl:80-107, Schrodinger_Surrogate.jl:89-114;
+// Tsit5 / controller / adjoint: [EXT OrdinaryDiffEqTsit5 1.1.0, OrdinaryDiffEqCore 1.9.0, SciMLSensitivity 7.69.0].
+#pragma once
+#include "kanode_host.h"
+#include "kanode_math.cuh"
+
+namespace kanode {
+
+constexpr int W_BT = 128;      // threads per block of the unit-per-thread kernels
+constexpr int W_ET = 256;      // threads per block of the elementwise kernels
+constexpr int W_MAXCH = 64;    // most partials per IC in the reduce kernels
+constexpr int W_HP = 16;       // padded hidden width of the [B][16] arrays
+constexpr int W_PT = 32;       // ICs per block in the kernels without a reduction
+
+struct WideModel {
+    int n, norm1, norm2;
+    float inv_h1, inv_h2;
+    float grid1[16], grid2[16];
+    long long offC1, offW1, offC2, offW2, np;
+};
+
+// per-IC solver state, structure of arrays (device)
+struct WideCtl {
+    double *t, *dt, *dtpropose, *qold, *q11, *told, *dtold, *d0, *d1, *dt0;
+    int *iter, *accept, *acc_now, *fail_now, *active, *modified, *do_s0, *sidx, *s_lo, *s_hi, *nrec, *naccept, *nreject, *nf,
+        *ret, *cur;
+    int* ridx;   // [7][B] dense-record index of every backward stage time
+};
+constexpr int W_NCTL_D = 10, W_NCTL_I = 16 + 7;
+
+template <class T> __device__ __forceinline__ T ld_cg(const T* p) { return __ldcg(p); }
+
+template <class T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+// deterministic block sum (blockDim multiple of 32, <= 1024); result valid in every thread
+template <class T> __device__ __forceinline__ T wblock_sum(T v, T* sred /*[33]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sred[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { T s = T(0); for (int w = 0; w < nw; ++w) s += sred[w]; sred[32] = s; }
+    __syncthreads();
+    return sred[32];
+}
+
+// features of one scalar: c[q] = rbf_q(norm(x)) (q < G), c[G] = swish(x)          (kdense.jl:116-123)
+template <class T, int G> __device__ __forceinline__ void w_features(int norm, T inv_h, const float* grid, T x, T (&c)[G + 1]) {
+    const T xn = normalize_rt(norm, x);
+#pragma unroll
+    for (int g = 0; g < G; ++g) { const T a = (xn - (T)grid[g]) * inv_h; c[g] = kexp(-a * a); }
+    swish_fwd(x, c[G]);
+}
+// d c[q] / dx  (utils.jl:15-21 + NNlib activation rules)
+template <class T, int G> __device__ __forceinline__ void w_dfeatures(int norm, T inv_h, const float* grid, T x, T (&d)[G + 1]) {
+    const T xn = normalize_rt(norm, x);
+    const T dn = normalize_deriv_rt(norm, xn);
+#pragma unroll
+    for (int g = 0; g < G; ++g) { const T a = (xn - (T)grid[g]) * inv_h; const T y = kexp(-a * a); d[g] = (T(-2) * a * y) * inv_h * dn; }
+    T s, ds; swish_both(x, s, ds);
+    d[G] = ds;
+}
+
+// stage input of a reduce kernel.  MODE 0: x = base + hs[b] * sum_j coef[j] * ks[j]   (Tsit5 stage combination)
+//                                  MODE 1: x = sol(t_stage) from the dense forward record (backward pass)
+template <class T> struct WideIn {
+    const T* base; const T* ks; const T* hs; T coef[7]; int ncoef;
+    const T* rec; int cap; const int* ridx; const T* th; const T* hd;
+    T* xstore;           // optional copy of x: [B][n]
+    const int* mask;     // per-IC, 0 = skip (may be null)
+};
+
+template <class T, int MODE> __device__ __forceinline__ T wide_input(const WideIn<T>& in, int b, int i, int n, int64_t B) {
+    if (MODE == 0) {
+        const int64_t e = (int64_t)b * n + i;
+        T acc = T(0);
+        for (int j = 0; j < in.ncoef; ++j) acc += in.coef[j] * in.ks[(int64_t)j * B * n + e];
+        return in.ncoef > 0 ? in.base[e] + in.hs[b] * acc : in.base[e];
+    } else {
+        T bw[7]; interp_weights(in.th[b], bw);
+        const T* r = in.rec + ((int64_t)b * in.cap + in.ridx[b]) * 8 * (int64_t)n;
+        T acc = T(0);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) acc += bw[j] * r[(int64_t)(1 + j) * n + i];
+        return r[i] + in.hd[b] * acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// shared tail of the two reduce kernels: red[v][tid] column sums -> part[chunk][b][H]; last block -> dst[b][W_HP]
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int H>
+__device__ __forceinline__ void wide_reduce_tail(T (*red)[W_BT + 1], int b0, int b1, int64_t B, T* part, T* dst, unsigned* counters, int* s_last,
+                                                 const int* mask) {
+    const int tid = threadIdx.x, chunk = blockIdx.x, nchunk = gridDim.x;
+    const int nv = (b1 - b0) * H;
+    __syncthreads();
+    for (int v = tid; v < nv; v += W_BT) {
+        T s = T(0);
+        for (int k = 0; k < W_BT; ++k) s += red[v][k];
+        part[((int64_t)chunk * B + b0 + v / H) * H + v % H] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *s_last = (atomicAdd(&counters[blockIdx.y], 1u) == (unsigned)(nchunk - 1));
+    __syncthreads();
+    if (!*s_last) return;
+    __threadfence();
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int v = warp; v < nv; v += W_BT / 32) {
+        const int b = b0 + v / H, o = v % H;
+        T s = T(0);
+        for (int c = lane; c < nchunk; c += 32) s += ld_cg(&part[((int64_t)c * B + b) * H + o]);
+        s = warp_sum(s);
+        if (lane == 0 && (!mask || mask[b])) dst[(int64_t)b * W_HP + o] = s;   // masked ICs keep their (FSAL-shifted) record
+    }
+    if (tid == 0) counters[blockIdx.y] = 0u;   // re-armed for the next launch on this stream
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// layer 1 forward (reduce over the n input units): hidden[b][o] = sum_i sum_q w1[i][q][o] * c_q(x[b][i])
+// grid (nchunk, nbt); block W_BT; each block walks P passes of W_BT units and <= GB ICs
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int H, int G, int MODE>
+__global__ void __launch_bounds__(W_BT) wide_l1_fwd_kernel(const __grid_constant__ WideModel m, const T* __restrict__ p, const WideIn<T> in,
+                                                           int64_t B, int P, int btile, T* part, T* hidden, unsigned* counters) {
+    constexpr int NQ = G + 1, NW = H * NQ, GB = sizeof(T) == 4 ? 8 : 4;
+    __shared__ T red[GB * H][W_BT + 1];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, n = m.n;
+    const int b0 = blockIdx.y * btile, b1 = (int)min((int64_t)(b0 + btile), B);
+    const T inv_h = (T)m.inv_h1;
+    for (int pass = 0; pass < P; ++pass) {
+        const int i = (blockIdx.x * P + pass) * W_BT + tid;
+        const bool valid = i < n;
+        T w[NW];
+        if (valid) {
+            const T* c = p + m.offC1 + (int64_t)i * G * H;
+#pragma unroll
+            for (int k = 0; k < G * H; ++k) w[k] = c[k];
+            const T* ww = p + m.offW1 + (int64_t)i * H;
+#pragma unroll
+            for (int k = 0; k < H; ++k) w[G * H + k] = ww[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < NW; ++k) w[k] = T(0);
+        }
+        for (int b = b0; b < b1; ++b) {
+            T acc[H];
+#pragma unroll
+            for (int o = 0; o < H; ++o) acc[o] = T(0);
+            if (valid && (!in.mask || in.mask[b])) {
+                const T x = wide_input<T, MODE>(in, b, i, n, B);
+                if (in.xstore) in.xstore[(int64_t)b * n + i] = x;
+                T c[NQ];
+                w_features<T, G>(m.norm1, inv_h, m.grid1, x, c);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                    for (int o = 0; o < H; ++o) acc[o] += w[q * H + o] * c[q];
+            }
+            const int bl = b - b0;
+#pragma unroll
+            for (int o = 0; o < H; ++o) {
+                if (pass == 0) red[bl * H + o][tid] = acc[o];
+                else red[bl * H + o][tid] += acc[o];
+            }
+        }
+    }
+    wide_reduce_tail<T, H>(red, b0, b1, B, part, hidden, counters, &s_last, in.mask);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// layer 2 forward (expand): out[b][o] = sum_j ( sum_q C2[(j,q)][o] * c_q(hidden[b][j]) + W2[j][o] * swish(hidden[b][j]) )
+// grid (ceil(n / W_BT), nbt); weights of output o in registers, features of the ICs in shared memory
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int H, int G> __device__ __forceinline__ void wide_load_w2(const WideModel& m, const T* __restrict__ p, int o, T (&w)[H * (G + 1)]) {
+    constexpr int NQ = G + 1;
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+#pragma unroll
+        for (int q = 0; q < G; ++q) w[j * NQ + q] = p[m.offC2 + (int64_t)(j * G + q) * m.n + o];
+        w[j * NQ + G] = p[m.offW2 + (int64_t)j * m.n + o];
+    }
+}
+
+template <class T, int H, int G>
+__global__ void __launch_bounds__(W_BT) wide_l2_fwd_kernel(const __grid_constant__ WideModel m, const T* __restrict__ p, const T* hidden, T* out,
+                                                           const int* mask, int64_t B, int btile) {
+    constexpr int NQ = G + 1, NW = H * NQ, NWP = (NW + 3) / 4 * 4;
+    __shared__ __align__(16) T f2[W_PT][NWP];
+    const int tid = threadIdx.x, n = m.n;
+    const int b0 = blockIdx.y * btile, b1 = (int)min((int64_t)(b0 + btile), B);
+    for (int v = tid; v < (b1 - b0) * H; v += W_BT) {
+        const int bl = v / H, j = v % H;
+        T c[NQ];
+        w_features<T, G>(m.norm2, (T)m.inv_h2, m.grid2, hidden[(int64_t)(b0 + bl) * W_HP + j], c);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) f2[bl][j * NQ + q] = c[q];
+    }
+    __syncthreads();
+    const int o = blockIdx.x * W_BT + tid;
+    if (o >= n) return;
+    T w[NW];
+    wide_load_w2<T, H, G>(m, p, o, w);
+    for (int b = b0; b < b1; ++b) {
+        if (mask && !mask[b]) continue;
+        const T* f = f2[b - b0];
+        T acc = T(0);
+#pragma unroll
+        for (int r = 0; r < NW; ++r) acc += w[r] * f[r];
+        out[(int64_t)b * n + o] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// layer 2 reverse (reduce over the n output units): hbar[b][j] = sum_o lam[b][o] * sum_q w2[o][j][q] * d_q(hidden[b][j])
+// lam = lprev + h * sum a_sj kl_j is formed here (and stored: it is ybar of layer 2 in the stage record)
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int H, int G>
+__global__ void __launch_bounds__(W_BT) wide_l2_vjp_kernel(const __grid_constant__ WideModel m, const T* __restrict__ p, const T* hidden,
+                                                           const WideIn<T> in, int64_t B, int P, int btile, T* part, T* hbar, unsigned* counters) {
+    constexpr int NQ = G + 1, NW = H * NQ, GB = sizeof(T) == 4 ? 8 : 4;
+    __shared__ T red[GB * H][W_BT + 1];
+    __shared__ T d2[GB][NW];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, n = m.n;
+    const int b0 = blockIdx.y * btile, b1 = (int)min((int64_t)(b0 + btile), B);
+    for (int v = tid; v < (b1 - b0) * H; v += W_BT) {
+        const int bl = v / H, j = v % H;
+        T d[NQ];
+        w_dfeatures<T, G>(m.norm2, (T)m.inv_h2, m.grid2, hidden[(int64_t)(b0 + bl) * W_HP + j], d);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) d2[bl][j * NQ + q] = d[q];
+    }
+    __syncthreads();
+    for (int pass = 0; pass < P; ++pass) {
+        const int o = (blockIdx.x * P + pass) * W_BT + tid;
+        const bool valid = o < n;
+        T w[NW];
+        if (valid) wide_load_w2<T, H, G>(m, p, o, w);
+        else {
+#pragma unroll
+            for (int k = 0; k < NW; ++k) w[k] = T(0);
+        }
+        for (int b = b0; b < b1; ++b) {
+            const int bl = b - b0;
+            T acc[H];
+#pragma unroll
+            for (int j = 0; j < H; ++j) acc[j] = T(0);
+            if (valid && (!in.mask || in.mask[b])) {
+                const T lam = wide_input<T, 0>(in, b, o, n, B);
+                if (in.xstore) in.xstore[(int64_t)b * n + o] = lam;
+                const T* d = d2[bl];
+#pragma unroll
+                for (int j = 0; j < H; ++j) {
+                    T inner = T(0);
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) inner += w[j * NQ + q] * d[j * NQ + q];
+                    acc[j] = lam * inner;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                if (pass == 0) red[bl * H + j][tid] = acc[j];
+                else red[bl * H + j][tid] += acc[j];
+            }
+        }
+    }
+    wide_reduce_tail<T, H>(red, b0, b1, B, part, hbar, counters, &s_last, in.mask);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// layer 1 reverse: dl[b][i] = -( dnorm * sum_g db_g/h * (w1[g][:] . hbar[b]) + dswish * (W1[i][:] . hbar[b]) )
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int H, int G>
+__global__ void __launch_bounds__(W_BT) wide_l1_vjp_kernel(const __grid_constant__ WideModel m, const T* __restrict__ p, const T* x1, const T* hbar,
+                                                           T* dl, const int* mask, int64_t B, int btile) {
+    constexpr int NW = H * (G + 1);
+    __shared__ T hb[W_PT][W_HP];
+    const int tid = threadIdx.x, n = m.n;
+    const int b0 = blockIdx.y * btile, b1 = (int)min((int64_t)(b0 + btile), B);
+    for (int v = tid; v < (b1 - b0) * W_HP; v += W_BT) hb[v / W_HP][v % W_HP] = (v % W_HP) < H ? hbar[(int64_t)(b0 + v / W_HP) * W_HP + v % W_HP] : T(0);
+    __syncthreads();
+    const int i = blockIdx.x * W_BT + tid;
+    if (i >= n) return;
+    T w[NW];
+    {
+        const T* c = p + m.offC1 + (int64_t)i * G * H;
+#pragma unroll
+        for (int k = 0; k < G * H; ++k) w[k] = c[k];
+        const T* ww = p + m.offW1 + (int64_t)i * H;
+#pragma unroll
+        for (int k = 0; k < H; ++k) w[G * H + k] = ww[k];
+    }
+    const T inv_h = (T)m.inv_h1;
+    for (int b = b0; b < b1; ++b) {
+        if (mask && !mask[b]) continue;
+        const T* yb = hb[b - b0];
+        const T x = x1[(int64_t)b * n + i];
+        const T xn = normalize_rt(m.norm1, x);
+        T xnbar = T(0);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const T a = (xn - (T)m.grid1[g]) * inv_h;
+            const T y = kexp(-a * a);
+            const T db = T(-2) * a * y;
+            T bbar = T(0);
+#pragma unroll
+            for (int o = 0; o < H; ++o) bbar += w[g * H + o] * yb[o];
+            xnbar += db * inv_h * bbar;
+        }
+        T xb = xnbar * normalize_deriv_rt(m.norm1, xn);
+        T s, ds; swish_both(x, s, ds);
+        T sbar = T(0);
+#pragma unroll
+        for (int o = 0; o < H; ++o) sbar += w[G * H + o] * yb[o];
+        xb += sbar * ds;
+        dl[(int64_t)b * n + i] = -xb;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// step-end pass over the gradient state g[b] (and the initdt norms of dg/dt)
+//   MODE 0: g_new = g_old + sum_s wb_s k_s, es += (sum_s wbt_s k_s / (abstol + max(|g_old|,|g_new|) reltol))^2
+//   MODE 1: es += (k_0 / abstol)^2                 MODE 2: es += ((k_1 - k_0) / abstol)^2
+// with k_s[(i,q),o] = ybar_s[o] * c_q(x_s[i]) rebuilt from the stage records.
+// ---------------------------------------------------------------------------------------------------------
+template <class T> struct WideGp {
+    const T* x1;    // [7][B][n]     layer-1 inputs  (y at the stage times)
+    const T* yb1;   // [7][B][W_HP]  layer-1 output cotangents
+    const T* x2;    // [7][B][W_HP]  layer-2 inputs  (hidden)
+    const T* yb2;   // [7][B][n]     layer-2 output cotangents (lambda at the stages)
+    T* g;           // [B][2][np]
+    const int* cur; const T* h; const int* mask;
+    T abstol, reltol;
+    T* es_part; int npart, off;   // es_part[b * npart + off + block]
+};
+
+template <class T> __device__ __forceinline__ void gp_finalize(const T* gold, T* gnew, int64_t j, T vb, T vt, T abstol, T reltol, T& es) {
+    const T g0 = gold[j];
+    const T g1 = g0 + vb;
+    const T sc = abstol + kmax(kabs(g0), kabs(g1)) * reltol;
+    const T r = vt / sc;
+    es += r * r;
+    gnew[j] = g1;
+}
+
+template <class T, int H, int G, int MODE>
+__global__ void __launch_bounds__(W_ET) wide_gp1_kernel(const __grid_constant__ WideModel m, const WideGp<T> a, int64_t B) {
+    constexpr int NQ = G + 1, NS = MODE == 0 ? 7 : (MODE == 1 ? 1 : 2);
+    __shared__ T A[H][8], At[H][8];
+    __shared__ T sred[33];
+    const int b = blockIdx.y, tid = threadIdx.x, n = m.n;
+    if (a.mask && !a.mask[b]) return;
+    if (tid < H * 8) {
+        const int o = tid / 8, s = tid % 8;
+        T v = T(0), vt = T(0);
+        if (s < NS) {
+            const T yb = a.yb1[((int64_t)s * B + b) * W_HP + o];
+            if (MODE == 0) { const T hh = a.h[b]; v = (-hh * Tab<T>::b(s)) * yb; vt = (-hh * Tab<T>::bt(s)) * yb; }
+            else v = yb;
+        }
+        A[o][s] = v; At[o][s] = vt;
+    }
+    __syncthreads();
+    const T* gold = nullptr; T* gnew = nullptr;
+    if (MODE == 0) { const int cur = a.cur[b]; gold = a.g + ((int64_t)b * 2 + cur) * m.np; gnew = a.g + ((int64_t)b * 2 + (cur ^ 1)) * m.np; }
+    const T inv_h = (T)m.inv_h1;
+    T es = T(0);
+    const int64_t nitem = (int64_t)n * NQ;
+    for (int64_t item = (int64_t)blockIdx.x * W_ET + tid; item < nitem; item += (int64_t)gridDim.x * W_ET) {
+        const int i = (int)(item / NQ), q = (int)(item - (int64_t)i * NQ);
+        T c[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const T x = a.x1[((int64_t)s * B + b) * n + i];
+            if (q < G) { const T aa = (normalize_rt(m.norm1, x) - (T)m.grid1[q]) * inv_h; c[s] = kexp(-aa * aa); }
+            else swish_fwd(x, c[s]);
+        }
+        const int64_t row = q < G ? m.offC1 + ((int64_t)i * G + q) * H : m.offW1 + (int64_t)i * H;
+#pragma unroll
+        for (int o = 0; o < H; ++o) {
+            if (MODE == 0) {
+                T vb = T(0), vt = T(0);
+#pragma unroll
+                for (int s = 0; s < 7; ++s) { vb += A[o][s] * c[s]; vt += At[o][s] * c[s]; }
+                gp_finalize<T>(gold, gnew, row + o, vb, vt, a.abstol, a.reltol, es);
+            } else if (MODE == 1) {
+                const T x1 = (A[o][0] * c[0]) / a.abstol;
+                es += x1 * x1;
+            } else {
+                const T x2 = (A[o][1] * c[1] - A[o][0] * c[0]) / a.abstol;
+                es += x2 * x2;
+            }
+        }
+    }
+    es = wblock_sum<T>(es, sred);
+    if (tid == 0) a.es_part[(int64_t)b * a.npart + a.off + blockIdx.x] = es;
+}
+
+// layer 2: grid (ceil(n / W_BT), H, B); thread = output unit o, block row j = hidden unit
+template <class T, int H, int G, int MODE>
+__global__ void __launch_bounds__(W_BT) wide_gp2_kernel(const __grid_constant__ WideModel m, const WideGp<T> a, int64_t B) {
+    constexpr int NQ = G + 1, NS = MODE == 0 ? 7 : (MODE == 1 ? 1 : 2);
+    __shared__ __align__(16) T F[NQ][8];
+    __shared__ T sred[33];
+    const int b = blockIdx.z, j = blockIdx.y, tid = threadIdx.x, n = m.n;
+    if (a.mask && !a.mask[b]) return;
+    if (tid < 8) {
+        T c[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) c[q] = T(0);
+        if (tid < NS) w_features<T, G>(m.norm2, (T)m.inv_h2, m.grid2, a.x2[((int64_t)tid * B + b) * W_HP + j], c);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) F[q][tid] = c[q];
+    }
+    __syncthreads();
+    const int o = blockIdx.x * W_BT + tid;
+    T es = T(0);
+    if (o < n) {
+        T al[NS], alt[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const T yb = a.yb2[((int64_t)s * B + b) * n + o];
+            if (MODE == 0) { const T hh = a.h[b]; al[s] = (-hh * Tab<T>::b(s)) * yb; alt[s] = (-hh * Tab<T>::bt(s)) * yb; }
+            else { al[s] = yb; alt[s] = T(0); }
+        }
+        const T* gold = nullptr; T* gnew = nullptr;
+        if (MODE == 0) { const int cur = a.cur[b]; gold = a.g + ((int64_t)b * 2 + cur) * m.np; gnew = a.g + ((int64_t)b * 2 + (cur ^ 1)) * m.np; }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int64_t row = q < G ? m.offC2 + (int64_t)(j * G + q) * n : m.offW2 + (int64_t)j * n;
+            if (MODE == 0) {
+                T vb = T(0), vt = T(0);
+#pragma unroll
+                for (int s = 0; s < 7; ++s) { vb += al[s] * F[q][s]; vt += alt[s] * F[q][s]; }
+                gp_finalize<T>(gold, gnew, row + o, vb, vt, a.abstol, a.reltol, es);
+            } else if (MODE == 1) {
+                const T x1 = (al[0] * F[q][0]) / a.abstol;
+                es += x1 * x1;
+            } else {
+                const T x2 = (al[1] * F[q][1] - al[0] * F[q][0]) / a.abstol;
+                es += x2 * x2;
+            }
+        }
+    }
+    es = wblock_sum<T>(es, sred);
+    if (tid == 0) a.es_part[(int64_t)b * a.npart + a.off + (int64_t)j * gridDim.x + blockIdx.x] = es;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// elementwise kernels over [B][n]; grid (ceil(n / W_ET), B)
+// ---------------------------------------------------------------------------------------------------------
+// norms of initdt: MODE 1: v0 = (u/sk)^2, v1 = (k0/sk)^2 ; MODE 2: v1 = ((k1-k0)/sk)^2    sk = abstol + |u| reltol
+template <class T, int MODE>
+__global__ void __launch_bounds__(W_ET) wide_norm_kernel(const T* u, const T* k0, const T* k1, int n, T abstol, T reltol, const int* mask,
+                                                         T* part0, T* part1, int npart, int off) {
+    __shared__ T sred[33];
+    const int b = blockIdx.y, i = blockIdx.x * W_ET + threadIdx.x;
+    if (mask && !mask[b]) return;
+    T v0 = T(0), v1 = T(0);
+    if (i < n) {
+        const int64_t e = (int64_t)b * n + i;
+        const T sk = abstol + kabs(u[e]) * reltol;
+        if (MODE == 1) { const T x0 = u[e] / sk, x1 = k0[e] / sk; v0 = x0 * x0; v1 = x1 * x1; }
+        else { const T x = (k1[e] - k0[e]) / sk; v1 = x * x; }
+    }
+    if (MODE == 1) { v0 = wblock_sum<T>(v0, sred); if (threadIdx.x == 0) part0[(int64_t)b * npart + off + blockIdx.x] = v0; }
+    v1 = wblock_sum<T>(v1, sred);
+    if (threadIdx.x == 0) part1[(int64_t)b * npart + off + blockIdx.x] = v1;
+}
+
+// embedded error of the state part: es += ((h sum_j bt_j k_j) / (abstol + max(|uprev|,|unew|) reltol))^2
+template <class T>
+__global__ void __launch_bounds__(W_ET) wide_err_kernel(const T* uprev, const T* unew, const T* k, int n, int64_t B, const T* h, T abstol, T reltol,
+                                                        const int* mask, T* es_part, int npart, int off) {
+    __shared__ T sred[33];
+    const int b = blockIdx.y, i = blockIdx.x * W_ET + threadIdx.x;
+    if (mask && !mask[b]) return;
+    T es = T(0);
+    if (i < n) {
+        const int64_t e = (int64_t)b * n + i;
+        T ut = T(0);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) ut += Tab<T>::bt(j) * k[(int64_t)j * B * n + e];
+        const T sc = abstol + kmax(kabs(uprev[e]), kabs(unew[e])) * reltol;
+        const T r = (h[b] * ut) / sc;
+        es = r * r;
+    }
+    es = wblock_sum<T>(es, sred);
+    if (threadIdx.x == 0) es_part[(int64_t)b * npart + off + blockIdx.x] = es;
+}
+
+template <class T> struct WideFwd {
+    const T* u0; T* uprev; T* unew; T* k;           // k: [7][B][n]
+    T* h;                                            // [B] current step
+    double t0, t1; const double* saveat; int nsave; T abstol, reltol; int maxiters;
+    T* out; const T* target; T* dg; double* loss_sum;
+    double* rec_t; T* rec_dt; T* rec; int cap;      // dense record (null rec: forward-only solve)
+    T* part0; T* part1; int npart;                   // [B][npart]
+    kanode_stats* stats; int* nsteps; int* retcode;
+};
+
+// block per IC: sum the partials in a fixed order (result in thread 0)
+template <class T> __device__ __forceinline__ T sum_partials(const T* part, int cnt, T* sred) {
+    T s = T(0);
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) s += part[k];
+    return wblock_sum<T>(s, sred);
+}
+
+template <class T> __device__ void wf_begin(const WideCtl& c, const WideFwd<T>& a, int b) {
+    if (!c.active[b]) return;
+    const double t = c.t[b], t0 = a.t0, t1 = a.t1;
+    if (!(t < t1)) { c.active[b] = 0; return; }
+    const double dtmax = fabs(t1 - t0), dtmin0 = fmax(eps_of(t0), eps_of(t1));
+    double dt = c.dt[b];
+    int iter = c.iter[b];
+    const bool accept = c.accept[b] != 0;
+    if (iter > 0) { if (!accept) dt = dt / fmin(1.0 / Ctrl::qmin, c.q11[b] / Ctrl::gamma); else dt = c.dtpropose[b]; }
+    ++iter;
+    const double dtmin_t = fmax(eps_of(t), dtmin0);
+    dt = fmin(fmax(fmin(fabs(dt), dtmax), dtmin_t), t1 - t);
+    int ret = RET_SUCCESS;
+    if (iter > a.maxiters) ret = RET_MAXITERS;
+    else if (!(dt > dtmin_t) && (t + dt < t1 || !accept) && iter > 1) ret = RET_DTMIN;
+    else if (dt != dt) ret = RET_UNSTABLE;
+    c.iter[b] = iter; c.dt[b] = dt;
+    if (ret != RET_SUCCESS) { c.ret[b] = ret; c.active[b] = 0; c.fail_now[b] = 1; return; }
+    a.h[b] = (T)dt;
+}
+
+// forward control: finish the attempt just evaluated (error norm -> accept / reject), then open the next one
+template <class T>
+__global__ void __launch_bounds__(128) wide_fwd_ctl_kernel(const WideCtl c, const WideFwd<T> a, int n, int phase) {
+    __shared__ T sred[33];
+    const int b = blockIdx.x;
+    if (phase == 0) {            // after k1 = f(u0): d0, d1 -> dt0
+        const T v0 = sum_partials<T>(a.part0 + (int64_t)b * a.npart, a.npart, sred);
+        const T v1 = sum_partials<T>(a.part1 + (int64_t)b * a.npart, a.npart, sred);
+        if (threadIdx.x) return;
+        const double d0 = sqrt((double)v0 / n), d1 = sqrt((double)v1 / n), dtmax = fabs(a.t1 - a.t0);
+        double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
+        dt0 = fmin(dt0, dtmax);
+        c.d1[b] = d1; c.dt0[b] = dt0;
+        a.h[b] = (T)dt0;
+        return;
+    }
+    if (phase == 1) {            // after k2 = f(u0 + dt0 k1): d2 -> dt; open the first attempt
+        const T s2 = sum_partials<T>(a.part1 + (int64_t)b * a.npart, a.npart, sred);
+        if (threadIdx.x) return;
+        const double dt0 = c.dt0[b], d1 = c.d1[b], dtmax = fabs(a.t1 - a.t0), dtmin0 = fmax(eps_of(a.t0), eps_of(a.t1));
+        const double d2 = sqrt((double)s2 / n) / dt0, mx = fmax(d1, d2);
+        const double dt1 = (mx <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / 5.0);
+        c.dt[b] = fmax(dtmin0, fmin(fmin(100.0 * dt0, dt1), dtmax));
+        c.nf[b] = 3;
+        wf_begin<T>(c, a, b);
+        return;
+    }
+    if (!c.active[b]) { if (threadIdx.x == 0) { c.acc_now[b] = 0; c.fail_now[b] = 0; } return; }
+    const T es = sum_partials<T>(a.part0 + (int64_t)b * a.npart, a.npart, sred);
+    if (threadIdx.x) return;
+    c.acc_now[b] = 0; c.fail_now[b] = 0;
+    c.nf[b] += 6;
+    const double EEst = (double)ksqrt(es / T(n));
+    if (EEst != EEst) { c.ret[b] = RET_UNSTABLE; c.active[b] = 0; c.fail_now[b] = 1; return; }
+    double q11 = c.q11[b];
+    const double q = pi_q(EEst, c.qold[b], q11);
+    c.q11[b] = q11;
+    const bool accept = EEst <= 1.0;
+    c.accept[b] = accept;
+    if (accept) {
+        const double t = c.t[b], dt = c.dt[b], t1 = a.t1, dtmax = fabs(a.t1 - a.t0), dtmin0 = fmax(eps_of(a.t0), eps_of(a.t1));
+        ++c.naccept[b];
+        c.qold[b] = fmax(EEst, Ctrl::qoldinit);
+        const double dtnew = dt / q;
+        double tnew = t + dt;
+        if (fabs(tnew - t1) < 100.0 * eps_of(fmax(fabs(t), fabs(t1)))) tnew = t1;
+        c.dtpropose[b] = fmax(fmin(dtmax, fabs(dtnew)), fmax(eps_of(tnew), dtmin0));
+        if (a.rec) {
+            const int nrec = c.nrec[b];
+            if (nrec >= a.cap) { c.ret[b] = RET_OVERFLOW; c.active[b] = 0; c.fail_now[b] = 1; return; }
+            a.rec_t[(int64_t)b * a.cap + nrec] = t;
+            a.rec_dt[(int64_t)b * a.cap + nrec] = a.h[b];
+            c.nrec[b] = nrec + 1;
+        }
+        int sidx = c.sidx[b];
+        c.s_lo[b] = sidx;
+        while (sidx < a.nsave && a.saveat[sidx] <= tnew) ++sidx;
+        c.s_hi[b] = sidx; c.sidx[b] = sidx;
+        c.told[b] = t; c.dtold[b] = dt; c.t[b] = tnew;
+        c.acc_now[b] = 1;
+    } else {
+        ++c.nreject[b];
+    }
+    wf_begin<T>(c, a, b);
+}
+
+// initial state of every IC
+template <class T>
+__global__ void __launch_bounds__(W_ET) wide_fwd_init_kernel(const WideCtl c, const WideFwd<T> a, int n) {
+    const int b = blockIdx.y, i = blockIdx.x * W_ET + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        c.t[b] = a.t0; c.dt[b] = 0.0; c.dtpropose[b] = 0.0; c.qold[b] = Ctrl::qoldinit; c.q11[b] = 1.0;
+        c.iter[b] = 0; c.accept[b] = 0; c.acc_now[b] = 0; c.fail_now[b] = 0; c.active[b] = a.t0 < a.t1 ? 1 : 0;
+        c.sidx[b] = a.t0 < a.t1 ? 0 : a.nsave; c.s_lo[b] = 0; c.s_hi[b] = 0; c.nrec[b] = 0; c.naccept[b] = 0; c.nreject[b] = 0; c.nf[b] = 1; c.ret[b] = RET_SUCCESS;
+    }
+    if (i >= n) return;
+    const T v = a.u0[(int64_t)b * n + i];
+    a.uprev[(int64_t)b * n + i] = v;
+    if (a.t0 == a.t1 && a.out) for (int s = 0; s < a.nsave; ++s) a.out[((int64_t)b * a.nsave + s) * n + i] = v;
+}
+
+// after the control decision: dense record, outputs at the save times passed, loss, state shift
+template <class T>
+__global__ void __launch_bounds__(W_ET) wide_fwd_accept_kernel(const WideCtl c, const WideFwd<T> a, int n, int64_t B) {
+    __shared__ double dred[33];
+    const int b = blockIdx.y, i = blockIdx.x * W_ET + threadIdx.x;
+    const bool acc = c.acc_now[b] != 0, failed = c.fail_now[b] != 0;
+    if (!acc && !failed) return;
+    double lsum = 0.0;
+    if (i < n) {
+        const int64_t e = (int64_t)b * n + i;
+        if (acc) {
+            const double told = c.told[b], dtold = c.dtold[b];
+            const T h = (T)dtold;
+            const T up = a.uprev[e];
+            T kk[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) kk[j] = a.k[(int64_t)j * B * n + e];
+            if (a.rec) {
+                T* r = a.rec + ((int64_t)b * a.cap + (c.nrec[b] - 1)) * 8 * (int64_t)n;
+                r[i] = up;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) r[(int64_t)(1 + j) * n + i] = kk[j];
+            }
+            for (int s = c.s_lo[b]; s < c.s_hi[b]; ++s) {
+                const T th = (T)((a.saveat[s] - told) / dtold);
+                T bw[7]; interp_weights(th, bw);
+                T accv = T(0);
+#pragma unroll
+                for (int j = 0; j < 7; ++j) accv += bw[j] * kk[j];
+                const T v = up + h * accv;
+                const int64_t o = ((int64_t)b * a.nsave + s) * n + i;
+                if (a.out) a.out[o] = v;
+                if (a.rec) {
+                    const T d = v - a.target[o];
+                    lsum += (double)d * (double)d;
+                    a.dg[o] = (T(2) / (T)((double)n * a.nsave)) * d;
+                }
+            }
+            a.uprev[e] = a.unew[e];
+            a.k[e] = kk[6];
+        }
+        if (failed)
+            for (int s = c.sidx[b]; s < a.nsave; ++s) {
+                const int64_t o = ((int64_t)b * a.nsave + s) * n + i;
+                if (a.out) a.out[o] = T(NAN);
+                if (a.rec) a.dg[o] = T(0);
+            }
+    }
+    if (a.rec && acc && c.s_hi[b] > c.s_lo[b]) {
+        const double tot = wblock_sum<double>(lsum, dred);
+        if (threadIdx.x == 0 && tot != 0.0) atomicAdd(a.loss_sum, tot);
+    }
+}
+
+template <class T>
+__global__ void wide_fwd_finish_kernel(const WideCtl c, const WideFwd<T> a, int64_t B) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (a.stats) a.stats[b] = kanode_stats{c.naccept[b], c.nreject[b], c.nf[b], c.ret[b]};
+    if (a.nsteps) { a.nsteps[b] = c.nrec[b]; a.retcode[b] = c.ret[b]; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward (interpolating adjoint) control
+// ---------------------------------------------------------------------------------------------------------
+template <class T> struct WideBwd {
+    T* lam;            // [B][n] lambda at the start of the attempt (== lprev of the generic kernel)
+    T* kl;             // [7][B][n]
+    T* x1; T* yb1; T* x2; T* yb2;      // stage records, 7 slots each
+    T* h; T* th; T* hd;                // [B], [7][B], [7][B]
+    double t0, t1; const double* saveat; int nsave; T abstol, reltol; int maxiters;
+    const double* rec_t; const T* rec_dt; const T* rec; int cap; const int* nsteps; const int* retcode;
+    const T* dg; T* g; long long np;
+    T* part0; T* part1; int npart;
+    T* du0; kanode_stats* stats;
+};
+
+template <class T> __device__ __forceinline__ void wb_stage_time(const WideCtl& c, const WideBwd<T>& a, int b, int64_t B, int s, double ts) {
+    const double* rt = a.rec_t + (int64_t)b * a.cap;
+    const int nsteps = a.nsteps[b];
+    int ridx = nsteps - 1;
+    while (ts < rt[ridx] && ridx > 0) --ridx;
+    while (ridx + 1 < nsteps && ts >= rt[ridx + 1]) ++ridx;
+    const T hd = a.rec_dt[(int64_t)b * a.cap + ridx];
+    c.ridx[(int64_t)s * B + b] = ridx;
+    a.hd[(int64_t)s * B + b] = hd;
+    a.th[(int64_t)s * B + b] = (T)((ts - rt[ridx]) / (double)hd);
+}
+
+template <class T> __device__ void wb_begin(const WideCtl& c, const WideBwd<T>& a, int b, int64_t B) {
+    c.do_s0[b] = 0;
+    if (!c.active[b]) return;
+    const double t = c.t[b], t0 = a.t0, t1 = a.t1;
+    if (!(t > t0)) { c.active[b] = 0; return; }
+    const double dtmax = fabs(t1 - t0), dtmin0 = fmax(eps_of(t0), eps_of(t1));
+    double dt = c.dt[b];
+    int iter = c.iter[b];
+    const bool accept = c.accept[b] != 0;
+    if (iter > 0) { if (!accept) dt = dt / fmin(1.0 / Ctrl::qmin, c.q11[b] / Ctrl::gamma); else dt = c.dtpropose[b]; }
+    ++iter;
+    const int sp = c.sidx[b];
+    const double tstop = (sp >= 0) ? fmax(a.saveat[sp], t0) : t0;
+    const double dtmin_t = fmax(eps_of(t), dtmin0);
+    dt = fmin(fmax(fmin(fabs(dt), dtmax), dtmin_t), t - tstop);
+    int ret = RET_SUCCESS;
+    if (iter > a.maxiters) ret = RET_MAXITERS;
+    else if (!(dt > dtmin_t) && (t - dt > tstop || !accept) && iter > 1) ret = RET_DTMIN;
+    else if (dt != dt) ret = RET_UNSTABLE;
+    c.iter[b] = iter; c.dt[b] = dt;
+    if (ret != RET_SUCCESS) { c.ret[b] = ret; c.active[b] = 0; return; }
+    a.h[b] = (T)(-dt);
+    c.do_s0[b] = c.modified[b];
+    c.modified[b] = 0;
+    for (int s = 0; s < 7; ++s) wb_stage_time<T>(c, a, b, B, s, t - tab_c(s) * dt);
+}
+
+template <class T>
+__global__ void __launch_bounds__(128) wide_bwd_ctl_kernel(const WideCtl c, const WideBwd<T> a, int n, int64_t B, int phase) {
+    __shared__ T sred[33];
+    const int b = blockIdx.x;
+    const int NZ = n + (int)a.np;
+    if (phase == -1) {           // state at t1: jumps at the end time (PresetTimeCallback fires at init), stage-0 time
+        if (threadIdx.x) return;
+        const int ok = a.retcode[b] == RET_SUCCESS && a.nsteps[b] > 0;
+        c.t[b] = a.t1; c.dt[b] = 0.0; c.dtpropose[b] = 0.0; c.qold[b] = Ctrl::qoldinit; c.q11[b] = 1.0;
+        c.iter[b] = 0; c.accept[b] = 0; c.acc_now[b] = 0; c.fail_now[b] = 0; c.active[b] = ok; c.modified[b] = 0; c.do_s0[b] = ok;
+        c.nrec[b] = 0; c.naccept[b] = 0; c.nreject[b] = 0; c.nf[b] = 0; c.ret[b] = a.retcode[b]; c.cur[b] = 0;
+        int sp = a.nsave - 1;
+        c.s_hi[b] = sp;
+        while (sp >= 0 && a.saveat[sp] == a.t1) --sp;
+        c.s_lo[b] = sp + 1; c.sidx[b] = sp;
+        if (ok) { wb_stage_time<T>(c, a, b, B, 0, a.t1); a.h[b] = T(0); }
+        return;
+    }
+    if (phase == 0) {            // d0, d1 of initdt on the augmented state -> dt0, stage-1 time
+        if (!c.active[b]) return;
+        const T v0 = sum_partials<T>(a.part0 + (int64_t)b * a.npart, a.npart, sred);
+        const T v1 = sum_partials<T>(a.part1 + (int64_t)b * a.npart, a.npart, sred);
+        if (threadIdx.x) return;
+        const double d0 = sqrt((double)v0 / NZ), d1 = sqrt((double)v1 / NZ), dtmax = fabs(a.t1 - a.t0);
+        double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
+        dt0 = fmin(dt0, dtmax);
+        c.d1[b] = d1; c.dt0[b] = dt0;
+        a.h[b] = -(T)dt0;
+        wb_stage_time<T>(c, a, b, B, 1, a.t1 - dt0);
+        return;
+    }
+    if (phase == 1) {
+        if (!c.active[b]) return;
+        const T s2 = sum_partials<T>(a.part1 + (int64_t)b * a.npart, a.npart, sred);
+        if (threadIdx.x) return;
+        const double dt0 = c.dt0[b], d1 = c.d1[b], dtmax = fabs(a.t1 - a.t0), dtmin0 = fmax(eps_of(a.t0), eps_of(a.t1));
+        const double d2 = sqrt((double)s2 / NZ) / dt0, mx = fmax(d1, d2);
+        const double dt1 = (mx <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / 5.0);
+        c.dt[b] = fmax(dtmin0, fmin(fmin(100.0 * dt0, dt1), dtmax));
+        c.nf[b] = 3;
+        wb_begin<T>(c, a, b, B);
+        return;
+    }
+    if (!c.active[b]) { if (threadIdx.x == 0) { c.acc_now[b] = 0; c.do_s0[b] = 0; } return; }
+    const T es = sum_partials<T>(a.part0 + (int64_t)b * a.npart, a.npart, sred);
+    if (threadIdx.x) return;
+    c.acc_now[b] = 0;
+    c.nf[b] += c.do_s0[b] ? 7 : 6;
+    const double EEst = (double)ksqrt(es / T(NZ));
+    if (EEst != EEst) { c.ret[b] = RET_UNSTABLE; c.active[b] = 0; c.do_s0[b] = 0; return; }
+    double q11 = c.q11[b];
+    const double q = pi_q(EEst, c.qold[b], q11);
+    c.q11[b] = q11;
+    const bool accept = EEst <= 1.0;
+    c.accept[b] = accept;
+    if (accept) {
+        const double t = c.t[b], dt = c.dt[b], t0 = a.t0, dtmax = fabs(a.t1 - a.t0), dtmin0 = fmax(eps_of(a.t0), eps_of(a.t1));
+        int sp = c.sidx[b];
+        const double tstop = (sp >= 0) ? fmax(a.saveat[sp], t0) : t0;
+        ++c.naccept[b];
+        c.qold[b] = fmax(EEst, Ctrl::qoldinit);
+        const double dtnew = dt / q;
+        double tnew = t - dt;
+        if (fabs(tnew - tstop) < 100.0 * eps_of(fmax(fabs(t), fabs(tstop)))) tnew = tstop;
+        c.dtpropose[b] = fmax(fmin(dtmax, fabs(dtnew)), fmax(eps_of(tnew), dtmin0));
+        c.t[b] = tnew;
+        c.cur[b] ^= 1;
+        c.s_hi[b] = sp;
+        while (sp >= 0 && a.saveat[sp] == tnew) --sp;
+        c.s_lo[b] = sp + 1; c.sidx[b] = sp;
+        c.modified[b] = c.s_hi[b] >= c.s_lo[b];
+        c.acc_now[b] = 1;
+    } else {
+        ++c.nreject[b];
+    }
+    wb_begin<T>(c, a, b, B);
+}
+
+// lambda at t1 (jumps of the save times equal to t1); g[b][0] is zeroed by the host
+template <class T>
+__global__ void __launch_bounds__(W_ET) wide_bwd_init_kernel(const WideCtl c, const WideBwd<T> a, int n) {
+    const int b = blockIdx.y, i = blockIdx.x * W_ET + threadIdx.x;
+    if (i >= n) return;
+    T l = T(0);
+    if (c.active[b]) for (int sp = c.s_hi[b]; sp >= c.s_lo[b]; --sp) l += a.dg[((int64_t)b * a.nsave + sp) * n + i];
+    a.lam[(int64_t)b * n + i] = l;
+}
+
+// accepted attempt: lambda <- lambda_new (+ jumps at the save time just reached); FSAL shift of slot 6 -> slot 0
+template <class T>
+__global__ void __launch_bounds__(W_ET) wide_bwd_accept_kernel(const WideCtl c, const WideBwd<T> a, int n, int64_t B) {
+    const int b = blockIdx.y, i = blockIdx.x * W_ET + threadIdx.x;
+    if (!c.acc_now[b]) return;
+    const bool modified = c.modified[b] != 0;
+    if (!modified && blockIdx.x == 0 && threadIdx.x < W_HP) {
+        a.x2[(int64_t)b * W_HP + threadIdx.x] = a.x2[((int64_t)6 * B + b) * W_HP + threadIdx.x];
+        a.yb1[(int64_t)b * W_HP + threadIdx.x] = a.yb1[((int64_t)6 * B + b) * W_HP + threadIdx.x];
+    }
+    if (i >= n) return;
+    const int64_t e = (int64_t)b * n + i, e6 = ((int64_t)6 * B + b) * n + i;
+    const T lnew = a.yb2[e6];
+    T l = lnew;
+    for (int sp = c.s_hi[b]; sp >= c.s_lo[b]; --sp) l += a.dg[((int64_t)b * a.nsave + sp) * n + i];
+    a.lam[e] = l;
+    if (!modified) { a.kl[e] = a.kl[e6]; a.x1[e] = a.x1[e6]; a.yb2[e] = lnew; }
+}
+
+template <class T>
+__global__ void __launch_bounds__(W_ET) wide_bwd_finish_kernel(const WideCtl c, const WideBwd<T> a, int n) {
+    const int b = blockIdx.y, i = blockIdx.x * W_ET + threadIdx.x;
+    const bool ran = a.retcode[b] == RET_SUCCESS && a.nsteps[b] > 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats)
+        a.stats[b] = ran ? kanode_stats{c.naccept[b], c.nreject[b], c.nf[b], c.ret[b]} : kanode_stats{0, 0, 0, a.retcode[b]};
+    if (i < n && a.du0) a.du0[(int64_t)b * n + i] = ran ? a.lam[(int64_t)b * n + i] : T(0);
+}
+
+// out[j] = sum over the ICs whose adjoint succeeded of g[b][cur[b]][j]
+template <class T>
+__global__ void __launch_bounds__(256) wide_grad_reduce_kernel(const T* g, const int* cur, const int* ret, long long np, int64_t B, T* out) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= np) return;
+    double acc = 0.0;
+    for (int64_t b = 0; b < B; ++b)
+        if (ret[b] == RET_SUCCESS) acc += (double)g[(b * 2 + cur[b]) * np + j];
+    out[j] = (T)acc;
+}
+
+// =========================================================================================================
+// host side
+// =========================================================================================================
+struct WideKey { int H, G; };
+inline bool wide_match(const kanode_desc& d, WideKey& k) {
+    if (d.rhs_kind != KANODE_RHS_CHAIN || d.n_layers != 2) return false;
+    const kanode_layer_desc &a = d.layers[0], &b = d.layers[1];
+    if (a.basis != KANODE_BASIS_RBF || b.basis != KANODE_BASIS_RBF || !a.use_base_act || !b.use_base_act) return false;
+    if (a.grid_len != b.grid_len || a.grid_len > 16) return false;
+    if (a.in_dims != b.out_dims || a.in_dims < 16) return false;     // narrow states belong to the thread-per-trajectory kernels
+    k = WideKey{a.out_dims, a.grid_len};
+    return (k.H == 10) && (k.G == 5 || k.G == 10);
+}
+
+inline WideModel wide_model(const kanode_handle* h) {
+    const kanode_desc& d = h->desc;
+    WideModel m{};
+    const kanode_layer_desc &a = d.layers[0], &b = d.layers[1];
+    m.n = d.n_state; m.norm1 = a.normalizer; m.norm2 = b.normalizer;
+    m.inv_h1 = 1.0f / a.denominator; m.inv_h2 = 1.0f / b.denominator;
+    for (int g = 0; g < a.grid_len; ++g) { m.grid1[g] = grid_point(a, g); m.grid2[g] = grid_point(b, g); }
+    const long long n = m.n, H = a.out_dims, G = a.grid_len;
+    m.offC1 = 0; m.offW1 = n * G * H; m.offC2 = m.offW1 + n * H; m.offW2 = m.offC2 + H * G * n;
+    m.np = (long long)h->np;
+    return m;
+}
+
+struct WideLaunch { int P, nchunk, bt_red, nbt_red, bt_par, nbt_par, uc, ec; };
+inline WideLaunch wide_launch(int n, int64_t B, int GB) {
+    WideLaunch L{};
+    L.uc = (n + W_BT - 1) / W_BT;
+    L.ec = (n + W_ET - 1) / W_ET;
+    L.P = (L.uc + W_MAXCH - 1) / W_MAXCH;
+    L.nchunk = (L.uc + L.P - 1) / L.P;
+    int bt = (int)((B * L.nchunk + 295) / 296);
+    L.bt_red = bt < 1 ? 1 : (bt > GB ? GB : bt);
+    L.nbt_red = (int)((B + L.bt_red - 1) / L.bt_red);
+    bt = (int)((B * L.uc + 591) / 592);
+    L.bt_par = bt < 1 ? 1 : (bt > W_PT ? W_PT : bt);
+    L.nbt_par = (int)((B + L.bt_par - 1) / L.bt_par);
+    return L;
+}
+
+// carve a byte arena
+struct Arena {
+    char* p; size_t off = 0;
+    template <class U> U* take(size_t count) { off = (off + 255) / 256 * 256; U* r = reinterpret_cast<U*>(p + off); off += sizeof(U) * count; return r; }
+};
+
+inline size_t wide_ctl_bytes(int64_t B) { return (size_t)(W_NCTL_D * 8 + W_NCTL_I * 4) * B + 64 * 256; }
+inline WideCtl wide_ctl_carve(Arena& A, int64_t B) {
+    WideCtl c{};
+    double** dd[] = {&c.t, &c.dt, &c.dtpropose, &c.qold, &c.q11, &c.told, &c.dtold, &c.d0, &c.d1, &c.dt0};
+    for (auto pp : dd) *pp = A.take<double>(B);
+    int** ii[] = {&c.iter, &c.accept, &c.acc_now, &c.fail_now, &c.active, &c.modified, &c.do_s0, &c.sidx, &c.s_lo, &c.s_hi, &c.nrec,
+                  &c.naccept, &c.nreject, &c.nf, &c.ret, &c.cur};
+    for (auto pp : ii) *pp = A.take<int>(B);
+    c.ridx = A.take<int>(7 * B);
+    return c;
+}
+
+// wait until no IC is active; polls the device flags (the host only decides how many more attempts to enqueue)
+inline int wide_any_active(kanode_handle* h, const int* d_active, int64_t B, bool& any) {
+    std::vector<int> act((size_t)B);
+    CK(h, cudaMemcpyAsync(act.data(), d_active, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    any = false;
+    for (int64_t b = 0; b < B; ++b) any |= act[(size_t)b] != 0;
+    return 0;
+}
+
+template <class T, int H, int G>
+int wide_forward(kanode_handle* h, const WideModel& m, const T* p, WideFwd<T> a, int64_t B, bool dense, WideCtl* ctl_out) {
+    constexpr int GB = sizeof(T) == 4 ? 8 : 4;
+    const int n = m.n;
+    const WideLaunch L = wide_launch(n, B, GB);
+    a.npart = L.ec;
+    const size_t nB = (size_t)n * B;
+    size_t bytes = wide_ctl_bytes(B) + sizeof(T) * (9 * nB + (size_t)B * (1 + W_HP + 2 * L.ec) + (size_t)L.nchunk * B * H) + sizeof(unsigned) * (size_t)B + 16 * 256;
+    char* base = nullptr;
+    ENSURE(h, W_WIDE_F, bytes, base);
+    Arena A{base};
+    WideCtl c = wide_ctl_carve(A, B);
+    a.uprev = A.take<T>(nB); a.unew = A.take<T>(nB); a.k = A.take<T>(7 * nB); a.h = A.take<T>(B);
+    T* hidden = A.take<T>((size_t)B * W_HP);
+    a.part0 = A.take<T>((size_t)B * L.ec); a.part1 = A.take<T>((size_t)B * L.ec);
+    T* part = A.take<T>((size_t)L.nchunk * B * H);
+    unsigned* counters = A.take<unsigned>(B);
+    if (!h->wide_counters_zeroed[0] || h->wide_counters_ptr[0] != counters) {
+        CK(h, cudaMemsetAsync(counters, 0, sizeof(unsigned) * (size_t)B, h->stream));
+        h->wide_counters_zeroed[0] = true; h->wide_counters_ptr[0] = counters;
+    }
+    if (!dense) { a.rec = nullptr; a.rec_t = nullptr; a.rec_dt = nullptr; }
+    cudaStream_t st = h->stream;
+    const dim3 ge(L.ec, (unsigned)B), gr(L.nchunk, L.nbt_red), gp(L.uc, L.nbt_par);
+    int64_t launches = 0;
+    auto rhs = [&](int ncoef, const T* coef, int kslot, T* xstore) {     // k[kslot] = f(uprev + h * sum coef_j k_j)
+        WideIn<T> in{};
+        in.base = a.uprev; in.ks = a.k; in.hs = a.h; in.ncoef = ncoef;
+        for (int j = 0; j < ncoef; ++j) in.coef[j] = coef[j];
+        in.xstore = xstore; in.mask = c.active;
+        wide_l1_fwd_kernel<T, H, G, 0><<<gr, W_BT, 0, st>>>(m, p, in, B, L.P, L.bt_red, part, hidden, counters);
+        wide_l2_fwd_kernel<T, H, G><<<gp, W_BT, 0, st>>>(m, p, hidden, a.k + (size_t)kslot * nB, c.active, B, L.bt_par);
+        launches += 2;
+    };
+    wide_fwd_init_kernel<T><<<ge, W_ET, 0, st>>>(c, a, n);
+    rhs(0, nullptr, 0, nullptr);
+    wide_norm_kernel<T, 1><<<ge, W_ET, 0, st>>>(a.uprev, a.k, nullptr, n, a.abstol, a.reltol, c.active, a.part0, a.part1, L.ec, 0);
+    wide_fwd_ctl_kernel<T><<<(unsigned)B, 128, 0, st>>>(c, a, n, 0);
+    const T one[1] = {T(1)};
+    rhs(1, one, 1, nullptr);
+    wide_norm_kernel<T, 2><<<ge, W_ET, 0, st>>>(a.uprev, a.k, a.k + nB, n, a.abstol, a.reltol, c.active, a.part0, a.part1, L.ec, 0);
+    wide_fwd_ctl_kernel<T><<<(unsigned)B, 128, 0, st>>>(c, a, n, 1);
+    launches += 5;
+    static const double A_[7][8] = KANODE_TSIT5_A;
+    int iters = 0;
+    const int slot = dense ? 1 : 0;
+    const int expect = h->wide_iters[slot];          // attempts the previous call of this kind needed
+    bool any = a.t0 < a.t1;
+    while (any) {
+        for (int s = 1; s < 7; ++s) {
+            T coef[7];
+            for (int j = 0; j < s; ++j) coef[j] = (T)A_[s][j];
+            rhs(s, coef, s, s == 6 ? a.unew : nullptr);
+        }
+        wide_err_kernel<T><<<ge, W_ET, 0, st>>>(a.uprev, a.unew, a.k, n, B, a.h, a.abstol, a.reltol, c.active, a.part0, L.ec, 0);
+        wide_fwd_ctl_kernel<T><<<(unsigned)B, 128, 0, st>>>(c, a, n, 2);
+        wide_fwd_accept_kernel<T><<<ge, W_ET, 0, st>>>(c, a, n, B);
+        launches += 3;
+        ++iters;
+        if (iters >= expect) {
+            if (int rc = wide_any_active(h, c.active, B, any)) return rc;
+            if (!any && iters == expect && iters > 1) --iters;      // possibly overshot: poll one attempt earlier next time
+        }
+        if (iters > a.maxiters + 2) break;
+    }
+    h->wide_iters[slot] = iters;
+    wide_fwd_finish_kernel<T><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(c, a, B);
+    h->launches += launches + 1;
+    CK(h, cudaGetLastError());
+    if (ctl_out) *ctl_out = c;
+    return 0;
+}
+
+template <class T, int H, int G>
+int wide_solve_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, double t0, double t1, const double* d_saveat, int nsave,
+                 double abstol, double reltol, T* d_out, kanode_stats* d_stats) {
+    const WideModel m = wide_model(h);
+    WideFwd<T> a{};
+    a.u0 = d_u0; a.t0 = t0; a.t1 = t1; a.saveat = d_saveat; a.nsave = nsave; a.abstol = (T)abstol; a.reltol = (T)reltol;
+    a.maxiters = 100000; a.out = d_out; a.stats = d_stats;
+    return wide_forward<T, H, G>(h, m, p, a, B, false, nullptr);
+}
+
+template <class T, int H, int G>
+int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, double t0, double t1, const double* d_saveat, int nsave,
+                     const T* d_target, double abstol, double reltol, double* d_loss_sum, T* d_grad_sum, T* d_du0,
+                     kanode_stats* d_fst, kanode_stats* d_bst, T* d_out_opt) {
+    constexpr int GB = sizeof(T) == 4 ? 8 : 4;
+    const WideModel m = wide_model(h);
+    const int n = m.n;
+    const size_t nB = (size_t)n * B, np = h->np;
+    const int cap = h->rec_cap;
+    cudaStream_t st = h->stream;
+    // ---- forward, dense ----
+    WideFwd<T> a{};
+    a.u0 = d_u0; a.t0 = t0; a.t1 = t1; a.saveat = d_saveat; a.nsave = nsave; a.abstol = (T)abstol; a.reltol = (T)reltol;
+    a.maxiters = 100000; a.out = d_out_opt; a.stats = d_fst; a.target = d_target; a.loss_sum = d_loss_sum; a.cap = cap;
+    ENSURE(h, W_REC_T, sizeof(double) * (size_t)cap * B, a.rec_t);
+    ENSURE(h, W_GEN2, sizeof(T) * (size_t)cap * B, a.rec_dt);
+    ENSURE(h, W_REC, sizeof(T) * (size_t)cap * 8 * nB, a.rec);
+    ENSURE(h, W_NSTEPS, sizeof(int) * (size_t)B, a.nsteps);
+    ENSURE(h, W_RET, sizeof(int) * (size_t)B, a.retcode);
+    ENSURE(h, W_DG, sizeof(T) * (size_t)nsave * nB, a.dg);
+    T* g = nullptr;
+    ENSURE(h, W_G, sizeof(T) * 2 * np * B, g);
+    cudaEventRecord(h->ev[0], st);
+    if (int rc = wide_forward<T, H, G>(h, m, p, a, B, true, nullptr)) return rc;
+    cudaEventRecord(h->ev[1], st);
+    // ---- backward ----
+    const WideLaunch L = wide_launch(n, B, GB);
+    const int gx1 = (int)std::min<int64_t>(((int64_t)n * (G + 1) + W_ET - 1) / W_ET, 256);
+    const int np_l = L.ec, np_1 = gx1, np_2 = L.uc * H, npart = np_l + np_1 + np_2;
+    size_t bytes = wide_ctl_bytes(B) + sizeof(T) * (nB + 7 * nB * 3 + (size_t)7 * B * W_HP * 2 + (size_t)B * 15 + 2 * (size_t)B * npart +
+                                                    (size_t)L.nchunk * B * H) + sizeof(unsigned) * (size_t)B + 24 * 256;
+    char* base = nullptr;
+    ENSURE(h, W_WIDE_B, bytes, base);
+    Arena A{base};
+    WideCtl c = wide_ctl_carve(A, B);
+    WideBwd<T> w{};
+    w.lam = A.take<T>(nB); w.kl = A.take<T>(7 * nB); w.x1 = A.take<T>(7 * nB); w.yb2 = A.take<T>(7 * nB);
+    w.yb1 = A.take<T>((size_t)7 * B * W_HP); w.x2 = A.take<T>((size_t)7 * B * W_HP);
+    w.h = A.take<T>(B); w.th = A.take<T>(7 * (size_t)B); w.hd = A.take<T>(7 * (size_t)B);
+    w.part0 = A.take<T>((size_t)B * npart); w.part1 = A.take<T>((size_t)B * npart);
+    T* part = A.take<T>((size_t)L.nchunk * B * H);
+    unsigned* counters = A.take<unsigned>(B);
+    if (!h->wide_counters_zeroed[1] || h->wide_counters_ptr[1] != counters) {
+        CK(h, cudaMemsetAsync(counters, 0, sizeof(unsigned) * (size_t)B, st));
+        h->wide_counters_zeroed[1] = true; h->wide_counters_ptr[1] = counters;
+    }
+    w.t0 = t0; w.t1 = t1; w.saveat = d_saveat; w.nsave = nsave; w.abstol = (T)abstol; w.reltol = (T)reltol; w.maxiters = 100000;
+    w.rec_t = a.rec_t; w.rec_dt = a.rec_dt; w.rec = a.rec; w.cap = cap; w.nsteps = a.nsteps; w.retcode = a.retcode;
+    w.dg = a.dg; w.g = g; w.np = (long long)np; w.npart = npart; w.du0 = d_du0; w.stats = d_bst;
+    CK(h, cudaMemset2DAsync(g, sizeof(T) * 2 * np, 0, sizeof(T) * np, (size_t)B, st));        // g[b][0][:] = 0
+    CK(h, cudaMemsetAsync(w.part0, 0, sizeof(T) * (size_t)B * npart, st));
+    CK(h, cudaMemsetAsync(w.part1, 0, sizeof(T) * (size_t)B * npart, st));
+    const dim3 ge(L.ec, (unsigned)B), gr(L.nchunk, L.nbt_red), gp(L.uc, L.nbt_par), gg1(gx1, (unsigned)B), gg2(L.uc, H, (unsigned)B);
+    int64_t launches = 0;
+    static const double A_[7][8] = KANODE_TSIT5_A;
+    // adjoint rhs of stage slot s: records x_l / ybar_l, kl[s] = -(df/du)^T lambda_s
+    auto adj = [&](int s, int ncoef, const T* coef, const int* mask) {
+        WideIn<T> in{};
+        in.rec = w.rec; in.cap = cap; in.ridx = c.ridx + (size_t)s * B; in.th = w.th + (size_t)s * B; in.hd = w.hd + (size_t)s * B;
+        in.xstore = w.x1 + (size_t)s * nB; in.mask = mask;
+        wide_l1_fwd_kernel<T, H, G, 1><<<gr, W_BT, 0, st>>>(m, p, in, B, L.P, L.bt_red, part, w.x2 + (size_t)s * B * W_HP, counters);
+        WideIn<T> il{};
+        il.base = w.lam; il.ks = w.kl; il.hs = w.h; il.ncoef = ncoef;
+        for (int j = 0; j < ncoef; ++j) il.coef[j] = coef[j];
+        il.xstore = w.yb2 + (size_t)s * nB; il.mask = mask;
+        wide_l2_vjp_kernel<T, H, G><<<gr, W_BT, 0, st>>>(m, p, w.x2 + (size_t)s * B * W_HP, il, B, L.P, L.bt_red, part, w.yb1 + (size_t)s * B * W_HP, counters);
+        wide_l1_vjp_kernel<T, H, G><<<gp, W_BT, 0, st>>>(m, p, w.x1 + (size_t)s * nB, w.yb1 + (size_t)s * B * W_HP, w.kl + (size_t)s * nB, mask, B, L.bt_par);
+        launches += 3;
+    };
+    WideGp<T> gpa{};
+    gpa.x1 = w.x1; gpa.yb1 = w.yb1; gpa.x2 = w.x2; gpa.yb2 = w.yb2; gpa.g = g; gpa.cur = c.cur; gpa.h = w.h; gpa.mask = c.active;
+    gpa.abstol = w.abstol; gpa.reltol = w.reltol; gpa.npart = npart;
+    auto gpass = [&](int mode, T* dst) {
+        WideGp<T> q1 = gpa, q2 = gpa;
+        q1.es_part = dst; q1.off = np_l; q2.es_part = dst; q2.off = np_l + np_1;
+        if (mode == 0) { wide_gp1_kernel<T, H, G, 0><<<gg1, W_ET, 0, st>>>(m, q1, B); wide_gp2_kernel<T, H, G, 0><<<gg2, W_BT, 0, st>>>(m, q2, B); }
+        else if (mode == 1) { wide_gp1_kernel<T, H, G, 1><<<gg1, W_ET, 0, st>>>(m, q1, B); wide_gp2_kernel<T, H, G, 1><<<gg2, W_BT, 0, st>>>(m, q2, B); }
+        else { wide_gp1_kernel<T, H, G, 2><<<gg1, W_ET, 0, st>>>(m, q1, B); wide_gp2_kernel<T, H, G, 2><<<gg2, W_BT, 0, st>>>(m, q2, B); }
+        launches += 2;
+    };
+    wide_bwd_ctl_kernel<T><<<(unsigned)B, 128, 0, st>>>(c, w, n, B, -1);
+    wide_bwd_init_kernel<T><<<ge, W_ET, 0, st>>>(c, w, n);
+    adj(0, 0, nullptr, c.active);
+    wide_norm_kernel<T, 1><<<ge, W_ET, 0, st>>>(w.lam, w.kl, nullptr, n, w.abstol, w.reltol, c.active, w.part0, w.part1, npart, 0);
+    gpass(1, w.part1);
+    wide_bwd_ctl_kernel<T><<<(unsigned)B, 128, 0, st>>>(c, w, n, B, 0);
+    const T one[1] = {T(1)};
+    adj(1, 1, one, c.active);
+    wide_norm_kernel<T, 2><<<ge, W_ET, 0, st>>>(w.lam, w.kl, w.kl + nB, n, w.abstol, w.reltol, c.active, w.part0, w.part1, npart, 0);
+    gpass(2, w.part1);
+    wide_bwd_ctl_kernel<T><<<(unsigned)B, 128, 0, st>>>(c, w, n, B, 1);
+    launches += 6;
+    int iters = 0;
+    const int expect = h->wide_iters[2];
+    bool any = t0 < t1;
+    while (any) {
+        adj(0, 0, nullptr, c.do_s0);                                   // only the ICs whose lambda jumped at a save time
+        for (int s = 1; s < 7; ++s) {
+            T coef[7];
+            for (int j = 0; j < s; ++j) coef[j] = (T)A_[s][j];
+            adj(s, s, coef, c.active);
+        }
+        wide_err_kernel<T><<<ge, W_ET, 0, st>>>(w.lam, w.yb2 + (size_t)6 * nB, w.kl, n, B, w.h, w.abstol, w.reltol, c.active, w.part0, npart, 0);
+        gpass(0, w.part0);
+        wide_bwd_ctl_kernel<T><<<(unsigned)B, 128, 0, st>>>(c, w, n, B, 2);
+        wide_bwd_accept_kernel<T><<<ge, W_ET, 0, st>>>(c, w, n, B);
+        launches += 3;
+        ++iters;
+        if (iters >= expect) {
+            if (int rc = wide_any_active(h, c.active, B, any)) return rc;
+            if (!any && iters == expect && iters > 1) --iters;
+        }
+        if (iters > w.maxiters + 2) break;
+    }
+    h->wide_iters[2] = iters;
+    wide_bwd_finish_kernel<T><<<ge, W_ET, 0, st>>>(c, w, n);
+    cudaEventRecord(h->ev[2], st);
+    wide_grad_reduce_kernel<T><<<(unsigned)((np + 255) / 256), 256, 0, st>>>(g, c.cur, c.ret, (long long)np, B, d_grad_sum);
+    cudaEventRecord(h->ev[3], st);
+    h->ev_valid = true;
+    h->launches += launches + 2;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace kanode
