@@ -16,7 +16,7 @@
 #include "kanode_small.cuh"
 #include "kanode_small_ls.cuh"
 #include "kanode_generic.cuh"
-#include "kanode_wide.cuh"
+#include "kanode_wide_api.h"
 
 using namespace kanode;
 
@@ -184,10 +184,8 @@ int solve_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double t1, 
     };
     if (small_dispatch<T>(h, run, rc)) return rc;
     WideKey wk;
-    if (h->wide && wide_match(h->desc, wk)) {
-        if (wk.G == 5) return wide_solve_t<T, 10, 5>(h, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);
-        return wide_solve_t<T, 10, 10>(h, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);
-    }
+    if (h->wide && wide_match(h->desc, wk))
+        return wide_solve(h, wk, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);
     return generic_solve<T>(h, d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);
 }
 
@@ -338,13 +336,9 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
     };
     if (small_dispatch<T>(h, run, rc)) return rc;
     WideKey wk;
-    if (h->wide && wide_match(h->desc, wk)) {
-        if (wk.G == 5)
-            return wide_loss_grad_t<T, 10, 5>(h, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol,
-                                              d_loss_sum, d_grad_sum, d_du0, d_fst, d_bst, d_out_opt);
-        return wide_loss_grad_t<T, 10, 10>(h, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol,
-                                           d_loss_sum, d_grad_sum, d_du0, d_fst, d_bst, d_out_opt);
-    }
+    if (h->wide && wide_match(h->desc, wk))
+        return wide_loss_grad(h, wk, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum,
+                              d_grad_sum, d_du0, d_fst, d_bst, d_out_opt);
     return generic_loss_grad<T>(h, d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum, d_grad_sum,
                                 d_du0, d_fst, d_bst, d_out_opt);
 }

@@ -27,6 +27,7 @@
 #pragma once
 #include "kanode_host.h"
 #include "kanode_math.cuh"
+#include "kanode_wide_api.h"
 
 namespace kanode {
 
@@ -149,7 +150,7 @@ __device__ __forceinline__ void wide_reduce_tail(T (*red)[W_BT + 1], int b0, int
 // grid (nchunk, nbt); block W_BT; each block walks P passes of W_BT units and <= GB ICs
 // ---------------------------------------------------------------------------------------------------------
 template <class T, int H, int G, int MODE>
-__global__ void __launch_bounds__(W_BT) wide_l1_fwd_kernel(const __grid_constant__ WideModel m, const T* __restrict__ p, const WideIn<T> in,
+__global__ void __launch_bounds__(W_BT) wide_l1_fwd_kernel(const __grid_constant__ WideModel m, const T* __restrict__ w1t, const WideIn<T> in,
                                                            int64_t B, int P, int btile, T* part, T* hidden, unsigned* counters) {
     constexpr int NQ = G + 1, NW = H * NQ, GB = sizeof(T) == 4 ? 8 : 4;
     __shared__ T red[GB * H][W_BT + 1];
@@ -161,32 +162,30 @@ __global__ void __launch_bounds__(W_BT) wide_l1_fwd_kernel(const __grid_constant
         const int i = (blockIdx.x * P + pass) * W_BT + tid;
         const bool valid = i < n;
         T w[NW];
-        if (valid) {
-            const T* c = p + m.offC1 + (int64_t)i * G * H;
 #pragma unroll
-            for (int k = 0; k < G * H; ++k) w[k] = c[k];
-            const T* ww = p + m.offW1 + (int64_t)i * H;
+        for (int k = 0; k < NW; ++k) w[k] = valid ? w1t[(int64_t)k * n + i] : T(0);     // [NW][n]: coalesced over the units
+        T xs[GB]; bool on[GB];
 #pragma unroll
-            for (int k = 0; k < H; ++k) w[G * H + k] = ww[k];
-        } else {
-#pragma unroll
-            for (int k = 0; k < NW; ++k) w[k] = T(0);
+        for (int bl = 0; bl < GB; ++bl) {                                                // all loads of the tile in flight together
+            const int b = b0 + bl;
+            on[bl] = valid && b < b1 && (!in.mask || in.mask[b]);
+            xs[bl] = on[bl] ? wide_input<T, MODE>(in, b, i, n, B) : T(0);
         }
-        for (int b = b0; b < b1; ++b) {
+#pragma unroll
+        for (int bl = 0; bl < GB; ++bl) {
+            if (b0 + bl >= b1) break;
             T acc[H];
 #pragma unroll
             for (int o = 0; o < H; ++o) acc[o] = T(0);
-            if (valid && (!in.mask || in.mask[b])) {
-                const T x = wide_input<T, MODE>(in, b, i, n, B);
-                if (in.xstore) in.xstore[(int64_t)b * n + i] = x;
+            if (on[bl]) {
+                if (in.xstore) in.xstore[(int64_t)(b0 + bl) * n + i] = xs[bl];
                 T c[NQ];
-                w_features<T, G>(m.norm1, inv_h, m.grid1, x, c);
+                w_features<T, G>(m.norm1, inv_h, m.grid1, xs[bl], c);
 #pragma unroll
                 for (int q = 0; q < NQ; ++q)
 #pragma unroll
                     for (int o = 0; o < H; ++o) acc[o] += w[q * H + o] * c[q];
             }
-            const int bl = b - b0;
 #pragma unroll
             for (int o = 0; o < H; ++o) {
                 if (pass == 0) red[bl * H + o][tid] = acc[o];
@@ -214,29 +213,39 @@ template <class T, int H, int G> __device__ __forceinline__ void wide_load_w2(co
 template <class T, int H, int G>
 __global__ void __launch_bounds__(W_BT) wide_l2_fwd_kernel(const __grid_constant__ WideModel m, const T* __restrict__ p, const T* hidden, T* out,
                                                            const int* mask, int64_t B, int btile) {
-    constexpr int NQ = G + 1, NW = H * NQ, NWP = (NW + 3) / 4 * 4;
-    __shared__ __align__(16) T f2[W_PT][NWP];
+    constexpr int NQ = G + 1, NW = H * NQ;
+    __shared__ __align__(16) T f2[NW][W_PT];              // features, IC index fastest: one vector load feeds 4 ICs
     const int tid = threadIdx.x, n = m.n;
     const int b0 = blockIdx.y * btile, b1 = (int)min((int64_t)(b0 + btile), B);
-    for (int v = tid; v < (b1 - b0) * H; v += W_BT) {
+    for (int v = tid; v < W_PT * H; v += W_BT) {
         const int bl = v / H, j = v % H;
         T c[NQ];
-        w_features<T, G>(m.norm2, (T)m.inv_h2, m.grid2, hidden[(int64_t)(b0 + bl) * W_HP + j], c);
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) f2[bl][j * NQ + q] = c[q];
+        for (int q = 0; q < NQ; ++q) c[q] = T(0);
+        if (b0 + bl < b1) w_features<T, G>(m.norm2, (T)m.inv_h2, m.grid2, hidden[(int64_t)(b0 + bl) * W_HP + j], c);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) f2[j * NQ + q][bl] = c[q];
     }
     __syncthreads();
     const int o = blockIdx.x * W_BT + tid;
     if (o >= n) return;
     T w[NW];
     wide_load_w2<T, H, G>(m, p, o, w);
-    for (int b = b0; b < b1; ++b) {
-        if (mask && !mask[b]) continue;
-        const T* f = f2[b - b0];
-        T acc = T(0);
+    for (int bl0 = 0; b0 + bl0 < b1; bl0 += 4) {
+        T acc[4] = {T(0), T(0), T(0), T(0)};
 #pragma unroll
-        for (int r = 0; r < NW; ++r) acc += w[r] * f[r];
-        out[(int64_t)b * n + o] = acc;
+        for (int r = 0; r < NW; ++r) {
+            T f[4];
+            if constexpr (sizeof(T) == 4) { const float4 v = *reinterpret_cast<const float4*>(&f2[r][bl0]); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+            else { const double2 v0 = *reinterpret_cast<const double2*>(&f2[r][bl0]), v1 = *reinterpret_cast<const double2*>(&f2[r][bl0 + 2]); f[0] = v0.x; f[1] = v0.y; f[2] = v1.x; f[3] = v1.y; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] += w[r] * f[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int b = b0 + bl0 + k;
+            if (b < b1 && (!mask || mask[b])) out[(int64_t)b * n + o] = acc[k];
+        }
     }
 }
 
@@ -249,16 +258,18 @@ __global__ void __launch_bounds__(W_BT) wide_l2_vjp_kernel(const __grid_constant
                                                            const WideIn<T> in, int64_t B, int P, int btile, T* part, T* hbar, unsigned* counters) {
     constexpr int NQ = G + 1, NW = H * NQ, GB = sizeof(T) == 4 ? 8 : 4;
     __shared__ T red[GB * H][W_BT + 1];
-    __shared__ T d2[GB][NW];
+    __shared__ __align__(16) T d2[NW][GB];                 // d c_q / d hidden_j, IC index fastest
     __shared__ int s_last;
     const int tid = threadIdx.x, n = m.n;
     const int b0 = blockIdx.y * btile, b1 = (int)min((int64_t)(b0 + btile), B);
-    for (int v = tid; v < (b1 - b0) * H; v += W_BT) {
+    for (int v = tid; v < GB * H; v += W_BT) {
         const int bl = v / H, j = v % H;
         T d[NQ];
-        w_dfeatures<T, G>(m.norm2, (T)m.inv_h2, m.grid2, hidden[(int64_t)(b0 + bl) * W_HP + j], d);
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) d2[bl][j * NQ + q] = d[q];
+        for (int q = 0; q < NQ; ++q) d[q] = T(0);
+        if (b0 + bl < b1) w_dfeatures<T, G>(m.norm2, (T)m.inv_h2, m.grid2, hidden[(int64_t)(b0 + bl) * W_HP + j], d);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) d2[j * NQ + q][bl] = d[q];
     }
     __syncthreads();
     for (int pass = 0; pass < P; ++pass) {
@@ -270,27 +281,38 @@ __global__ void __launch_bounds__(W_BT) wide_l2_vjp_kernel(const __grid_constant
 #pragma unroll
             for (int k = 0; k < NW; ++k) w[k] = T(0);
         }
-        for (int b = b0; b < b1; ++b) {
-            const int bl = b - b0;
-            T acc[H];
+        T lam[GB];
 #pragma unroll
-            for (int j = 0; j < H; ++j) acc[j] = T(0);
-            if (valid && (!in.mask || in.mask[b])) {
-                const T lam = wide_input<T, 0>(in, b, o, n, B);
-                if (in.xstore) in.xstore[(int64_t)b * n + o] = lam;
-                const T* d = d2[bl];
+        for (int bl = 0; bl < GB; ++bl) {
+            const int b = b0 + bl;
+            const bool on = valid && b < b1 && (!in.mask || in.mask[b]);
+            lam[bl] = on ? wide_input<T, 0>(in, b, o, n, B) : T(0);
+            if (on && in.xstore) in.xstore[(int64_t)b * n + o] = lam[bl];
+        }
 #pragma unroll
-                for (int j = 0; j < H; ++j) {
-                    T inner = T(0);
+        for (int j = 0; j < H; ++j) {
+            T inner[GB];
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) inner += w[j * NQ + q] * d[j * NQ + q];
-                    acc[j] = lam * inner;
+            for (int bl = 0; bl < GB; ++bl) inner[bl] = T(0);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const T wv = w[j * NQ + q];
+                T d[GB];
+                if constexpr (sizeof(T) == 4) {
+                    const float4 v0 = *reinterpret_cast<const float4*>(&d2[j * NQ + q][0]), v1 = *reinterpret_cast<const float4*>(&d2[j * NQ + q][4]);
+                    d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w; d[4] = v1.x; d[5] = v1.y; d[6] = v1.z; d[7] = v1.w;
+                } else {
+                    const double2 v0 = *reinterpret_cast<const double2*>(&d2[j * NQ + q][0]), v1 = *reinterpret_cast<const double2*>(&d2[j * NQ + q][2]);
+                    d[0] = v0.x; d[1] = v0.y; d[2] = v1.x; d[3] = v1.y;
                 }
+#pragma unroll
+                for (int bl = 0; bl < GB; ++bl) inner[bl] += wv * d[bl];
             }
 #pragma unroll
-            for (int j = 0; j < H; ++j) {
-                if (pass == 0) red[bl * H + j][tid] = acc[j];
-                else red[bl * H + j][tid] += acc[j];
+            for (int bl = 0; bl < GB; ++bl) {
+                const T a = lam[bl] * inner[bl];
+                if (pass == 0) red[bl * H + j][tid] = a;
+                else red[bl * H + j][tid] += a;
             }
         }
     }
@@ -301,49 +323,56 @@ __global__ void __launch_bounds__(W_BT) wide_l2_vjp_kernel(const __grid_constant
 // layer 1 reverse: dl[b][i] = -( dnorm * sum_g db_g/h * (w1[g][:] . hbar[b]) + dswish * (W1[i][:] . hbar[b]) )
 // ---------------------------------------------------------------------------------------------------------
 template <class T, int H, int G>
-__global__ void __launch_bounds__(W_BT) wide_l1_vjp_kernel(const __grid_constant__ WideModel m, const T* __restrict__ p, const T* x1, const T* hbar,
+__global__ void __launch_bounds__(W_BT) wide_l1_vjp_kernel(const __grid_constant__ WideModel m, const T* __restrict__ w1t, const T* x1, const T* hbar,
                                                            T* dl, const int* mask, int64_t B, int btile) {
-    constexpr int NW = H * (G + 1);
+    constexpr int NW = H * (G + 1), PF = 8;
     __shared__ T hb[W_PT][W_HP];
     const int tid = threadIdx.x, n = m.n;
     const int b0 = blockIdx.y * btile, b1 = (int)min((int64_t)(b0 + btile), B);
-    for (int v = tid; v < (b1 - b0) * W_HP; v += W_BT) hb[v / W_HP][v % W_HP] = (v % W_HP) < H ? hbar[(int64_t)(b0 + v / W_HP) * W_HP + v % W_HP] : T(0);
+    for (int v = tid; v < W_PT * W_HP; v += W_BT) {
+        const int bl = v / W_HP, o = v % W_HP;
+        hb[bl][o] = (o < H && b0 + bl < b1) ? hbar[(int64_t)(b0 + bl) * W_HP + o] : T(0);
+    }
     __syncthreads();
     const int i = blockIdx.x * W_BT + tid;
     if (i >= n) return;
     T w[NW];
-    {
-        const T* c = p + m.offC1 + (int64_t)i * G * H;
 #pragma unroll
-        for (int k = 0; k < G * H; ++k) w[k] = c[k];
-        const T* ww = p + m.offW1 + (int64_t)i * H;
-#pragma unroll
-        for (int k = 0; k < H; ++k) w[G * H + k] = ww[k];
-    }
+    for (int k = 0; k < NW; ++k) w[k] = w1t[(int64_t)k * n + i];
     const T inv_h = (T)m.inv_h1;
-    for (int b = b0; b < b1; ++b) {
-        if (mask && !mask[b]) continue;
-        const T* yb = hb[b - b0];
-        const T x = x1[(int64_t)b * n + i];
-        const T xn = normalize_rt(m.norm1, x);
-        T xnbar = T(0);
+    for (int bl0 = 0; b0 + bl0 < b1; bl0 += PF) {
+        T xs[PF]; bool on[PF];
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const T a = (xn - (T)m.grid1[g]) * inv_h;
-            const T y = kexp(-a * a);
-            const T db = T(-2) * a * y;
-            T bbar = T(0);
-#pragma unroll
-            for (int o = 0; o < H; ++o) bbar += w[g * H + o] * yb[o];
-            xnbar += db * inv_h * bbar;
+        for (int k = 0; k < PF; ++k) {
+            const int b = b0 + bl0 + k;
+            on[k] = b < b1 && (!mask || mask[b]);
+            xs[k] = on[k] ? x1[(int64_t)b * n + i] : T(0);
         }
-        T xb = xnbar * normalize_deriv_rt(m.norm1, xn);
-        T s, ds; swish_both(x, s, ds);
-        T sbar = T(0);
 #pragma unroll
-        for (int o = 0; o < H; ++o) sbar += w[G * H + o] * yb[o];
-        xb += sbar * ds;
-        dl[(int64_t)b * n + i] = -xb;
+        for (int k = 0; k < PF; ++k) {
+            if (!on[k]) continue;
+            const T* yb = hb[bl0 + k];
+            const T x = xs[k];
+            const T xn = normalize_rt(m.norm1, x);
+            T xnbar = T(0);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const T a = (xn - (T)m.grid1[g]) * inv_h;
+                const T y = kexp(-a * a);
+                const T db = T(-2) * a * y;
+                T bbar = T(0);
+#pragma unroll
+                for (int o = 0; o < H; ++o) bbar += w[g * H + o] * yb[o];
+                xnbar += db * inv_h * bbar;
+            }
+            T xb = xnbar * normalize_deriv_rt(m.norm1, xn);
+            T sw, ds; swish_both(x, sw, ds);
+            T sbar = T(0);
+#pragma unroll
+            for (int o = 0; o < H; ++o) sbar += w[G * H + o] * yb[o];
+            xb += sbar * ds;
+            dl[(int64_t)(b0 + bl0 + k) * n + i] = -xb;
+        }
     }
 }
 
@@ -373,74 +402,106 @@ template <class T> __device__ __forceinline__ void gp_finalize(const T* gold, T*
     gnew[j] = g1;
 }
 
+// Layer 1: its slice of g is one contiguous array of (n*G + n) rows x H (C1 rows (i,q), then the W1 rows i), streamed with
+// coalesced 2-element accesses.  A thread's output pair o0 = (2*tid) % H is the same in every iteration (2*W_GT % H == 0),
+// so its 2 x 7 x 2 weighted cotangents stay in registers; the 7 stage features of a row come from shared memory.
+constexpr int W_GT = 320, W_GK = 8;      // threads per block, iterations per block (tile = W_GK * 2 * W_GT elements)
+template <class T> struct alignas(2 * sizeof(T)) WVec2 { T x, y; };
+
 template <class T, int H, int G, int MODE>
-__global__ void __launch_bounds__(W_ET) wide_gp1_kernel(const __grid_constant__ WideModel m, const WideGp<T> a, int64_t B) {
-    constexpr int NQ = G + 1, NS = MODE == 0 ? 7 : (MODE == 1 ? 1 : 2);
-    __shared__ T A[H][8], At[H][8];
+__global__ void __launch_bounds__(W_GT) wide_gp1_kernel(const __grid_constant__ WideModel m, const WideGp<T> a, int64_t B) {
+    static_assert(H % 2 == 0 && (2 * W_GT) % H == 0, "pair mapping");
+    constexpr int NS = MODE == 0 ? 7 : (MODE == 1 ? 1 : 2);
+    constexpr int ROWS = W_GK * 2 * W_GT / H;
+    __shared__ T C[NS][ROWS];
     __shared__ T sred[33];
     const int b = blockIdx.y, tid = threadIdx.x, n = m.n;
     if (a.mask && !a.mask[b]) return;
-    if (tid < H * 8) {
-        const int o = tid / 8, s = tid % 8;
-        T v = T(0), vt = T(0);
-        if (s < NS) {
-            const T yb = a.yb1[((int64_t)s * B + b) * W_HP + o];
-            if (MODE == 0) { const T hh = a.h[b]; v = (-hh * Tab<T>::b(s)) * yb; vt = (-hh * Tab<T>::bt(s)) * yb; }
-            else v = yb;
+    const int64_t nrowC = (int64_t)n * G, nrow = nrowC + n;
+    const int64_t row0 = (int64_t)blockIdx.x * ROWS;
+    const T inv_h = (T)m.inv_h1;
+    for (int idx = tid; idx < NS * ROWS; idx += W_GT) {
+        const int s = idx / ROWS, rl = idx - s * ROWS;
+        const int64_t R = row0 + rl;
+        T c = T(0);
+        if (R < nrowC) {
+            const int i = (int)(R / G), q = (int)(R - (int64_t)i * G);
+            const T aa = (normalize_rt(m.norm1, a.x1[((int64_t)s * B + b) * n + i]) - (T)m.grid1[q]) * inv_h;
+            c = kexp(-aa * aa);
+        } else if (R < nrow) {
+            swish_fwd(a.x1[((int64_t)s * B + b) * n + (R - nrowC)], c);
         }
-        A[o][s] = v; At[o][s] = vt;
+        C[s][rl] = c;
     }
+    const int o0 = (2 * tid) % H;
+    T ab[NS][2], at[NS][2];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const T yb = a.yb1[((int64_t)s * B + b) * W_HP + o0 + k];
+            if (MODE == 0) { const T hh = a.h[b]; ab[s][k] = (-hh * Tab<T>::b(s)) * yb; at[s][k] = (-hh * Tab<T>::bt(s)) * yb; }
+            else { ab[s][k] = yb; at[s][k] = T(0); }
+        }
     __syncthreads();
     const T* gold = nullptr; T* gnew = nullptr;
-    if (MODE == 0) { const int cur = a.cur[b]; gold = a.g + ((int64_t)b * 2 + cur) * m.np; gnew = a.g + ((int64_t)b * 2 + (cur ^ 1)) * m.np; }
-    const T inv_h = (T)m.inv_h1;
+    if (MODE == 0) { const int cur = a.cur[b]; gold = a.g + ((int64_t)b * 2 + cur) * m.np + m.offC1; gnew = a.g + ((int64_t)b * 2 + (cur ^ 1)) * m.np + m.offC1; }
+    const int64_t e0 = row0 * H, E = nrow * H;
     T es = T(0);
-    const int64_t nitem = (int64_t)n * NQ;
-    for (int64_t item = (int64_t)blockIdx.x * W_ET + tid; item < nitem; item += (int64_t)gridDim.x * W_ET) {
-        const int i = (int)(item / NQ), q = (int)(item - (int64_t)i * NQ);
-        T c[NS];
+    WVec2<T> g0[W_GK];
+    if (MODE == 0) {
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            const T x = a.x1[((int64_t)s * B + b) * n + i];
-            if (q < G) { const T aa = (normalize_rt(m.norm1, x) - (T)m.grid1[q]) * inv_h; c[s] = kexp(-aa * aa); }
-            else swish_fwd(x, c[s]);
+        for (int k = 0; k < W_GK; ++k) {
+            const int64_t e = e0 + 2 * tid + (int64_t)k * 2 * W_GT;
+            g0[k] = e < E ? *reinterpret_cast<const WVec2<T>*>(gold + e) : WVec2<T>{T(0), T(0)};
         }
-        const int64_t row = q < G ? m.offC1 + ((int64_t)i * G + q) * H : m.offW1 + (int64_t)i * H;
+    }
 #pragma unroll
-        for (int o = 0; o < H; ++o) {
-            if (MODE == 0) {
-                T vb = T(0), vt = T(0);
+    for (int k = 0; k < W_GK; ++k) {
+        const int el = 2 * tid + k * 2 * W_GT;
+        const int64_t e = e0 + el;
+        if (e >= E) break;
+        const int rl = el / H;
+        if (MODE == 0) {
+            T vb0 = T(0), vb1 = T(0), vt0 = T(0), vt1 = T(0);
 #pragma unroll
-                for (int s = 0; s < 7; ++s) { vb += A[o][s] * c[s]; vt += At[o][s] * c[s]; }
-                gp_finalize<T>(gold, gnew, row + o, vb, vt, a.abstol, a.reltol, es);
-            } else if (MODE == 1) {
-                const T x1 = (A[o][0] * c[0]) / a.abstol;
-                es += x1 * x1;
-            } else {
-                const T x2 = (A[o][1] * c[1] - A[o][0] * c[0]) / a.abstol;
-                es += x2 * x2;
-            }
+            for (int s = 0; s < 7; ++s) { const T c = C[s][rl]; vb0 += ab[s][0] * c; vb1 += ab[s][1] * c; vt0 += at[s][0] * c; vt1 += at[s][1] * c; }
+            WVec2<T> g1;
+            g1.x = g0[k].x + vb0; g1.y = g0[k].y + vb1;
+            const T r0 = vt0 / (a.abstol + kmax(kabs(g0[k].x), kabs(g1.x)) * a.reltol);
+            const T r1 = vt1 / (a.abstol + kmax(kabs(g0[k].y), kabs(g1.y)) * a.reltol);
+            es += r0 * r0; es += r1 * r1;
+            *reinterpret_cast<WVec2<T>*>(gnew + e) = g1;
+        } else if (MODE == 1) {
+            const T x0 = (ab[0][0] * C[0][rl]) / a.abstol, x1 = (ab[0][1] * C[0][rl]) / a.abstol;
+            es += x0 * x0; es += x1 * x1;
+        } else {
+            const T x0 = (ab[NS - 1][0] * C[NS - 1][rl] - ab[0][0] * C[0][rl]) / a.abstol;
+            const T x1 = (ab[NS - 1][1] * C[NS - 1][rl] - ab[0][1] * C[0][rl]) / a.abstol;
+            es += x0 * x0; es += x1 * x1;
         }
     }
     es = wblock_sum<T>(es, sred);
     if (tid == 0) a.es_part[(int64_t)b * a.npart + a.off + blockIdx.x] = es;
 }
 
-// layer 2: grid (ceil(n / W_BT), H, B); thread = output unit o, block row j = hidden unit
+// Layer 2: rows (j,q) of length n; thread = output unit o walks all H*(G+1) rows (coalesced over o); the 7 stage features of a
+// row are uniform over the block (shared memory, vector loads), the weighted cotangents of o stay in registers.
 template <class T, int H, int G, int MODE>
 __global__ void __launch_bounds__(W_BT) wide_gp2_kernel(const __grid_constant__ WideModel m, const WideGp<T> a, int64_t B) {
-    constexpr int NQ = G + 1, NS = MODE == 0 ? 7 : (MODE == 1 ? 1 : 2);
-    __shared__ __align__(16) T F[NQ][8];
+    constexpr int NQ = G + 1, NW = H * NQ, NS = MODE == 0 ? 7 : (MODE == 1 ? 1 : 2);
+    __shared__ __align__(16) T F[NW][8];
     __shared__ T sred[33];
-    const int b = blockIdx.z, j = blockIdx.y, tid = threadIdx.x, n = m.n;
+    const int b = blockIdx.y, tid = threadIdx.x, n = m.n;
     if (a.mask && !a.mask[b]) return;
-    if (tid < 8) {
+    for (int v = tid; v < 8 * H; v += W_BT) {
+        const int s = v / H, j = v % H;
         T c[NQ];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) c[q] = T(0);
-        if (tid < NS) w_features<T, G>(m.norm2, (T)m.inv_h2, m.grid2, a.x2[((int64_t)tid * B + b) * W_HP + j], c);
+        if (s < NS) w_features<T, G>(m.norm2, (T)m.inv_h2, m.grid2, a.x2[((int64_t)s * B + b) * W_HP + j], c);
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) F[q][tid] = c[q];
+        for (int q = 0; q < NQ; ++q) F[j * NQ + q][s] = c[q];
     }
     __syncthreads();
     const int o = blockIdx.x * W_BT + tid;
@@ -454,26 +515,59 @@ __global__ void __launch_bounds__(W_BT) wide_gp2_kernel(const __grid_constant__ 
             else { al[s] = yb; alt[s] = T(0); }
         }
         const T* gold = nullptr; T* gnew = nullptr;
-        if (MODE == 0) { const int cur = a.cur[b]; gold = a.g + ((int64_t)b * 2 + cur) * m.np; gnew = a.g + ((int64_t)b * 2 + (cur ^ 1)) * m.np; }
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            const int64_t row = q < G ? m.offC2 + (int64_t)(j * G + q) * n : m.offW2 + (int64_t)j * n;
+        if (MODE == 0) { const int cur = a.cur[b]; gold = a.g + ((int64_t)b * 2 + cur) * m.np + m.offC2 + o; gnew = a.g + ((int64_t)b * 2 + (cur ^ 1)) * m.np + m.offC2 + o; }
+#pragma unroll 2
+        for (int j = 0; j < H; ++j) {
+            T g0[NQ];
             if (MODE == 0) {
-                T vb = T(0), vt = T(0);
 #pragma unroll
-                for (int s = 0; s < 7; ++s) { vb += al[s] * F[q][s]; vt += alt[s] * F[q][s]; }
-                gp_finalize<T>(gold, gnew, row + o, vb, vt, a.abstol, a.reltol, es);
-            } else if (MODE == 1) {
-                const T x1 = (al[0] * F[q][0]) / a.abstol;
-                es += x1 * x1;
-            } else {
-                const T x2 = (al[1] * F[q][1] - al[0] * F[q][0]) / a.abstol;
-                es += x2 * x2;
+                for (int q = 0; q < NQ; ++q) g0[q] = gold[(int64_t)(q < G ? j * G + q : H * G + j) * n];
+            }
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const T* f = F[j * NQ + q];
+                if (MODE == 0) {
+                    T fs[8];
+                    if constexpr (sizeof(T) == 4) {
+                        const float4 v0 = *reinterpret_cast<const float4*>(f), v1 = *reinterpret_cast<const float4*>(f + 4);
+                        fs[0] = v0.x; fs[1] = v0.y; fs[2] = v0.z; fs[3] = v0.w; fs[4] = v1.x; fs[5] = v1.y; fs[6] = v1.z; fs[7] = v1.w;
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) fs[s] = f[s];
+                    }
+                    T vb = T(0), vt = T(0);
+#pragma unroll
+                    for (int s = 0; s < 7; ++s) { vb += al[s] * fs[s]; vt += alt[s] * fs[s]; }
+                    const T g1 = g0[q] + vb;
+                    const T r = vt / (a.abstol + kmax(kabs(g0[q]), kabs(g1)) * a.reltol);
+                    es += r * r;
+                    gnew[(int64_t)(q < G ? j * G + q : H * G + j) * n] = g1;
+                } else if (MODE == 1) {
+                    const T x1 = (al[0] * f[0]) / a.abstol;
+                    es += x1 * x1;
+                } else {
+                    const T x2 = (al[NS - 1] * f[NS - 1] - al[0] * f[0]) / a.abstol;
+                    es += x2 * x2;
+                }
             }
         }
     }
     es = wblock_sum<T>(es, sred);
-    if (tid == 0) a.es_part[(int64_t)b * a.npart + a.off + (int64_t)j * gridDim.x + blockIdx.x] = es;
+    if (tid == 0) a.es_part[(int64_t)b * a.npart + a.off + blockIdx.x] = es;
+}
+
+// w1t[(q*H + o)][i]: layer-1 weights transposed so that a warp of consecutive input units loads them coalesced
+template <class T, int H, int G>
+__global__ void __launch_bounds__(256) wide_transpose_w1_kernel(const __grid_constant__ WideModel m, const T* __restrict__ p, T* __restrict__ w1t) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;       // over the source layout (coalesced reads)
+    const int64_t nC = (int64_t)m.n * G * H, nW = (int64_t)m.n * H;
+    if (idx < nC) {
+        const int64_t i = idx / (G * H); const int r = (int)(idx - i * G * H);       // r = q*H + o
+        w1t[(int64_t)r * m.n + i] = p[m.offC1 + idx];
+    } else if (idx < nC + nW) {
+        const int64_t k = idx - nC; const int64_t i = k / H; const int o = (int)(k - i * H);
+        w1t[(int64_t)(G * H + o) * m.n + i] = p[m.offW1 + k];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -884,17 +978,6 @@ __global__ void __launch_bounds__(256) wide_grad_reduce_kernel(const T* g, const
 // =========================================================================================================
 // host side
 // =========================================================================================================
-struct WideKey { int H, G; };
-inline bool wide_match(const kanode_desc& d, WideKey& k) {
-    if (d.rhs_kind != KANODE_RHS_CHAIN || d.n_layers != 2) return false;
-    const kanode_layer_desc &a = d.layers[0], &b = d.layers[1];
-    if (a.basis != KANODE_BASIS_RBF || b.basis != KANODE_BASIS_RBF || !a.use_base_act || !b.use_base_act) return false;
-    if (a.grid_len != b.grid_len || a.grid_len > 16) return false;
-    if (a.in_dims != b.out_dims || a.in_dims < 16) return false;     // narrow states belong to the thread-per-trajectory kernels
-    k = WideKey{a.out_dims, a.grid_len};
-    return (k.H == 10) && (k.G == 5 || k.G == 10);
-}
-
 inline WideModel wide_model(const kanode_handle* h) {
     const kanode_desc& d = h->desc;
     WideModel m{};
@@ -952,11 +1035,29 @@ inline int wide_any_active(kanode_handle* h, const int* d_active, int64_t B, boo
     return 0;
 }
 
+// layer-1 weights in the transposed device layout, refreshed when the parameters changed
+template <class T, int H, int G> int wide_w1t(kanode_handle* h, const WideModel& m, const T* p, const T** out) {
+    T* d = nullptr;
+    const size_t cnt = (size_t)m.n * H * (G + 1);
+    const int slot = sizeof(T) == 4 ? 0 : 1;
+    if (slot == 0) ENSURE(h, W_W1T32, sizeof(T) * cnt, d); else ENSURE(h, W_W1T64, sizeof(T) * cnt, d);
+    if (h->wide_w1t_version[slot] != h->params_version) {
+        wide_transpose_w1_kernel<T, H, G><<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(m, p, d);
+        ++h->launches;
+        CK(h, cudaGetLastError());
+        h->wide_w1t_version[slot] = h->params_version;
+    }
+    *out = d;
+    return 0;
+}
+
 template <class T, int H, int G>
 int wide_forward(kanode_handle* h, const WideModel& m, const T* p, WideFwd<T> a, int64_t B, bool dense, WideCtl* ctl_out) {
     constexpr int GB = sizeof(T) == 4 ? 8 : 4;
     const int n = m.n;
     const WideLaunch L = wide_launch(n, B, GB);
+    const T* w1t = nullptr;
+    if (int rc = wide_w1t<T, H, G>(h, m, p, &w1t)) return rc;
     a.npart = L.ec;
     const size_t nB = (size_t)n * B;
     size_t bytes = wide_ctl_bytes(B) + sizeof(T) * (9 * nB + (size_t)B * (1 + W_HP + 2 * L.ec) + (size_t)L.nchunk * B * H) + sizeof(unsigned) * (size_t)B + 16 * 256;
@@ -982,7 +1083,7 @@ int wide_forward(kanode_handle* h, const WideModel& m, const T* p, WideFwd<T> a,
         in.base = a.uprev; in.ks = a.k; in.hs = a.h; in.ncoef = ncoef;
         for (int j = 0; j < ncoef; ++j) in.coef[j] = coef[j];
         in.xstore = xstore; in.mask = c.active;
-        wide_l1_fwd_kernel<T, H, G, 0><<<gr, W_BT, 0, st>>>(m, p, in, B, L.P, L.bt_red, part, hidden, counters);
+        wide_l1_fwd_kernel<T, H, G, 0><<<gr, W_BT, 0, st>>>(m, w1t, in, B, L.P, L.bt_red, part, hidden, counters);
         wide_l2_fwd_kernel<T, H, G><<<gp, W_BT, 0, st>>>(m, p, hidden, a.k + (size_t)kslot * nB, c.active, B, L.bt_par);
         launches += 2;
     };
@@ -1062,8 +1163,11 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     cudaEventRecord(h->ev[1], st);
     // ---- backward ----
     const WideLaunch L = wide_launch(n, B, GB);
-    const int gx1 = (int)std::min<int64_t>(((int64_t)n * (G + 1) + W_ET - 1) / W_ET, 256);
-    const int np_l = L.ec, np_1 = gx1, np_2 = L.uc * H, npart = np_l + np_1 + np_2;
+    const T* w1t = nullptr;
+    if (int rc = wide_w1t<T, H, G>(h, m, p, &w1t)) return rc;
+    constexpr int ROWS1 = W_GK * 2 * W_GT / H;
+    const int gx1 = (int)(((int64_t)n * (G + 1) + ROWS1 - 1) / ROWS1);
+    const int np_l = L.ec, np_1 = gx1, np_2 = L.uc, npart = np_l + np_1 + np_2;
     size_t bytes = wide_ctl_bytes(B) + sizeof(T) * (nB + 7 * nB * 3 + (size_t)7 * B * W_HP * 2 + (size_t)B * 15 + 2 * (size_t)B * npart +
                                                     (size_t)L.nchunk * B * H) + sizeof(unsigned) * (size_t)B + 24 * 256;
     char* base = nullptr;
@@ -1087,7 +1191,7 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     CK(h, cudaMemset2DAsync(g, sizeof(T) * 2 * np, 0, sizeof(T) * np, (size_t)B, st));        // g[b][0][:] = 0
     CK(h, cudaMemsetAsync(w.part0, 0, sizeof(T) * (size_t)B * npart, st));
     CK(h, cudaMemsetAsync(w.part1, 0, sizeof(T) * (size_t)B * npart, st));
-    const dim3 ge(L.ec, (unsigned)B), gr(L.nchunk, L.nbt_red), gp(L.uc, L.nbt_par), gg1(gx1, (unsigned)B), gg2(L.uc, H, (unsigned)B);
+    const dim3 ge(L.ec, (unsigned)B), gr(L.nchunk, L.nbt_red), gp(L.uc, L.nbt_par), gg1(gx1, (unsigned)B), gg2(L.uc, (unsigned)B);
     int64_t launches = 0;
     static const double A_[7][8] = KANODE_TSIT5_A;
     // adjoint rhs of stage slot s: records x_l / ybar_l, kl[s] = -(df/du)^T lambda_s
@@ -1095,13 +1199,13 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
         WideIn<T> in{};
         in.rec = w.rec; in.cap = cap; in.ridx = c.ridx + (size_t)s * B; in.th = w.th + (size_t)s * B; in.hd = w.hd + (size_t)s * B;
         in.xstore = w.x1 + (size_t)s * nB; in.mask = mask;
-        wide_l1_fwd_kernel<T, H, G, 1><<<gr, W_BT, 0, st>>>(m, p, in, B, L.P, L.bt_red, part, w.x2 + (size_t)s * B * W_HP, counters);
+        wide_l1_fwd_kernel<T, H, G, 1><<<gr, W_BT, 0, st>>>(m, w1t, in, B, L.P, L.bt_red, part, w.x2 + (size_t)s * B * W_HP, counters);
         WideIn<T> il{};
         il.base = w.lam; il.ks = w.kl; il.hs = w.h; il.ncoef = ncoef;
         for (int j = 0; j < ncoef; ++j) il.coef[j] = coef[j];
         il.xstore = w.yb2 + (size_t)s * nB; il.mask = mask;
         wide_l2_vjp_kernel<T, H, G><<<gr, W_BT, 0, st>>>(m, p, w.x2 + (size_t)s * B * W_HP, il, B, L.P, L.bt_red, part, w.yb1 + (size_t)s * B * W_HP, counters);
-        wide_l1_vjp_kernel<T, H, G><<<gp, W_BT, 0, st>>>(m, p, w.x1 + (size_t)s * nB, w.yb1 + (size_t)s * B * W_HP, w.kl + (size_t)s * nB, mask, B, L.bt_par);
+        wide_l1_vjp_kernel<T, H, G><<<gp, W_BT, 0, st>>>(m, w1t, w.x1 + (size_t)s * nB, w.yb1 + (size_t)s * B * W_HP, w.kl + (size_t)s * nB, mask, B, L.bt_par);
         launches += 3;
     };
     WideGp<T> gpa{};
@@ -1110,9 +1214,9 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     auto gpass = [&](int mode, T* dst) {
         WideGp<T> q1 = gpa, q2 = gpa;
         q1.es_part = dst; q1.off = np_l; q2.es_part = dst; q2.off = np_l + np_1;
-        if (mode == 0) { wide_gp1_kernel<T, H, G, 0><<<gg1, W_ET, 0, st>>>(m, q1, B); wide_gp2_kernel<T, H, G, 0><<<gg2, W_BT, 0, st>>>(m, q2, B); }
-        else if (mode == 1) { wide_gp1_kernel<T, H, G, 1><<<gg1, W_ET, 0, st>>>(m, q1, B); wide_gp2_kernel<T, H, G, 1><<<gg2, W_BT, 0, st>>>(m, q2, B); }
-        else { wide_gp1_kernel<T, H, G, 2><<<gg1, W_ET, 0, st>>>(m, q1, B); wide_gp2_kernel<T, H, G, 2><<<gg2, W_BT, 0, st>>>(m, q2, B); }
+        if (mode == 0) { wide_gp1_kernel<T, H, G, 0><<<gg1, W_GT, 0, st>>>(m, q1, B); wide_gp2_kernel<T, H, G, 0><<<gg2, W_BT, 0, st>>>(m, q2, B); }
+        else if (mode == 1) { wide_gp1_kernel<T, H, G, 1><<<gg1, W_GT, 0, st>>>(m, q1, B); wide_gp2_kernel<T, H, G, 1><<<gg2, W_BT, 0, st>>>(m, q2, B); }
+        else { wide_gp1_kernel<T, H, G, 2><<<gg1, W_GT, 0, st>>>(m, q1, B); wide_gp2_kernel<T, H, G, 2><<<gg2, W_BT, 0, st>>>(m, q2, B); }
         launches += 2;
     };
     wide_bwd_ctl_kernel<T><<<(unsigned)B, 128, 0, st>>>(c, w, n, B, -1);
