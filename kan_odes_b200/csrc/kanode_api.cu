@@ -184,7 +184,7 @@ int solve_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double t1, 
     };
     if (small_dispatch<T>(h, run, rc)) return rc;
     WideKey wk;
-    if (h->wide && wide_match(h->desc, wk))
+    if (h->wide && wide_match(h->desc, wk) && (int64_t)B * h->n * 8 < (1ll << 31))
         return wide_solve(h, wk, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);
     return generic_solve<T>(h, d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);
 }
@@ -336,7 +336,7 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
     };
     if (small_dispatch<T>(h, run, rc)) return rc;
     WideKey wk;
-    if (h->wide && wide_match(h->desc, wk))
+    if (h->wide && wide_match(h->desc, wk) && (int64_t)B * h->n * 8 < (1ll << 31))
         return wide_loss_grad(h, wk, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum,
                               d_grad_sum, d_du0, d_fst, d_bst, d_out_opt);
     return generic_loss_grad<T>(h, d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum, d_grad_sum,

@@ -54,6 +54,9 @@ struct WideCtl {
 constexpr int W_NCTL_D = 10, W_NCTL_I = 16 + 7;
 
 template <class T> __device__ __forceinline__ T ld_cg(const T* p) { return __ldcg(p); }
+// ratio for the error norm: fp32 uses rcp.approx (1 ulp; it only feeds EEst), fp64 the IEEE quotient
+__device__ __forceinline__ float wdiv(float a, float b) { return a * krcp(b); }
+__device__ __forceinline__ double wdiv(double a, double b) { return a / b; }
 
 template <class T> __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
@@ -98,19 +101,51 @@ template <class T> struct WideIn {
     const int* mask;     // per-IC, 0 = skip (may be null)
 };
 
-template <class T, int MODE> __device__ __forceinline__ T wide_input(const WideIn<T>& in, int b, int i, int n, int64_t B) {
-    if (MODE == 0) {
-        const int64_t e = (int64_t)b * n + i;
-        T acc = T(0);
-        for (int j = 0; j < in.ncoef; ++j) acc += in.coef[j] * in.ks[(int64_t)j * B * n + e];
-        return in.ncoef > 0 ? in.base[e] + in.hs[b] * acc : in.base[e];
-    } else {
-        T bw[7]; interp_weights(in.th[b], bw);
-        const T* r = in.rec + ((int64_t)b * in.cap + in.ridx[b]) * 8 * (int64_t)n;
-        T acc = T(0);
+// Inputs of unit i for the NB ICs b0..b0+NB of a tile.  All global loads are issued before the first dependent FMA (the
+// loop is written in phases and fully unrolled), so one memory latency covers the whole tile.
+template <class T, int MODE, int NB>
+__device__ __forceinline__ void wide_inputs(const WideIn<T>& in, int b0, int b1, int i, bool valid, int n, int64_t B, T (&xs)[NB], bool (&on)[NB]) {
 #pragma unroll
-        for (int j = 0; j < 7; ++j) acc += bw[j] * r[(int64_t)(1 + j) * n + i];
-        return r[i] + in.hd[b] * acc;
+    for (int bl = 0; bl < NB; ++bl) { const int b = b0 + bl; on[bl] = valid && b < b1 && (!in.mask || in.mask[b]); }
+    if (MODE == 0) {
+        T base[NB], hs[NB], kv[NB][6];
+        const int Bn = (int)B * n;
+#pragma unroll
+        for (int bl = 0; bl < NB; ++bl) {
+            const int e = (b0 + bl) * n + i;
+            base[bl] = on[bl] ? in.base[e] : T(0);
+            hs[bl] = on[bl] && in.ncoef > 0 ? in.hs[b0 + bl] : T(0);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) kv[bl][j] = (on[bl] && j < in.ncoef) ? in.ks[(int64_t)j * Bn + e] : T(0);
+        }
+#pragma unroll
+        for (int bl = 0; bl < NB; ++bl) {
+            T acc = T(0);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) acc += in.coef[j] * kv[bl][j];
+            xs[bl] = in.ncoef > 0 ? base[bl] + hs[bl] * acc : base[bl];
+        }
+    } else {
+        T th[NB], hd[NB], raw[NB][8];
+        const T* r[NB];
+#pragma unroll
+        for (int bl = 0; bl < NB; ++bl) {
+            const int b = on[bl] ? b0 + bl : b0;
+            th[bl] = in.th[b]; hd[bl] = in.hd[b];
+            r[bl] = in.rec + ((int64_t)b * in.cap + in.ridx[b]) * 8 * (int64_t)n + i;
+        }
+#pragma unroll
+        for (int bl = 0; bl < NB; ++bl)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) raw[bl][j] = on[bl] ? r[bl][j * n] : T(0);
+#pragma unroll
+        for (int bl = 0; bl < NB; ++bl) {
+            T bw[7]; interp_weights(th[bl], bw);
+            T acc = T(0);
+#pragma unroll
+            for (int j = 0; j < 7; ++j) acc += bw[j] * raw[bl][1 + j];
+            xs[bl] = raw[bl][0] + hd[bl] * acc;
+        }
     }
 }
 
@@ -161,16 +196,11 @@ __global__ void __launch_bounds__(W_BT) wide_l1_fwd_kernel(const __grid_constant
     for (int pass = 0; pass < P; ++pass) {
         const int i = (blockIdx.x * P + pass) * W_BT + tid;
         const bool valid = i < n;
+        T xs[GB]; bool on[GB];
+        wide_inputs<T, MODE, GB>(in, b0, b1, i, valid, n, B, xs, on);
         T w[NW];
 #pragma unroll
-        for (int k = 0; k < NW; ++k) w[k] = valid ? w1t[(int64_t)k * n + i] : T(0);     // [NW][n]: coalesced over the units
-        T xs[GB]; bool on[GB];
-#pragma unroll
-        for (int bl = 0; bl < GB; ++bl) {                                                // all loads of the tile in flight together
-            const int b = b0 + bl;
-            on[bl] = valid && b < b1 && (!in.mask || in.mask[b]);
-            xs[bl] = on[bl] ? wide_input<T, MODE>(in, b, i, n, B) : T(0);
-        }
+        for (int k = 0; k < NW; ++k) w[k] = valid ? w1t[k * n + i] : T(0);               // [NW][n]: coalesced over the units
 #pragma unroll
         for (int bl = 0; bl < GB; ++bl) {
             if (b0 + bl >= b1) break;
@@ -203,10 +233,12 @@ __global__ void __launch_bounds__(W_BT) wide_l1_fwd_kernel(const __grid_constant
 template <class T, int H, int G> __device__ __forceinline__ void wide_load_w2(const WideModel& m, const T* __restrict__ p, int o, T (&w)[H * (G + 1)]) {
     constexpr int NQ = G + 1;
 #pragma unroll
+    const T* c2 = p + m.offC2 + o;
+    const T* w2 = p + m.offW2 + o;
     for (int j = 0; j < H; ++j) {
 #pragma unroll
-        for (int q = 0; q < G; ++q) w[j * NQ + q] = p[m.offC2 + (int64_t)(j * G + q) * m.n + o];
-        w[j * NQ + G] = p[m.offW2 + (int64_t)j * m.n + o];
+        for (int q = 0; q < G; ++q) w[j * NQ + q] = c2[(j * G + q) * m.n];
+        w[j * NQ + G] = w2[j * m.n];
     }
 }
 
@@ -275,19 +307,17 @@ __global__ void __launch_bounds__(W_BT) wide_l2_vjp_kernel(const __grid_constant
     for (int pass = 0; pass < P; ++pass) {
         const int o = (blockIdx.x * P + pass) * W_BT + tid;
         const bool valid = o < n;
+        T lam[GB]; bool on[GB];
+        wide_inputs<T, 0, GB>(in, b0, b1, o, valid, n, B, lam, on);
         T w[NW];
         if (valid) wide_load_w2<T, H, G>(m, p, o, w);
         else {
 #pragma unroll
             for (int k = 0; k < NW; ++k) w[k] = T(0);
         }
-        T lam[GB];
+        if (in.xstore) {
 #pragma unroll
-        for (int bl = 0; bl < GB; ++bl) {
-            const int b = b0 + bl;
-            const bool on = valid && b < b1 && (!in.mask || in.mask[b]);
-            lam[bl] = on ? wide_input<T, 0>(in, b, o, n, B) : T(0);
-            if (on && in.xstore) in.xstore[(int64_t)b * n + o] = lam[bl];
+            for (int bl = 0; bl < GB; ++bl) if (on[bl]) in.xstore[(b0 + bl) * n + o] = lam[bl];
         }
 #pragma unroll
         for (int j = 0; j < H; ++j) {
@@ -405,33 +435,44 @@ template <class T> __device__ __forceinline__ void gp_finalize(const T* gold, T*
 // Layer 1: its slice of g is one contiguous array of (n*G + n) rows x H (C1 rows (i,q), then the W1 rows i), streamed with
 // coalesced 2-element accesses.  A thread's output pair o0 = (2*tid) % H is the same in every iteration (2*W_GT % H == 0),
 // so its 2 x 7 x 2 weighted cotangents stay in registers; the 7 stage features of a row come from shared memory.
-constexpr int W_GT = 320, W_GK = 8;      // threads per block, iterations per block (tile = W_GK * 2 * W_GT elements)
+constexpr int W_GT = 320, W_GK = 5;      // threads per block, iterations per block (tile = W_GK * 2 * W_GT elements)
 template <class T> struct alignas(2 * sizeof(T)) WVec2 { T x, y; };
 
+// grid.x = nblkC blocks over the C1 rows (tiles aligned to whole input units) followed by the blocks over the W1 rows
 template <class T, int H, int G, int MODE>
-__global__ void __launch_bounds__(W_GT) wide_gp1_kernel(const __grid_constant__ WideModel m, const WideGp<T> a, int64_t B) {
+__global__ void __launch_bounds__(W_GT) wide_gp1_kernel(const __grid_constant__ WideModel m, const WideGp<T> a, int64_t B, int nblkC) {
     static_assert(H % 2 == 0 && (2 * W_GT) % H == 0, "pair mapping");
     constexpr int NS = MODE == 0 ? 7 : (MODE == 1 ? 1 : 2);
-    constexpr int ROWS = W_GK * 2 * W_GT / H;
+    constexpr int ROWS = W_GK * 2 * W_GT / H, UNITS = ROWS / G;
+    static_assert(ROWS % G == 0, "tiles hold whole input units");
     __shared__ T C[NS][ROWS];
     __shared__ T sred[33];
     const int b = blockIdx.y, tid = threadIdx.x, n = m.n;
     if (a.mask && !a.mask[b]) return;
-    const int64_t nrowC = (int64_t)n * G, nrow = nrowC + n;
-    const int64_t row0 = (int64_t)blockIdx.x * ROWS;
+    const bool segW = (int)blockIdx.x >= nblkC;
+    const int row0 = (segW ? (int)blockIdx.x - nblkC : (int)blockIdx.x) * ROWS;       // row within the segment
+    const int nrows = segW ? n : n * G;
     const T inv_h = (T)m.inv_h1;
-    for (int idx = tid; idx < NS * ROWS; idx += W_GT) {
-        const int s = idx / ROWS, rl = idx - s * ROWS;
-        const int64_t R = row0 + rl;
-        T c = T(0);
-        if (R < nrowC) {
-            const int i = (int)(R / G), q = (int)(R - (int64_t)i * G);
-            const T aa = (normalize_rt(m.norm1, a.x1[((int64_t)s * B + b) * n + i]) - (T)m.grid1[q]) * inv_h;
-            c = kexp(-aa * aa);
-        } else if (R < nrow) {
-            swish_fwd(a.x1[((int64_t)s * B + b) * n + (R - nrowC)], c);
+    if (!segW) {
+        const int i0 = row0 / G;
+        for (int idx = tid; idx < NS * UNITS; idx += W_GT) {
+            const int s = idx / UNITS, il = idx - s * UNITS, i = i0 + il;
+            if (i < n) {
+                const T xn = normalize_rt(m.norm1, a.x1[((int64_t)s * B + b) * n + i]);
+#pragma unroll
+                for (int q = 0; q < G; ++q) { const T aa = (xn - (T)m.grid1[q]) * inv_h; C[s][il * G + q] = kexp(-aa * aa); }
+            } else {
+#pragma unroll
+                for (int q = 0; q < G; ++q) C[s][il * G + q] = T(0);
+            }
         }
-        C[s][rl] = c;
+    } else {
+        for (int idx = tid; idx < NS * ROWS; idx += W_GT) {
+            const int s = idx / ROWS, rl = idx - s * ROWS, i = row0 + rl;
+            T c = T(0);
+            if (i < n) swish_fwd(a.x1[((int64_t)s * B + b) * n + i], c);
+            C[s][rl] = c;
+        }
     }
     const int o0 = (2 * tid) % H;
     T ab[NS][2], at[NS][2];
@@ -444,23 +485,23 @@ __global__ void __launch_bounds__(W_GT) wide_gp1_kernel(const __grid_constant__ 
             else { ab[s][k] = yb; at[s][k] = T(0); }
         }
     __syncthreads();
+    const int64_t seg = segW ? m.offW1 : m.offC1;
     const T* gold = nullptr; T* gnew = nullptr;
-    if (MODE == 0) { const int cur = a.cur[b]; gold = a.g + ((int64_t)b * 2 + cur) * m.np + m.offC1; gnew = a.g + ((int64_t)b * 2 + (cur ^ 1)) * m.np + m.offC1; }
-    const int64_t e0 = row0 * H, E = nrow * H;
+    if (MODE == 0) { const int cur = a.cur[b]; gold = a.g + ((int64_t)b * 2 + cur) * m.np + seg + (int64_t)row0 * H; gnew = a.g + ((int64_t)b * 2 + (cur ^ 1)) * m.np + seg + (int64_t)row0 * H; }
+    const int E = (nrows - row0) * H;             // elements of this tile that exist
     T es = T(0);
     WVec2<T> g0[W_GK];
     if (MODE == 0) {
 #pragma unroll
         for (int k = 0; k < W_GK; ++k) {
-            const int64_t e = e0 + 2 * tid + (int64_t)k * 2 * W_GT;
-            g0[k] = e < E ? *reinterpret_cast<const WVec2<T>*>(gold + e) : WVec2<T>{T(0), T(0)};
+            const int el = 2 * tid + k * 2 * W_GT;
+            g0[k] = el < E ? *reinterpret_cast<const WVec2<T>*>(gold + el) : WVec2<T>{T(0), T(0)};
         }
     }
 #pragma unroll
     for (int k = 0; k < W_GK; ++k) {
         const int el = 2 * tid + k * 2 * W_GT;
-        const int64_t e = e0 + el;
-        if (e >= E) break;
+        if (el >= E) break;
         const int rl = el / H;
         if (MODE == 0) {
             T vb0 = T(0), vb1 = T(0), vt0 = T(0), vt1 = T(0);
@@ -468,10 +509,10 @@ __global__ void __launch_bounds__(W_GT) wide_gp1_kernel(const __grid_constant__ 
             for (int s = 0; s < 7; ++s) { const T c = C[s][rl]; vb0 += ab[s][0] * c; vb1 += ab[s][1] * c; vt0 += at[s][0] * c; vt1 += at[s][1] * c; }
             WVec2<T> g1;
             g1.x = g0[k].x + vb0; g1.y = g0[k].y + vb1;
-            const T r0 = vt0 / (a.abstol + kmax(kabs(g0[k].x), kabs(g1.x)) * a.reltol);
-            const T r1 = vt1 / (a.abstol + kmax(kabs(g0[k].y), kabs(g1.y)) * a.reltol);
+            const T r0 = wdiv(vt0, a.abstol + kmax(kabs(g0[k].x), kabs(g1.x)) * a.reltol);
+            const T r1 = wdiv(vt1, a.abstol + kmax(kabs(g0[k].y), kabs(g1.y)) * a.reltol);
             es += r0 * r0; es += r1 * r1;
-            *reinterpret_cast<WVec2<T>*>(gnew + e) = g1;
+            *reinterpret_cast<WVec2<T>*>(gnew + el) = g1;
         } else if (MODE == 1) {
             const T x0 = (ab[0][0] * C[0][rl]) / a.abstol, x1 = (ab[0][1] * C[0][rl]) / a.abstol;
             es += x0 * x0; es += x1 * x1;
@@ -539,7 +580,7 @@ __global__ void __launch_bounds__(W_BT) wide_gp2_kernel(const __grid_constant__ 
 #pragma unroll
                     for (int s = 0; s < 7; ++s) { vb += al[s] * fs[s]; vt += alt[s] * fs[s]; }
                     const T g1 = g0[q] + vb;
-                    const T r = vt / (a.abstol + kmax(kabs(g0[q]), kabs(g1)) * a.reltol);
+                    const T r = wdiv(vt, a.abstol + kmax(kabs(g0[q]), kabs(g1)) * a.reltol);
                     es += r * r;
                     gnew[(int64_t)(q < G ? j * G + q : H * G + j) * n] = g1;
                 } else if (MODE == 1) {
@@ -1166,7 +1207,7 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     const T* w1t = nullptr;
     if (int rc = wide_w1t<T, H, G>(h, m, p, &w1t)) return rc;
     constexpr int ROWS1 = W_GK * 2 * W_GT / H;
-    const int gx1 = (int)(((int64_t)n * (G + 1) + ROWS1 - 1) / ROWS1);
+    const int nblkC = (int)(((int64_t)n * G + ROWS1 - 1) / ROWS1), gx1 = nblkC + (n + ROWS1 - 1) / ROWS1;
     const int np_l = L.ec, np_1 = gx1, np_2 = L.uc, npart = np_l + np_1 + np_2;
     size_t bytes = wide_ctl_bytes(B) + sizeof(T) * (nB + 7 * nB * 3 + (size_t)7 * B * W_HP * 2 + (size_t)B * 15 + 2 * (size_t)B * npart +
                                                     (size_t)L.nchunk * B * H) + sizeof(unsigned) * (size_t)B + 24 * 256;
@@ -1214,9 +1255,9 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     auto gpass = [&](int mode, T* dst) {
         WideGp<T> q1 = gpa, q2 = gpa;
         q1.es_part = dst; q1.off = np_l; q2.es_part = dst; q2.off = np_l + np_1;
-        if (mode == 0) { wide_gp1_kernel<T, H, G, 0><<<gg1, W_GT, 0, st>>>(m, q1, B); wide_gp2_kernel<T, H, G, 0><<<gg2, W_BT, 0, st>>>(m, q2, B); }
-        else if (mode == 1) { wide_gp1_kernel<T, H, G, 1><<<gg1, W_GT, 0, st>>>(m, q1, B); wide_gp2_kernel<T, H, G, 1><<<gg2, W_BT, 0, st>>>(m, q2, B); }
-        else { wide_gp1_kernel<T, H, G, 2><<<gg1, W_GT, 0, st>>>(m, q1, B); wide_gp2_kernel<T, H, G, 2><<<gg2, W_BT, 0, st>>>(m, q2, B); }
+        if (mode == 0) { wide_gp1_kernel<T, H, G, 0><<<gg1, W_GT, 0, st>>>(m, q1, B, nblkC); wide_gp2_kernel<T, H, G, 0><<<gg2, W_BT, 0, st>>>(m, q2, B); }
+        else if (mode == 1) { wide_gp1_kernel<T, H, G, 1><<<gg1, W_GT, 0, st>>>(m, q1, B, nblkC); wide_gp2_kernel<T, H, G, 1><<<gg2, W_BT, 0, st>>>(m, q2, B); }
+        else { wide_gp1_kernel<T, H, G, 2><<<gg1, W_GT, 0, st>>>(m, q1, B, nblkC); wide_gp2_kernel<T, H, G, 2><<<gg2, W_BT, 0, st>>>(m, q2, B); }
         launches += 2;
     };
     wide_bwd_ctl_kernel<T><<<(unsigned)B, 128, 0, st>>>(c, w, n, B, -1);
