@@ -219,6 +219,12 @@ int kanode_set_record_capacity(kanode_handle* h, int32_t max_steps);
  * ms[2] = gradient reduction.  Blocks until that call has finished. */
 int kanode_last_timing(kanode_handle* h, float* ms3);
 
+/* wide (batched lockstep) engine only: device time [ms] spent in the step-end passes over the per-IC gradient state g
+ * (the HBM-bound kernels wide_gp1/wide_gp2) during the LAST kanode_loss_grad*() call, and the number of such passes
+ * (= lockstep step attempts).  CUDA events around each pass on the handle's stream.  Fails if the last call did not
+ * go through the wide engine. */
+int kanode_last_gpass_timing(kanode_handle* h, float* ms, int32_t* passes);
+
 /* number of kernel launches issued by this handle since creation (for bench accounting) */
 int64_t kanode_launch_count(const kanode_handle* h);
 

@@ -59,7 +59,7 @@ EXPORTED_SYMBOLS = (
     "kanode_vjp", "kanode_solve", "kanode_solve_dev", "kanode_loss_grad", "kanode_loss_grad_dev",
     "kanode_launch_count", "kanode_set_record_capacity",
     "kanode_set_params_f64", "kanode_rhs_f64", "kanode_vjp_f64", "kanode_solve_f64", "kanode_loss_grad_f64",
-    "kanode_loss_grad_dev_f64", "kanode_last_timing", "kanode_adam_step_dev",
+    "kanode_loss_grad_dev_f64", "kanode_last_timing", "kanode_adam_step_dev", "kanode_last_gpass_timing",
 )
 
 _lib = None
@@ -109,6 +109,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.kanode_adam_step_dev.restype = C.c_int
     lib.kanode_last_timing.argtypes = [vp, vp]
     lib.kanode_last_timing.restype = C.c_int
+    lib.kanode_last_gpass_timing.argtypes = [vp, vp, vp]
+    lib.kanode_last_gpass_timing.restype = C.c_int
     lib.kanode_launch_count.restype = C.c_int64
     lib.kanode_launch_count.argtypes = [vp]
     for name in ("kanode_create", "kanode_destroy", "kanode_sync", "kanode_set_params", "kanode_set_params_dev",

@@ -196,6 +196,7 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
     if (!h->have_params) return fail(h, KANODE_ERR_INVALID, "parameters not set");
     if (int rc = check_saveat(h, t0, t1, saveat, nsave)) return rc;
     if (nsave < 1) return fail(h, KANODE_ERR_INVALID, "loss needs at least one save time");
+    h->wide_gp_used = 0;
     CK(h, cudaMemsetAsync(d_loss_sum, 0, sizeof(double), h->stream));
     if (B <= 0) { CK(h, cudaMemsetAsync(d_grad_sum, 0, sizeof(T) * h->np, h->stream)); return 0; }
     const double* d_saveat = nullptr;
@@ -504,6 +505,7 @@ int kanode_destroy(kanode_handle* h) {
     for (auto& b : h->ws) if (b.p) cudaFree(b.p);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->aux_ev) if (e) cudaEventDestroy(e);
+    for (auto& e : h->wide_gp_ev) cudaEventDestroy(e);
     if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -542,6 +544,16 @@ int kanode_last_timing(kanode_handle* h, float* ms3) {
     if (!ms3 || !h->ev_valid) return fail(h, KANODE_ERR_INVALID, "no timed loss_grad call yet");
     CK(h, cudaEventSynchronize(h->ev[3]));
     for (int i = 0; i < 3; ++i) CK(h, cudaEventElapsedTime(&ms3[i], h->ev[i], h->ev[i + 1]));
+    return 0;
+}
+
+int kanode_last_gpass_timing(kanode_handle* h, float* ms, int32_t* passes) {
+    if (int rc = enter(h)) return rc;
+    if (!ms || !passes || !h->ev_valid || h->wide_gp_used < 2) return fail(h, KANODE_ERR_INVALID, "no wide loss_grad call yet");
+    CK(h, cudaEventSynchronize(h->ev[3]));
+    float tot = 0.f;
+    for (int i = 0; i + 1 < h->wide_gp_used; i += 2) { float t = 0.f; CK(h, cudaEventElapsedTime(&t, h->wide_gp_ev[i], h->wide_gp_ev[i + 1])); tot += t; }
+    *ms = tot; *passes = h->wide_gp_used / 2;
     return 0;
 }
 

@@ -66,6 +66,8 @@ struct kanode_handle {
     int wide = 1;                            // 0: force the block-per-trajectory kernels (KANODE_WIDE=0)
     int wide_iters[3] = {0, 0, 0};
     uint64_t wide_w1t_version[2] = {~0ull, ~0ull};
+    std::vector<cudaEvent_t> wide_gp_ev;     // event pairs around the g passes of the last wide loss_grad call
+    int wide_gp_used = 0;
     bool wide_counters_zeroed[2] = {false, false};
     const void* wide_counters_ptr[2] = {nullptr, nullptr};
 };

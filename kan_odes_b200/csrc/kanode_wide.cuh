@@ -28,6 +28,8 @@
 #include "kanode_host.h"
 #include "kanode_math.cuh"
 #include "kanode_wide_api.h"
+#include <algorithm>
+#include <cstdlib>
 
 namespace kanode {
 
@@ -185,7 +187,7 @@ __device__ __forceinline__ void wide_reduce_tail(T (*red)[W_BT + 1], int b0, int
 // grid (nchunk, nbt); block W_BT; each block walks P passes of W_BT units and <= GB ICs
 // ---------------------------------------------------------------------------------------------------------
 template <class T, int H, int G, int MODE>
-__global__ void __launch_bounds__(W_BT) wide_l1_fwd_kernel(const __grid_constant__ WideModel m, const T* __restrict__ w1t, const WideIn<T> in,
+__global__ void __launch_bounds__(W_BT, 3) wide_l1_fwd_kernel(const __grid_constant__ WideModel m, const T* __restrict__ w1t, const WideIn<T> in,
                                                            int64_t B, int P, int btile, T* part, T* hidden, unsigned* counters) {
     constexpr int NQ = G + 1, NW = H * NQ, GB = sizeof(T) == 4 ? 8 : 4;
     __shared__ T red[GB * H][W_BT + 1];
@@ -243,7 +245,7 @@ template <class T, int H, int G> __device__ __forceinline__ void wide_load_w2(co
 }
 
 template <class T, int H, int G>
-__global__ void __launch_bounds__(W_BT) wide_l2_fwd_kernel(const __grid_constant__ WideModel m, const T* __restrict__ p, const T* hidden, T* out,
+__global__ void __launch_bounds__(W_BT, 3) wide_l2_fwd_kernel(const __grid_constant__ WideModel m, const T* __restrict__ p, const T* hidden, T* out,
                                                            const int* mask, int64_t B, int btile) {
     constexpr int NQ = G + 1, NW = H * NQ;
     __shared__ __align__(16) T f2[NW][W_PT];              // features, IC index fastest: one vector load feeds 4 ICs
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(W_BT) wide_l2_fwd_kernel(const __grid_constant
 // lam = lprev + h * sum a_sj kl_j is formed here (and stored: it is ybar of layer 2 in the stage record)
 // ---------------------------------------------------------------------------------------------------------
 template <class T, int H, int G>
-__global__ void __launch_bounds__(W_BT) wide_l2_vjp_kernel(const __grid_constant__ WideModel m, const T* __restrict__ p, const T* hidden,
+__global__ void __launch_bounds__(W_BT, 3) wide_l2_vjp_kernel(const __grid_constant__ WideModel m, const T* __restrict__ p, const T* hidden,
                                                            const WideIn<T> in, int64_t B, int P, int btile, T* part, T* hbar, unsigned* counters) {
     constexpr int NQ = G + 1, NW = H * NQ, GB = sizeof(T) == 4 ? 8 : 4;
     __shared__ T red[GB * H][W_BT + 1];
@@ -353,7 +355,7 @@ __global__ void __launch_bounds__(W_BT) wide_l2_vjp_kernel(const __grid_constant
 // layer 1 reverse: dl[b][i] = -( dnorm * sum_g db_g/h * (w1[g][:] . hbar[b]) + dswish * (W1[i][:] . hbar[b]) )
 // ---------------------------------------------------------------------------------------------------------
 template <class T, int H, int G>
-__global__ void __launch_bounds__(W_BT) wide_l1_vjp_kernel(const __grid_constant__ WideModel m, const T* __restrict__ w1t, const T* x1, const T* hbar,
+__global__ void __launch_bounds__(W_BT, 3) wide_l1_vjp_kernel(const __grid_constant__ WideModel m, const T* __restrict__ w1t, const T* x1, const T* hbar,
                                                            T* dl, const int* mask, int64_t B, int btile) {
     constexpr int NW = H * (G + 1), PF = 8;
     __shared__ T hb[W_PT][W_HP];
@@ -1035,9 +1037,10 @@ inline WideModel wide_model(const kanode_handle* h) {
 struct WideLaunch { int P, nchunk, bt_red, nbt_red, bt_par, nbt_par, uc, ec; };
 inline WideLaunch wide_launch(int n, int64_t B, int GB) {
     WideLaunch L{};
+    static const int maxch = [] { const char* e = std::getenv("KANODE_WIDE_MAXCH"); return e ? std::atoi(e) : W_MAXCH; }();   // tuning experiments
     L.uc = (n + W_BT - 1) / W_BT;
     L.ec = (n + W_ET - 1) / W_ET;
-    L.P = (L.uc + W_MAXCH - 1) / W_MAXCH;
+    L.P = (L.uc + maxch - 1) / maxch;
     L.nchunk = (L.uc + L.P - 1) / L.P;
     int bt = (int)((B * L.nchunk + 295) / 296);
     L.bt_red = bt < 1 ? 1 : (bt > GB ? GB : bt);
@@ -1252,12 +1255,19 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     WideGp<T> gpa{};
     gpa.x1 = w.x1; gpa.yb1 = w.yb1; gpa.x2 = w.x2; gpa.yb2 = w.yb2; gpa.g = g; gpa.cur = c.cur; gpa.h = w.h; gpa.mask = c.active;
     gpa.abstol = w.abstol; gpa.reltol = w.reltol; gpa.npart = npart;
+    h->wide_gp_used = 0;
+    auto gp_event = [&]() {
+        if ((size_t)h->wide_gp_used == h->wide_gp_ev.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; h->wide_gp_ev.push_back(e); }
+        cudaEventRecord(h->wide_gp_ev[h->wide_gp_used++], st);
+    };
     auto gpass = [&](int mode, T* dst) {
         WideGp<T> q1 = gpa, q2 = gpa;
+        if (mode == 0) gp_event();
         q1.es_part = dst; q1.off = np_l; q2.es_part = dst; q2.off = np_l + np_1;
         if (mode == 0) { wide_gp1_kernel<T, H, G, 0><<<gg1, W_GT, 0, st>>>(m, q1, B, nblkC); wide_gp2_kernel<T, H, G, 0><<<gg2, W_BT, 0, st>>>(m, q2, B); }
         else if (mode == 1) { wide_gp1_kernel<T, H, G, 1><<<gg1, W_GT, 0, st>>>(m, q1, B, nblkC); wide_gp2_kernel<T, H, G, 1><<<gg2, W_BT, 0, st>>>(m, q2, B); }
         else { wide_gp1_kernel<T, H, G, 2><<<gg1, W_GT, 0, st>>>(m, q1, B, nblkC); wide_gp2_kernel<T, H, G, 2><<<gg2, W_BT, 0, st>>>(m, q2, B); }
+        if (mode == 0) gp_event();
         launches += 2;
     };
     wide_bwd_ctl_kernel<T><<<(unsigned)B, 128, 0, st>>>(c, w, n, B, -1);
