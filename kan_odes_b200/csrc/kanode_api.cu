@@ -140,6 +140,8 @@ template <class T> int rhs_dev(kanode_handle* h, const T* d_u, T* d_du, int64_t 
         return 0;
     };
     if (small_dispatch<T>(h, run, rc)) return rc;
+    WideKey wk;
+    if (h->wide && wide_match(h->desc, wk) && (int64_t)B * h->n * 8 < (1ll << 31)) return wide_rhs(h, wk, generic_params<T>(h), d_u, d_du, B);
     return generic_rhs<T>(h, d_u, d_du, B);
 }
 
@@ -480,6 +482,7 @@ int kanode_create(const kanode_desc* desc, int device, void* stream, kanode_hand
     if (const char* e = std::getenv("KANODE_LOCKSTEP")) h->lockstep = std::atoi(e);
     if (const char* e = std::getenv("KANODE_SCHEDULE")) h->schedule = std::atoi(e);
     if (const char* e = std::getenv("KANODE_WIDE")) h->wide = std::atoi(e);
+    if (const char* e = std::getenv("KANODE_WIDE_TC")) h->wide_tc = std::atoi(e);
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, KANODE_ERR_CUDA, "cudaSetDevice failed"); }
     if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
     else {

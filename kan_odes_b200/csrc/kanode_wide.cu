@@ -4,6 +4,10 @@
 namespace kanode {
 
 #define KANODE_WIDE_DEF(T)                                                                                                       \
+    int wide_rhs(kanode_handle* h, WideKey k, const T* p, const T* d_u, T* d_du, int64_t B) {                                   \
+        if (k.G == 5) return wide_rhs_t<T, 10, 5>(h, p, d_u, d_du, B);                                                           \
+        return wide_rhs_t<T, 10, 10>(h, p, d_u, d_du, B);                                                                        \
+    }                                                                                                                            \
     int wide_solve(kanode_handle* h, WideKey k, const T* p, const T* d_u0, int64_t B, double t0, double t1, const double* d_saveat, \
                    int nsave, double abstol, double reltol, T* d_out, kanode_stats* d_stats) {                                   \
         if (k.G == 5) return wide_solve_t<T, 10, 5>(h, p, d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);     \

@@ -284,6 +284,164 @@ __global__ void __launch_bounds__(W_BT, 3) wide_l2_fwd_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// layer 2 forward on the 5th-generation tensor cores (fp32 instantiation): the expand contraction
+//     out[o][b] = sum_r w2[o][r] * f2[b][r]        M = 128 output units per CTA, N = 32 ICs, K = H*(G+1) padded to 112
+// is a dense GEMM tile.  tcgen05.mma kind::tf32 (FP32 accumulate in TMEM) with the 3xTF32 split
+//     a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo ,  x_hi = x with the low 13 mantissa bits cleared, x_lo = x - x_hi
+// keeps ~22 mantissa bits (the fp32 parity budget is 1e-5).  The weight operand comes from a device image that is
+// already in the UMMA shared-memory layout (K-major, no swizzle: [K/4][128 rows][4] = 8x16-byte core matrices), so one
+// bulk async copy (TMA, mbarrier completion) stages it; the feature operand is produced by the CTA's threads in the
+// same layout.  One elected thread issues the 14 x 3 MMAs, tcgen05.commit signals the epilogue, each warp reads its
+// 32 TMEM lanes (tcgen05.ld 32x32b) and stores out[b][o] coalesced over o.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TC_M = 128, TC_N = 32;
+__device__ __forceinline__ uint32_t w_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void w_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(w_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void w_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(w_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void w_tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(w_smem_u32(dst)), "l"(src), "r"(bytes), "r"(w_smem_u32(bar)) : "memory");
+}
+// bounded wait: a mis-programmed pipeline traps instead of hanging the GPU
+__device__ __forceinline__ void w_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(w_smem_u32(bar)), "r"(parity) : "memory");
+        if (!ok && spin > (1u << 26)) __trap();
+    }
+}
+// UMMA shared-memory descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B; lbo = byte distance between the two
+// 16-byte K chunks of one MMA, sbo = byte distance between 8-row groups   [cute/arch/mma_sm100_desc.hpp: SmemDescriptor]
+__device__ __forceinline__ uint64_t w_umma_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void w_umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ float w_tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// device image of the layer-2 weights for the tensor-core kernel: [ceil(n/128)][hi|lo][KC][128][4]
+template <int H, int G>
+__global__ void __launch_bounds__(256) wide_w2_image_kernel(const __grid_constant__ WideModel m, const float* __restrict__ p, float* __restrict__ img) {
+    constexpr int NQ = G + 1, NW = H * NQ, KC = (NW + 7) / 8 * 2;
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int nch = (m.n + TC_M - 1) / TC_M;
+    if (idx >= (int64_t)nch * KC * TC_M * 4) return;
+    const int kk = (int)(idx & 3), r = (int)((idx >> 2) % TC_M), kc = (int)((idx / (4 * TC_M)) % KC), cm = (int)(idx / ((int64_t)4 * TC_M * KC));
+    const int o = cm * TC_M + r, k = kc * 4 + kk;
+    float v = 0.f;
+    if (o < m.n && k < NW) { const int j = k / NQ, q = k - j * NQ; v = q < G ? p[m.offC2 + (int64_t)(j * G + q) * m.n + o] : p[m.offW2 + (int64_t)j * m.n + o]; }
+    const float hi = w_tf32_hi(v);
+    float* base = img + (int64_t)cm * 2 * KC * TC_M * 4;
+    base[((int64_t)kc * TC_M + r) * 4 + kk] = hi;
+    base[(int64_t)KC * TC_M * 4 + ((int64_t)kc * TC_M + r) * 4 + kk] = v - hi;
+}
+
+template <int H, int G>
+__global__ void __launch_bounds__(128) wide_l2_fwd_tc_kernel(const __grid_constant__ WideModel m, const float* __restrict__ img, const float* hidden,
+                                                             float* out, const int* mask, int64_t B) {
+    constexpr int NQ = G + 1, NW = H * NQ, KC = (NW + 7) / 8 * 2, KSTEPS = KC / 2;
+    constexpr uint32_t A_BYTES = KC * TC_M * 16, B_BYTES = KC * TC_N * 16;
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    float* a_hi = reinterpret_cast<float*>(tc_smem);
+    float* a_lo = reinterpret_cast<float*>(tc_smem + A_BYTES);
+    float* b_hi = reinterpret_cast<float*>(tc_smem + 2 * A_BYTES);
+    float* b_lo = reinterpret_cast<float*>(tc_smem + 2 * A_BYTES + B_BYTES);
+    uint64_t* bar_a = reinterpret_cast<uint64_t*>(tc_smem + 2 * A_BYTES + 2 * B_BYTES);
+    uint64_t* bar_mma = bar_a + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_a + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n = m.n;
+    const int b0 = blockIdx.y * TC_N;
+    if (tid == 0) {
+        w_mbar_init(bar_a, 1); w_mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {        // TMEM: 32 fp32 accumulator columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(w_smem_u32(tmem_slot)), "n"(TC_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {         // weights: the image is already in the operand layout -> bulk copies, one mbarrier
+        const float* src = img + (int64_t)blockIdx.x * 2 * KC * TC_M * 4;
+        w_mbar_expect_tx(bar_a, 2 * A_BYTES);
+        constexpr uint32_t PIECE = A_BYTES / 2;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) w_tma_load_1d(tc_smem + c * PIECE, reinterpret_cast<const unsigned char*>(src) + c * PIECE, PIECE, bar_a);
+    }
+    // feature operand [KC][TC_N][4], hi and lo
+    for (int v = tid; v < 2 * B_BYTES / 4; v += 128) b_hi[v] = 0.f;          // (b_lo follows b_hi)
+    __syncthreads();
+    for (int v = tid; v < TC_N * H; v += 128) {
+        const int bl = v / H, j = v - bl * H;
+        if (b0 + bl >= B) continue;
+        float c[NQ];
+        w_features<float, G>(m.norm2, m.inv_h2, m.grid2, hidden[(int64_t)(b0 + bl) * W_HP + j], c);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int k = j * NQ + q;
+            const float hi = w_tf32_hi(c[q]);
+            b_hi[((k >> 2) * TC_N + bl) * 4 + (k & 3)] = hi;
+            b_lo[((k >> 2) * TC_N + bl) * 4 + (k & 3)] = c[q] - hi;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core (async proxy)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    if (warp == 0) {
+        w_mbar_wait(bar_a, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+            // instruction descriptor: D=F32, A=B=TF32, both K-major, N>>3, M>>4   [cute/arch/mma_sm100_desc.hpp: InstrDescriptor]
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+            const uint32_t ah = w_smem_u32(a_hi), al = w_smem_u32(a_lo), bh = w_smem_u32(b_hi), bl_ = w_smem_u32(b_lo);
+#pragma unroll 1
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                const uint32_t ao = ks * 2 * TC_M * 16, bo = ks * 2 * TC_N * 16;
+                const uint64_t dah = w_umma_desc(ah + ao, TC_M * 16, 128), dal = w_umma_desc(al + ao, TC_M * 16, 128);
+                const uint64_t dbh = w_umma_desc(bh + bo, TC_N * 16, 128), dbl = w_umma_desc(bl_ + bo, TC_N * 16, 128);
+                w_umma_tf32(tmem, dal, dbh, idesc, ks > 0 ? 1u : 0u);        // small terms first
+                w_umma_tf32(tmem, dah, dbl, idesc, 1u);
+                w_umma_tf32(tmem, dah, dbh, idesc, 1u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(w_smem_u32(bar_mma)) : "memory");
+        }
+        __syncwarp();
+    }
+    w_mbar_wait(bar_mma, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t v[TC_N];
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                   "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+                   "=r"(v[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const int o = blockIdx.x * TC_M + tid;
+    if (o < n) {
+#pragma unroll
+        for (int c = 0; c < TC_N; ++c) {
+            const int b = b0 + c;
+            if (b < B && (!mask || mask[b])) out[(int64_t)b * n + o] = __uint_as_float(v[c]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_N) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // layer 2 reverse (reduce over the n output units): hbar[b][j] = sum_o lam[b][o] * sum_q w2[o][j][q] * d_q(hidden[b][j])
 // lam = lprev + h * sum a_sj kl_j is formed here (and stored: it is ybar of layer 2 in the stage record)
 // ---------------------------------------------------------------------------------------------------------
@@ -1095,6 +1253,66 @@ template <class T, int H, int G> int wide_w1t(kanode_handle* h, const WideModel&
     return 0;
 }
 
+// tensor-core image of the layer-2 weights (fp32 only), refreshed when the parameters changed
+template <int H, int G> int wide_w2_image(kanode_handle* h, const WideModel& m, const float* p, const float** out) {
+    constexpr int KC = (H * (G + 1) + 7) / 8 * 2;
+    float* d = nullptr;
+    const size_t cnt = (size_t)((m.n + TC_M - 1) / TC_M) * 2 * KC * TC_M * 4;
+    ENSURE(h, W_W2IMG, sizeof(float) * cnt, d);
+    if (h->wide_w2img_version != h->params_version) {
+        wide_w2_image_kernel<H, G><<<(unsigned)((cnt / 2 + 255) / 256), 256, 0, h->stream>>>(m, p, d);
+        ++h->launches;
+        CK(h, cudaGetLastError());
+        h->wide_w2img_version = h->params_version;
+    }
+    *out = d;
+    return 0;
+}
+
+// k = layer2(hidden): tensor-core kernel for fp32 (KANODE_WIDE_TC=0 selects the CUDA-core kernel), CUDA cores for fp64
+template <class T, int H, int G>
+int wide_l2_forward(kanode_handle* h, const WideModel& m, const T* p, const T* hidden, T* out, const int* mask, int64_t B, const WideLaunch& L) {
+    if constexpr (sizeof(T) == 4) {
+        if (h->wide_tc) {
+            constexpr int KC = (H * (G + 1) + 7) / 8 * 2;
+            constexpr size_t smem = 2 * (size_t)KC * TC_M * 16 + 2 * (size_t)KC * TC_N * 16 + 64;
+            const float* img = nullptr;
+            if (int rc = wide_w2_image<H, G>(h, m, p, &img)) return rc;
+            static bool attr_set = false;
+            if (!attr_set) { CK(h, cudaFuncSetAttribute(wide_l2_fwd_tc_kernel<H, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+            const dim3 g((m.n + TC_M - 1) / TC_M, (unsigned)((B + TC_N - 1) / TC_N));
+            wide_l2_fwd_tc_kernel<H, G><<<g, 128, smem, h->stream>>>(m, img, hidden, out, mask, B);
+            return 0;
+        }
+    }
+    wide_l2_fwd_kernel<T, H, G><<<dim3(L.uc, L.nbt_par), W_BT, 0, h->stream>>>(m, p, hidden, out, mask, B, L.bt_par);
+    return 0;
+}
+
+// du = chain(u) for a batch (kanode_rhs): the two forward contraction kernels of the engine
+template <class T, int H, int G>
+int wide_rhs_t(kanode_handle* h, const T* p, const T* d_u, T* d_du, int64_t B) {
+    constexpr int GB = sizeof(T) == 4 ? 8 : 4;
+    const WideModel m = wide_model(h);
+    const WideLaunch L = wide_launch(m.n, B, GB);
+    const T* w1t = nullptr;
+    if (int rc = wide_w1t<T, H, G>(h, m, p, &w1t)) return rc;
+    char* base = nullptr;
+    ENSURE(h, W_WIDE_R, sizeof(T) * ((size_t)B * W_HP + (size_t)L.nchunk * B * H) + sizeof(unsigned) * (size_t)B + 4 * 256, base);
+    Arena A{base};
+    T* hidden = A.take<T>((size_t)B * W_HP);
+    T* part = A.take<T>((size_t)L.nchunk * B * H);
+    unsigned* counters = A.take<unsigned>(B);
+    CK(h, cudaMemsetAsync(counters, 0, sizeof(unsigned) * (size_t)B, h->stream));
+    WideIn<T> in{};
+    in.base = d_u;
+    wide_l1_fwd_kernel<T, H, G, 0><<<dim3(L.nchunk, L.nbt_red), W_BT, 0, h->stream>>>(m, w1t, in, B, L.P, L.bt_red, part, hidden, counters);
+    if (int rc = wide_l2_forward<T, H, G>(h, m, p, hidden, d_du, nullptr, B, L)) return rc;
+    h->launches += 2;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
 template <class T, int H, int G>
 int wide_forward(kanode_handle* h, const WideModel& m, const T* p, WideFwd<T> a, int64_t B, bool dense, WideCtl* ctl_out) {
     constexpr int GB = sizeof(T) == 4 ? 8 : 4;
@@ -1128,7 +1346,7 @@ int wide_forward(kanode_handle* h, const WideModel& m, const T* p, WideFwd<T> a,
         for (int j = 0; j < ncoef; ++j) in.coef[j] = coef[j];
         in.xstore = xstore; in.mask = c.active;
         wide_l1_fwd_kernel<T, H, G, 0><<<gr, W_BT, 0, st>>>(m, w1t, in, B, L.P, L.bt_red, part, hidden, counters);
-        wide_l2_fwd_kernel<T, H, G><<<gp, W_BT, 0, st>>>(m, p, hidden, a.k + (size_t)kslot * nB, c.active, B, L.bt_par);
+        wide_l2_forward<T, H, G>(h, m, p, hidden, a.k + (size_t)kslot * nB, c.active, B, L);
         launches += 2;
     };
     wide_fwd_init_kernel<T><<<ge, W_ET, 0, st>>>(c, a, n);

@@ -17,6 +17,7 @@ inline bool wide_match(const kanode_desc& d, WideKey& k) {
 
 
 #define KANODE_WIDE_DECL(T)                                                                                                      \
+    int wide_rhs(kanode_handle* h, WideKey k, const T* p, const T* d_u, T* d_du, int64_t B);                                    \
     int wide_solve(kanode_handle* h, WideKey k, const T* p, const T* d_u0, int64_t B, double t0, double t1, const double* d_saveat, \
                    int nsave, double abstol, double reltol, T* d_out, kanode_stats* d_stats);                                    \
     int wide_loss_grad(kanode_handle* h, WideKey k, const T* p, const T* d_u0, int64_t B, double t0, double t1,                  \
