@@ -59,14 +59,14 @@ struct kanode_handle {
     std::string err;
     // grow-only device workspace, keyed by purpose
     enum { W_U0, W_OUT, W_TARGET, W_STATS_F, W_STATS_B, W_SAVEAT, W_REC_T, W_REC, W_NSTEPS, W_RET, W_DG, W_FAC, W_G,
-           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_WPK32, W_WPK64, W_LAM, W_GEN, W_GEN2, W_LS, W_ATT, W_ORDER, W_WIDE_F, W_WIDE_B, W_W1T32, W_W1T64, W_W2IMG, W_WIDE_R, W_COUNT };
+           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_WPK32, W_WPK64, W_LAM, W_GEN, W_GEN2, W_LS, W_ATT, W_ORDER, W_WIDE_F, W_WIDE_B, W_W1T32, W_W1T64, W_W2IMG, W_W2TIMG, W_WIDE_R, W_COUNT };
     DevBuf ws[W_COUNT];
     kanode::GenericModel gm{};               // layer table for the generic kernels
     // wide (batched lockstep) engine: attempts the last forward-only / dense-forward / backward call needed, counter state
     int wide = 1;                            // 0: force the block-per-trajectory kernels (KANODE_WIDE=0)
     int wide_iters[3] = {0, 0, 0};
     uint64_t wide_w1t_version[2] = {~0ull, ~0ull};
-    uint64_t wide_w2img_version = ~0ull;
+    uint64_t wide_w2img_version = ~0ull, wide_w2timg_version = ~0ull;
     int wide_tc = 1;                         // fp32 layer-2 forward contraction on tcgen05 (KANODE_WIDE_TC=0: CUDA cores)
     std::vector<cudaEvent_t> wide_gp_ev;     // event pairs around the g passes of the last wide loss_grad call
     int wide_gp_used = 0;

@@ -154,25 +154,19 @@ __device__ __forceinline__ void wide_inputs(const WideIn<T>& in, int b0, int b1,
 // ---------------------------------------------------------------------------------------------------------
 // shared tail of the two reduce kernels: red[v][tid] column sums -> part[chunk][b][H]; last block -> dst[b][W_HP]
 // ---------------------------------------------------------------------------------------------------------
+// last block of a b-tile (device counter) adds the per-block partials part[chunk][b][H] in a fixed order -> dst[b][W_HP]
 template <class T, int H>
-__device__ __forceinline__ void wide_reduce_tail(T (*red)[W_BT + 1], int b0, int b1, int64_t B, T* part, T* dst, unsigned* counters, int* s_last,
-                                                 const int* mask) {
-    const int tid = threadIdx.x, chunk = blockIdx.x, nchunk = gridDim.x;
+__device__ __forceinline__ void wide_finalize(int b0, int b1, int64_t B, T* part, T* dst, unsigned* counters, int* s_last, const int* mask) {
+    const int tid = threadIdx.x, nchunk = gridDim.x;
     const int nv = (b1 - b0) * H;
-    __syncthreads();
-    for (int v = tid; v < nv; v += W_BT) {
-        T s = T(0);
-        for (int k = 0; k < W_BT; ++k) s += red[v][k];
-        part[((int64_t)chunk * B + b0 + v / H) * H + v % H] = s;
-    }
     __threadfence();
     __syncthreads();
     if (tid == 0) *s_last = (atomicAdd(&counters[blockIdx.y], 1u) == (unsigned)(nchunk - 1));
     __syncthreads();
     if (!*s_last) return;
     __threadfence();
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int v = warp; v < nv; v += W_BT / 32) {
+    const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    for (int v = warp; v < nv; v += nw) {
         const int b = b0 + v / H, o = v % H;
         T s = T(0);
         for (int c = lane; c < nchunk; c += 32) s += ld_cg(&part[((int64_t)c * B + b) * H + o]);
@@ -180,6 +174,19 @@ __device__ __forceinline__ void wide_reduce_tail(T (*red)[W_BT + 1], int b0, int
         if (lane == 0 && (!mask || mask[b])) dst[(int64_t)b * W_HP + o] = s;   // masked ICs keep their (FSAL-shifted) record
     }
     if (tid == 0) counters[blockIdx.y] = 0u;   // re-armed for the next launch on this stream
+}
+template <class T, int H>
+__device__ __forceinline__ void wide_reduce_tail(T (*red)[W_BT + 1], int b0, int b1, int64_t B, T* part, T* dst, unsigned* counters, int* s_last,
+                                                 const int* mask) {
+    const int tid = threadIdx.x, chunk = blockIdx.x;
+    const int nv = (b1 - b0) * H;
+    __syncthreads();
+    for (int v = tid; v < nv; v += W_BT) {
+        T s = T(0);
+        for (int k = 0; k < W_BT; ++k) s += red[v][k];
+        part[((int64_t)chunk * B + b0 + v / H) * H + v % H] = s;
+    }
+    wide_finalize<T, H>(b0, b1, B, part, dst, counters, s_last, mask);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -507,6 +514,165 @@ __global__ void __launch_bounds__(W_BT, 3) wide_l2_vjp_kernel(const __grid_const
         }
     }
     wide_reduce_tail<T, H>(red, b0, b1, B, part, hbar, counters, &s_last, in.mask);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// layer 2 reverse on tcgen05 (fp32, n % 128 == 0):  S[r][b] = sum_o W2t[r][o] * lam[b][o]   (M = 128 rows r = (j,q), 110 used;
+// N = 32 ICs; K = o, 128 per pass, accumulated in TMEM over the P passes of the block), then hbar[b][j] = sum_q S[(j,q)][b] * d2[b][(j,q)].
+// A (weights) arrives by TMA from an image in the UMMA layout; B (lambda at the stage = lam + h*sum a*kl, also recorded as
+// ybar of layer 2) is formed by the threads with coalesced 16-byte loads and written hi/lo in the K-major core-matrix layout.
+// ---------------------------------------------------------------------------------------------------------
+template <int H, int G>
+__global__ void __launch_bounds__(256) wide_w2t_image_kernel(const __grid_constant__ WideModel m, const float* __restrict__ p, float* __restrict__ img) {
+    constexpr int NQ = G + 1, NW = H * NQ;
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int nblk = m.n / TC_M;
+    if (idx >= (int64_t)nblk * 32 * TC_M * 4) return;
+    const int kk = (int)(idx & 3), r = (int)((idx >> 2) % TC_M), kc = (int)((idx / (4 * TC_M)) % 32), ob = (int)(idx / ((int64_t)4 * TC_M * 32));
+    const int o = ob * 128 + kc * 4 + kk;
+    float v = 0.f;
+    if (r < NW) { const int j = r / NQ, q = r - j * NQ; v = q < G ? p[m.offC2 + (int64_t)(j * G + q) * m.n + o] : p[m.offW2 + (int64_t)j * m.n + o]; }
+    const float hi = w_tf32_hi(v);
+    float* base = img + (int64_t)ob * 2 * 32 * TC_M * 4;
+    base[((int64_t)kc * TC_M + r) * 4 + kk] = hi;
+    base[(int64_t)32 * TC_M * 4 + ((int64_t)kc * TC_M + r) * 4 + kk] = v - hi;
+}
+
+template <int H, int G>
+__global__ void __launch_bounds__(128) wide_l2_vjp_tc_kernel(const __grid_constant__ WideModel m, const float* __restrict__ img, const float* hidden,
+                                                             const WideIn<float> in, int64_t B, int P, float* part, float* hbar, unsigned* counters) {
+    constexpr int NQ = G + 1, NW = H * NQ, NWP = (NW + 3) / 4 * 4, KC = 32, KSTEPS = KC / 2;
+    constexpr uint32_t A_BYTES = KC * TC_M * 16, B_BYTES = KC * TC_N * 16;
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    float* a_hi = reinterpret_cast<float*>(tc_smem);
+    float* a_lo = reinterpret_cast<float*>(tc_smem + A_BYTES);
+    float* b_hi = reinterpret_cast<float*>(tc_smem + 2 * A_BYTES);
+    float* b_lo = reinterpret_cast<float*>(tc_smem + 2 * A_BYTES + B_BYTES);
+    float* d2 = reinterpret_cast<float*>(tc_smem + 2 * A_BYTES + 2 * B_BYTES);                 // [TC_N][NWP]
+    uint64_t* bar_a = reinterpret_cast<uint64_t*>(tc_smem + 2 * A_BYTES + 2 * B_BYTES + TC_N * NWP * 4);
+    uint64_t* bar_mma = bar_a + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_a + 2);
+    int* s_last = reinterpret_cast<int*>(tmem_slot + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n = m.n;
+    const int b0 = blockIdx.y * TC_N, b1 = (int)min((int64_t)(b0 + TC_N), B);
+    const int nblk = n / TC_M;
+    const int npass = min(P, nblk - (int)blockIdx.x * P);
+    if (tid == 0) {
+        w_mbar_init(bar_a, 1); w_mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(w_smem_u32(tmem_slot)), "n"(TC_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int v = tid; v < TC_N * H; v += 128) {
+        const int bl = v / H, j = v - bl * H;
+        float d[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) d[q] = 0.f;
+        if (b0 + bl < b1) w_dfeatures<float, G>(m.norm2, m.inv_h2, m.grid2, hidden[(int64_t)(b0 + bl) * W_HP + j], d);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) d2[bl * NWP + j * NQ + q] = d[q];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const int bl_l = lane & 7, c_l = lane >> 3;                   // lane -> (IC, 16-byte chunk): 64 B contiguous per IC in global, conflict-free STS.128
+    const int Bn = (int)B * n;
+    for (int pass = 0; pass < npass; ++pass) {
+        const int ob = blockIdx.x * P + pass;
+        if (pass > 0) { w_mbar_wait(bar_mma, (pass - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+        if (tid == 0) {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(img + (int64_t)ob * 2 * KC * TC_M * 4);
+            w_mbar_expect_tx(bar_a, 2 * A_BYTES);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) w_tma_load_1d(tc_smem + c * (A_BYTES / 2), src + c * (A_BYTES / 2), A_BYTES / 2, bar_a);
+        }
+#pragma unroll
+        for (int grp = 0; grp < 2; ++grp) {
+            float4 base[4], kv[4][6]; float hs[4]; bool on[4]; int bl[4], ch[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                bl[k] = bl_l + 8 * k; ch[k] = c_l + 4 * warp + 16 * grp;
+                const int b = b0 + bl[k];
+                on[k] = b < b1 && (!in.mask || in.mask[b]);
+                const int e = b * n + ob * TC_M + ch[k] * 4;
+                base[k] = on[k] ? *reinterpret_cast<const float4*>(in.base + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                hs[k] = on[k] && in.ncoef > 0 ? in.hs[b] : 0.f;
+#pragma unroll
+                for (int j = 0; j < 6; ++j)
+                    kv[k][j] = (on[k] && j < in.ncoef) ? *reinterpret_cast<const float4*>(in.ks + (int64_t)j * Bn + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { const float cj = in.coef[j]; acc.x += cj * kv[k][j].x; acc.y += cj * kv[k][j].y; acc.z += cj * kv[k][j].z; acc.w += cj * kv[k][j].w; }
+                float4 lam = base[k];
+                if (in.ncoef > 0) { lam.x = base[k].x + hs[k] * acc.x; lam.y = base[k].y + hs[k] * acc.y; lam.z = base[k].z + hs[k] * acc.z; lam.w = base[k].w + hs[k] * acc.w; }
+                if (on[k] && in.xstore) *reinterpret_cast<float4*>(in.xstore + (b0 + bl[k]) * n + ob * TC_M + ch[k] * 4) = lam;
+                const float4 hi = make_float4(w_tf32_hi(lam.x), w_tf32_hi(lam.y), w_tf32_hi(lam.z), w_tf32_hi(lam.w));
+                const float4 lo = make_float4(lam.x - hi.x, lam.y - hi.y, lam.z - hi.z, lam.w - hi.w);
+                *reinterpret_cast<float4*>(b_hi + (ch[k] * TC_N + bl[k]) * 4) = hi;
+                *reinterpret_cast<float4*>(b_lo + (ch[k] * TC_N + bl[k]) * 4) = lo;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (warp == 0) {
+            w_mbar_wait(bar_a, pass & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+                const uint32_t ah = w_smem_u32(a_hi), al = w_smem_u32(a_lo), bh = w_smem_u32(b_hi), blo = w_smem_u32(b_lo);
+#pragma unroll 1
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                    const uint32_t ao = ks * 2 * TC_M * 16, bo = ks * 2 * TC_N * 16;
+                    const uint64_t dah = w_umma_desc(ah + ao, TC_M * 16, 128), dal = w_umma_desc(al + ao, TC_M * 16, 128);
+                    const uint64_t dbh = w_umma_desc(bh + bo, TC_N * 16, 128), dbl = w_umma_desc(blo + bo, TC_N * 16, 128);
+                    w_umma_tf32(tmem, dal, dbh, idesc, (pass > 0 || ks > 0) ? 1u : 0u);
+                    w_umma_tf32(tmem, dah, dbl, idesc, 1u);
+                    w_umma_tf32(tmem, dah, dbh, idesc, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(w_smem_u32(bar_mma)) : "memory");
+            }
+            __syncwarp();
+        }
+    }
+    w_mbar_wait(bar_mma, (npass - 1) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t v[TC_N];
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                   "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+                   "=r"(v[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    // S[r][b] * d2[b][r] staged in shared memory (the operand buffers are free now), then summed over q per hidden unit
+    float* ps = a_hi;                                             // [128][33]
+    if (tid < NW) {
+#pragma unroll
+        for (int c = 0; c < TC_N; ++c) ps[tid * 33 + c] = __uint_as_float(v[c]) * d2[c * NWP + tid];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    for (int idx = tid; idx < TC_N * H; idx += 128) {
+        const int j = idx / TC_N, bl = idx - j * TC_N;
+        if (b0 + bl >= b1) continue;
+        float sacc = 0.f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) sacc += ps[(j * NQ + q) * 33 + bl];
+        part[((int64_t)blockIdx.x * B + b0 + bl) * H + j] = sacc;
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_N) : "memory");
+    wide_finalize<float, H>(b0, b1, B, part, hbar, counters, s_last, in.mask);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1269,6 +1435,44 @@ template <int H, int G> int wide_w2_image(kanode_handle* h, const WideModel& m, 
     return 0;
 }
 
+template <int H, int G> int wide_w2t_image(kanode_handle* h, const WideModel& m, const float* p, const float** out) {
+    float* d = nullptr;
+    const size_t cnt = (size_t)(m.n / TC_M) * 2 * 32 * TC_M * 4;
+    ENSURE(h, W_W2TIMG, sizeof(float) * cnt, d);
+    if (h->wide_w2timg_version != h->params_version) {
+        wide_w2t_image_kernel<H, G><<<(unsigned)((cnt / 2 + 255) / 256), 256, 0, h->stream>>>(m, p, d);
+        ++h->launches;
+        CK(h, cudaGetLastError());
+        h->wide_w2timg_version = h->params_version;
+    }
+    *out = d;
+    return 0;
+}
+
+// hbar = layer-2 reverse of lambda_s: tcgen05 kernel for fp32 when n is a multiple of 128, CUDA cores otherwise
+template <class T, int H, int G>
+int wide_l2_reverse(kanode_handle* h, const WideModel& m, const T* p, const T* hidden, const WideIn<T>& in, int64_t B, const WideLaunch& L,
+                    T* part, T* hbar, unsigned* counters) {
+    if constexpr (sizeof(T) == 4) {
+        if (h->wide_tc && m.n % TC_M == 0) {
+            constexpr int NWP = (H * (G + 1) + 3) / 4 * 4;
+            constexpr size_t smem = 2 * (size_t)32 * TC_M * 16 + 2 * (size_t)32 * TC_N * 16 + (size_t)TC_N * NWP * 4 + 64;
+            const float* img = nullptr;
+            if (int rc = wide_w2t_image<H, G>(h, m, p, &img)) return rc;
+            static bool attr_set = false;
+            if (!attr_set) { CK(h, cudaFuncSetAttribute(wide_l2_vjp_tc_kernel<H, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+            const int nblk = m.n / TC_M, nbt = (int)((B + TC_N - 1) / TC_N);
+            int P = (nblk * nbt + 147) / 148; P = P < 1 ? 1 : P;                 // about one block per SM
+            P = std::max(P, (nblk + W_MAXCH - 1) / W_MAXCH);
+            const dim3 g((nblk + P - 1) / P, nbt);
+            wide_l2_vjp_tc_kernel<H, G><<<g, 128, smem, h->stream>>>(m, img, hidden, in, B, P, part, hbar, counters);
+            return 0;
+        }
+    }
+    wide_l2_vjp_kernel<T, H, G><<<dim3(L.nchunk, L.nbt_red), W_BT, 0, h->stream>>>(m, p, hidden, in, B, L.P, L.bt_red, part, hbar, counters);
+    return 0;
+}
+
 // k = layer2(hidden): tensor-core kernel for fp32 (KANODE_WIDE_TC=0 selects the CUDA-core kernel), CUDA cores for fp64
 template <class T, int H, int G>
 int wide_l2_forward(kanode_handle* h, const WideModel& m, const T* p, const T* hidden, T* out, const int* mask, int64_t B, const WideLaunch& L) {
@@ -1466,7 +1670,7 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
         il.base = w.lam; il.ks = w.kl; il.hs = w.h; il.ncoef = ncoef;
         for (int j = 0; j < ncoef; ++j) il.coef[j] = coef[j];
         il.xstore = w.yb2 + (size_t)s * nB; il.mask = mask;
-        wide_l2_vjp_kernel<T, H, G><<<gr, W_BT, 0, st>>>(m, p, w.x2 + (size_t)s * B * W_HP, il, B, L.P, L.bt_red, part, w.yb1 + (size_t)s * B * W_HP, counters);
+        wide_l2_reverse<T, H, G>(h, m, p, w.x2 + (size_t)s * B * W_HP, il, B, L, part, w.yb1 + (size_t)s * B * W_HP, counters);
         wide_l1_vjp_kernel<T, H, G><<<gp, W_BT, 0, st>>>(m, w1t, w.x1 + (size_t)s * nB, w.yb1 + (size_t)s * B * W_HP, w.kl + (size_t)s * nB, mask, B, L.bt_par);
         launches += 3;
     };

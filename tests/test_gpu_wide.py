@@ -113,3 +113,32 @@ def test_wide_empty_time_span(monkeypatch):
     ode.close()
     assert (sol.stats.retcode == 0).all() and (sol.stats.naccept == 0).all()
     assert np.array_equal(sol.array[:, 0, :], u0)
+
+
+@pytest.mark.parametrize("n,G,B", [(256, 10, 5), (384, 5, 40)])
+def test_wide_tensor_core_kernels_match_cuda_core_fp32(n, G, B, monkeypatch):
+    """fp32: the tcgen05 contraction kernels (3xTF32, TMEM accumulator; layer-2 forward for any n, layer-2 reverse for
+    n % 128 == 0) against the CUDA-core kernels of the same engine (KANODE_WIDE_TC=0), and both against the fp64 oracle."""
+    chain, p, u0, tspan, saveat, tg = _problem(n, G, B, seed=n + 1)
+    orc = Oracle(chain.desc(), np.float64)
+    res = {}
+    for tc in (1, 0):
+        monkeypatch.setenv("KANODE_WIDE", "1"); monkeypatch.setenv("KANODE_WIDE_TC", str(tc))
+        ode = K.KanOde(chain, dtype=np.float32); ode.set_params(p)
+        rhs = ode.rhs(u0)
+        r = ode.loss_grad(u0, tspan, saveat, tg)
+        ode.close()
+        res[tc] = (rhs, r)
+    ref_rhs = orc.rhs(p, u0)
+    for tc in (1, 0):
+        assert _relmax(res[tc][0], ref_rhs) < 2e-5, tc                      # RHS arithmetic within the fp32 parity budget
+    assert _relmax(res[1][0], res[0][0]) < 5e-6
+    a, b = res[1][1], res[0][1]
+    assert (a["fwd_stats"].retcode == 0).all() and (a["bwd_stats"].retcode == 0).all()
+    same = (a["fwd_stats"].naccept == b["fwd_stats"].naccept).all() and (a["bwd_stats"].naccept == b["bwd_stats"].naccept).all() \
+        and (a["bwd_stats"].nreject == b["bwd_stats"].nreject).all()
+    tol = 2e-4 if same else 2e-2                                            # different fp32 step sequences: solver accuracy only
+    assert abs(a["loss"] - b["loss"]) < tol * abs(b["loss"])
+    assert _relmax(a["grad"], b["grad"]) < tol, (same, _relmax(a["grad"], b["grad"]))
+    ref = orc.loss_grad(p, u0, tspan, saveat, tg)
+    assert _relmax(a["grad"], ref["grad"]) < 2e-2 and abs(a["loss"] - ref["loss"]) < 5e-3 * abs(ref["loss"])
