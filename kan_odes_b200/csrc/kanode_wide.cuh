@@ -165,13 +165,20 @@ __device__ __forceinline__ void wide_finalize(int b0, int b1, int64_t B, T* part
     __syncthreads();
     if (!*s_last) return;
     __threadfence();
-    const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    for (int v = warp; v < nv; v += nw) {
-        const int b = b0 + v / H, o = v % H;
+    for (int v = tid; v < nv; v += blockDim.x) {      // thread per value: coalesced over v, 8 independent loads in flight
+        const T* src = part + (int64_t)b0 * H + v;
         T s = T(0);
-        for (int c = lane; c < nchunk; c += 32) s += ld_cg(&part[((int64_t)c * B + b) * H + o]);
-        s = warp_sum(s);
-        if (lane == 0 && (!mask || mask[b])) dst[(int64_t)b * W_HP + o] = s;   // masked ICs keep their (FSAL-shifted) record
+        int c = 0;
+        for (; c + 8 <= nchunk; c += 8) {
+            T t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] = ld_cg(src + (int64_t)(c + k) * B * H);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += t[k];
+        }
+        for (; c < nchunk; ++c) s += ld_cg(src + (int64_t)c * B * H);
+        const int b = b0 + v / H;
+        if (!mask || mask[b]) dst[(int64_t)b * W_HP + v % H] = s;   // masked ICs keep their (FSAL-shifted) record
     }
     if (tid == 0) counters[blockIdx.y] = 0u;   // re-armed for the next launch on this stream
 }
@@ -187,6 +194,19 @@ __device__ __forceinline__ void wide_reduce_tail(T (*red)[W_BT + 1], int b0, int
         part[((int64_t)chunk * B + b0 + v / H) * H + v % H] = s;
     }
     wide_finalize<T, H>(b0, b1, B, part, dst, counters, s_last, mask);
+}
+
+// dst[b][o] = sum_c part[c][b][o] as its own launch (tensor-core reduce kernel: many chunks, no last-block tail):
+// 16 lanes per value, each adds every 16th chunk, then a fixed-order shuffle tree
+template <class T, int H>
+__global__ void __launch_bounds__(128) wide_sum_partials_kernel(const T* part, int nchunk, int64_t B, T* dst, const int* mask) {
+    const int64_t v = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 4);
+    const int g = threadIdx.x & 15;
+    T s = T(0);
+    if (v < B * H) for (int c = g; c < nchunk; c += 16) s += ld_cg(part + (int64_t)c * B * H + v);
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (g == 0 && v < B * H) { const int64_t b = v / H; if (!mask || mask[b]) dst[b * W_HP + (v - b * H)] = s; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -522,26 +542,28 @@ __global__ void __launch_bounds__(W_BT, 3) wide_l2_vjp_kernel(const __grid_const
 // A (weights) arrives by TMA from an image in the UMMA layout; B (lambda at the stage = lam + h*sum a*kl, also recorded as
 // ybar of layer 2) is formed by the threads with coalesced 16-byte loads and written hi/lo in the K-major core-matrix layout.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int TC_KB = 64;            // output units (K of the reverse contraction) per block
 template <int H, int G>
 __global__ void __launch_bounds__(256) wide_w2t_image_kernel(const __grid_constant__ WideModel m, const float* __restrict__ p, float* __restrict__ img) {
-    constexpr int NQ = G + 1, NW = H * NQ;
+    constexpr int NQ = G + 1, NW = H * NQ, KC = TC_KB / 4;
     const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const int nblk = m.n / TC_M;
-    if (idx >= (int64_t)nblk * 32 * TC_M * 4) return;
-    const int kk = (int)(idx & 3), r = (int)((idx >> 2) % TC_M), kc = (int)((idx / (4 * TC_M)) % 32), ob = (int)(idx / ((int64_t)4 * TC_M * 32));
-    const int o = ob * 128 + kc * 4 + kk;
+    const int nblk = m.n / TC_KB;
+    if (idx >= (int64_t)nblk * KC * TC_M * 4) return;
+    const int kk = (int)(idx & 3), r = (int)((idx >> 2) % TC_M), kc = (int)((idx / (4 * TC_M)) % KC), ob = (int)(idx / ((int64_t)4 * TC_M * KC));
+    const int o = ob * TC_KB + kc * 4 + kk;
     float v = 0.f;
     if (r < NW) { const int j = r / NQ, q = r - j * NQ; v = q < G ? p[m.offC2 + (int64_t)(j * G + q) * m.n + o] : p[m.offW2 + (int64_t)j * m.n + o]; }
     const float hi = w_tf32_hi(v);
-    float* base = img + (int64_t)ob * 2 * 32 * TC_M * 4;
+    float* base = img + (int64_t)ob * 2 * KC * TC_M * 4;
     base[((int64_t)kc * TC_M + r) * 4 + kk] = hi;
-    base[(int64_t)32 * TC_M * 4 + ((int64_t)kc * TC_M + r) * 4 + kk] = v - hi;
+    base[(int64_t)KC * TC_M * 4 + ((int64_t)kc * TC_M + r) * 4 + kk] = v - hi;
 }
 
+// grid (n / 64, ceil(B / 32)); 94 KB of shared memory -> two blocks per SM overlap each other's load and MMA phases
 template <int H, int G>
 __global__ void __launch_bounds__(128) wide_l2_vjp_tc_kernel(const __grid_constant__ WideModel m, const float* __restrict__ img, const float* hidden,
-                                                             const WideIn<float> in, int64_t B, int P, float* part, float* hbar, unsigned* counters) {
-    constexpr int NQ = G + 1, NW = H * NQ, NWP = (NW + 3) / 4 * 4, KC = 32, KSTEPS = KC / 2;
+                                                             const WideIn<float> in, int64_t B, float* part) {
+    constexpr int NQ = G + 1, NW = H * NQ, NWP = (NW + 3) / 4 * 4, KC = TC_KB / 4, KSTEPS = KC / 2;
     constexpr uint32_t A_BYTES = KC * TC_M * 16, B_BYTES = KC * TC_N * 16;
     extern __shared__ __align__(128) unsigned char tc_smem[];
     float* a_hi = reinterpret_cast<float*>(tc_smem);
@@ -552,11 +574,9 @@ __global__ void __launch_bounds__(128) wide_l2_vjp_tc_kernel(const __grid_consta
     uint64_t* bar_a = reinterpret_cast<uint64_t*>(tc_smem + 2 * A_BYTES + 2 * B_BYTES + TC_N * NWP * 4);
     uint64_t* bar_mma = bar_a + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_a + 2);
-    int* s_last = reinterpret_cast<int*>(tmem_slot + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n = m.n;
     const int b0 = blockIdx.y * TC_N, b1 = (int)min((int64_t)(b0 + TC_N), B);
-    const int nblk = n / TC_M;
-    const int npass = min(P, nblk - (int)blockIdx.x * P);
+    const int ob = blockIdx.x;
     if (tid == 0) {
         w_mbar_init(bar_a, 1); w_mbar_init(bar_mma, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -565,84 +585,79 @@ __global__ void __launch_bounds__(128) wide_l2_vjp_tc_kernel(const __grid_consta
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(w_smem_u32(tmem_slot)), "n"(TC_N) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int v = tid; v < TC_N * H; v += 128) {
-        const int bl = v / H, j = v - bl * H;
-        float d[NQ];
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(img + (int64_t)ob * 2 * KC * TC_M * 4);
+        w_mbar_expect_tx(bar_a, 2 * A_BYTES);
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) d[q] = 0.f;
-        if (b0 + bl < b1) w_dfeatures<float, G>(m.norm2, m.inv_h2, m.grid2, hidden[(int64_t)(b0 + bl) * W_HP + j], d);
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) d2[bl * NWP + j * NQ + q] = d[q];
+        for (int c = 0; c < 4; ++c) w_tma_load_1d(tc_smem + c * (A_BYTES / 2), src + c * (A_BYTES / 2), A_BYTES / 2, bar_a);
     }
+    {   // lambda operand: lane -> (IC, 16-byte chunk): 64 B contiguous per IC in global memory, conflict-free STS.128
+        const int bl_l = lane & 7, c_l = lane >> 3;
+        const int Bn = (int)B * n;
+        float4 base[4], kv[4][6]; float hs[4]; bool on[4]; int bl[4];
+        const int ch = c_l + 4 * warp;                                                  // 0..15
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            bl[k] = bl_l + 8 * k;
+            const int b = b0 + bl[k];
+            on[k] = b < b1 && (!in.mask || in.mask[b]);
+            const int e = b * n + ob * TC_KB + ch * 4;
+            base[k] = on[k] ? *reinterpret_cast<const float4*>(in.base + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            hs[k] = on[k] && in.ncoef > 0 ? in.hs[b] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                kv[k][j] = (on[k] && j < in.ncoef) ? *reinterpret_cast<const float4*>(in.ks + (int64_t)j * Bn + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // per-IC derivative table while the loads are in flight
+        for (int v = tid; v < TC_N * H; v += 128) {
+            const int bq = v / H, j = v - bq * H;
+            float d[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) d[q] = 0.f;
+            if (b0 + bq < b1) w_dfeatures<float, G>(m.norm2, m.inv_h2, m.grid2, hidden[(int64_t)(b0 + bq) * W_HP + j], d);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) d2[bq * NWP + j * NQ + q] = d[q];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) { const float cj = in.coef[j]; acc.x += cj * kv[k][j].x; acc.y += cj * kv[k][j].y; acc.z += cj * kv[k][j].z; acc.w += cj * kv[k][j].w; }
+            float4 lam = base[k];
+            if (in.ncoef > 0) { lam.x = base[k].x + hs[k] * acc.x; lam.y = base[k].y + hs[k] * acc.y; lam.z = base[k].z + hs[k] * acc.z; lam.w = base[k].w + hs[k] * acc.w; }
+            if (on[k] && in.xstore) *reinterpret_cast<float4*>(in.xstore + (b0 + bl[k]) * n + ob * TC_KB + ch * 4) = lam;
+            const float4 hi = make_float4(w_tf32_hi(lam.x), w_tf32_hi(lam.y), w_tf32_hi(lam.z), w_tf32_hi(lam.w));
+            const float4 lo = make_float4(lam.x - hi.x, lam.y - hi.y, lam.z - hi.z, lam.w - hi.w);
+            *reinterpret_cast<float4*>(b_hi + (ch * TC_N + bl[k]) * 4) = hi;
+            *reinterpret_cast<float4*>(b_lo + (ch * TC_N + bl[k]) * 4) = lo;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    const int bl_l = lane & 7, c_l = lane >> 3;                   // lane -> (IC, 16-byte chunk): 64 B contiguous per IC in global, conflict-free STS.128
-    const int Bn = (int)B * n;
-    for (int pass = 0; pass < npass; ++pass) {
-        const int ob = blockIdx.x * P + pass;
-        if (pass > 0) { w_mbar_wait(bar_mma, (pass - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-        if (tid == 0) {
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(img + (int64_t)ob * 2 * KC * TC_M * 4);
-            w_mbar_expect_tx(bar_a, 2 * A_BYTES);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) w_tma_load_1d(tc_smem + c * (A_BYTES / 2), src + c * (A_BYTES / 2), A_BYTES / 2, bar_a);
-        }
-#pragma unroll
-        for (int grp = 0; grp < 2; ++grp) {
-            float4 base[4], kv[4][6]; float hs[4]; bool on[4]; int bl[4], ch[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                bl[k] = bl_l + 8 * k; ch[k] = c_l + 4 * warp + 16 * grp;
-                const int b = b0 + bl[k];
-                on[k] = b < b1 && (!in.mask || in.mask[b]);
-                const int e = b * n + ob * TC_M + ch[k] * 4;
-                base[k] = on[k] ? *reinterpret_cast<const float4*>(in.base + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-                hs[k] = on[k] && in.ncoef > 0 ? in.hs[b] : 0.f;
-#pragma unroll
-                for (int j = 0; j < 6; ++j)
-                    kv[k][j] = (on[k] && j < in.ncoef) ? *reinterpret_cast<const float4*>(in.ks + (int64_t)j * Bn + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < 6; ++j) { const float cj = in.coef[j]; acc.x += cj * kv[k][j].x; acc.y += cj * kv[k][j].y; acc.z += cj * kv[k][j].z; acc.w += cj * kv[k][j].w; }
-                float4 lam = base[k];
-                if (in.ncoef > 0) { lam.x = base[k].x + hs[k] * acc.x; lam.y = base[k].y + hs[k] * acc.y; lam.z = base[k].z + hs[k] * acc.z; lam.w = base[k].w + hs[k] * acc.w; }
-                if (on[k] && in.xstore) *reinterpret_cast<float4*>(in.xstore + (b0 + bl[k]) * n + ob * TC_M + ch[k] * 4) = lam;
-                const float4 hi = make_float4(w_tf32_hi(lam.x), w_tf32_hi(lam.y), w_tf32_hi(lam.z), w_tf32_hi(lam.w));
-                const float4 lo = make_float4(lam.x - hi.x, lam.y - hi.y, lam.z - hi.z, lam.w - hi.w);
-                *reinterpret_cast<float4*>(b_hi + (ch[k] * TC_N + bl[k]) * 4) = hi;
-                *reinterpret_cast<float4*>(b_lo + (ch[k] * TC_N + bl[k]) * 4) = lo;
-            }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+    if (warp == 0) {
+        w_mbar_wait(bar_a, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (warp == 0) {
-            w_mbar_wait(bar_a, pass & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-                const uint32_t ah = w_smem_u32(a_hi), al = w_smem_u32(a_lo), bh = w_smem_u32(b_hi), blo = w_smem_u32(b_lo);
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+            const uint32_t ah = w_smem_u32(a_hi), al = w_smem_u32(a_lo), bh = w_smem_u32(b_hi), blo = w_smem_u32(b_lo);
 #pragma unroll 1
-                for (int ks = 0; ks < KSTEPS; ++ks) {
-                    const uint32_t ao = ks * 2 * TC_M * 16, bo = ks * 2 * TC_N * 16;
-                    const uint64_t dah = w_umma_desc(ah + ao, TC_M * 16, 128), dal = w_umma_desc(al + ao, TC_M * 16, 128);
-                    const uint64_t dbh = w_umma_desc(bh + bo, TC_N * 16, 128), dbl = w_umma_desc(blo + bo, TC_N * 16, 128);
-                    w_umma_tf32(tmem, dal, dbh, idesc, (pass > 0 || ks > 0) ? 1u : 0u);
-                    w_umma_tf32(tmem, dah, dbl, idesc, 1u);
-                    w_umma_tf32(tmem, dah, dbh, idesc, 1u);
-                }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(w_smem_u32(bar_mma)) : "memory");
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                const uint32_t ao = ks * 2 * TC_M * 16, bo = ks * 2 * TC_N * 16;
+                const uint64_t dah = w_umma_desc(ah + ao, TC_M * 16, 128), dal = w_umma_desc(al + ao, TC_M * 16, 128);
+                const uint64_t dbh = w_umma_desc(bh + bo, TC_N * 16, 128), dbl = w_umma_desc(blo + bo, TC_N * 16, 128);
+                w_umma_tf32(tmem, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+                w_umma_tf32(tmem, dah, dbl, idesc, 1u);
+                w_umma_tf32(tmem, dah, dbh, idesc, 1u);
             }
-            __syncwarp();
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(w_smem_u32(bar_mma)) : "memory");
         }
+        __syncwarp();
     }
-    w_mbar_wait(bar_mma, (npass - 1) & 1);
+    w_mbar_wait(bar_mma, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t v[TC_N];
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
@@ -664,15 +679,14 @@ __global__ void __launch_bounds__(128) wide_l2_vjp_tc_kernel(const __grid_consta
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     for (int idx = tid; idx < TC_N * H; idx += 128) {
-        const int j = idx / TC_N, bl = idx - j * TC_N;
-        if (b0 + bl >= b1) continue;
+        const int j = idx / TC_N, bq = idx - j * TC_N;
+        if (b0 + bq >= b1) continue;
         float sacc = 0.f;
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) sacc += ps[(j * NQ + q) * 33 + bl];
-        part[((int64_t)blockIdx.x * B + b0 + bl) * H + j] = sacc;
+        for (int q = 0; q < NQ; ++q) sacc += ps[(j * NQ + q) * 33 + bq];
+        part[((int64_t)ob * B + b0 + bq) * H + j] = sacc;
     }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_N) : "memory");
-    wide_finalize<float, H>(b0, b1, B, part, hbar, counters, s_last, in.mask);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1437,7 +1451,7 @@ template <int H, int G> int wide_w2_image(kanode_handle* h, const WideModel& m, 
 
 template <int H, int G> int wide_w2t_image(kanode_handle* h, const WideModel& m, const float* p, const float** out) {
     float* d = nullptr;
-    const size_t cnt = (size_t)(m.n / TC_M) * 2 * 32 * TC_M * 4;
+    const size_t cnt = (size_t)(m.n / TC_KB) * 2 * (TC_KB / 4) * TC_M * 4;
     ENSURE(h, W_W2TIMG, sizeof(float) * cnt, d);
     if (h->wide_w2timg_version != h->params_version) {
         wide_w2t_image_kernel<H, G><<<(unsigned)((cnt / 2 + 255) / 256), 256, 0, h->stream>>>(m, p, d);
@@ -1449,23 +1463,25 @@ template <int H, int G> int wide_w2t_image(kanode_handle* h, const WideModel& m,
     return 0;
 }
 
+// partial-sum rows the reduce kernels may need: CUDA-core kernels <= W_MAXCH, the tensor-core reverse kernel n / 64
+inline size_t wide_part_rows(int n, const WideLaunch& L) { return (size_t)std::max(L.nchunk, n / TC_KB + 1); }
+
 // hbar = layer-2 reverse of lambda_s: tcgen05 kernel for fp32 when n is a multiple of 128, CUDA cores otherwise
 template <class T, int H, int G>
 int wide_l2_reverse(kanode_handle* h, const WideModel& m, const T* p, const T* hidden, const WideIn<T>& in, int64_t B, const WideLaunch& L,
                     T* part, T* hbar, unsigned* counters) {
     if constexpr (sizeof(T) == 4) {
         if (h->wide_tc && m.n % TC_M == 0) {
-            constexpr int NWP = (H * (G + 1) + 3) / 4 * 4;
-            constexpr size_t smem = 2 * (size_t)32 * TC_M * 16 + 2 * (size_t)32 * TC_N * 16 + (size_t)TC_N * NWP * 4 + 64;
+            constexpr int NWP = (H * (G + 1) + 3) / 4 * 4, KC = TC_KB / 4;
+            constexpr size_t smem = 2 * (size_t)KC * TC_M * 16 + 2 * (size_t)KC * TC_N * 16 + (size_t)TC_N * NWP * 4 + 64;
             const float* img = nullptr;
             if (int rc = wide_w2t_image<H, G>(h, m, p, &img)) return rc;
             static bool attr_set = false;
             if (!attr_set) { CK(h, cudaFuncSetAttribute(wide_l2_vjp_tc_kernel<H, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-            const int nblk = m.n / TC_M, nbt = (int)((B + TC_N - 1) / TC_N);
-            int P = (nblk * nbt + 147) / 148; P = P < 1 ? 1 : P;                 // about one block per SM
-            P = std::max(P, (nblk + W_MAXCH - 1) / W_MAXCH);
-            const dim3 g((nblk + P - 1) / P, nbt);
-            wide_l2_vjp_tc_kernel<H, G><<<g, 128, smem, h->stream>>>(m, img, hidden, in, B, P, part, hbar, counters);
+            const int nblk = m.n / TC_KB;
+            wide_l2_vjp_tc_kernel<H, G><<<dim3(nblk, (unsigned)((B + TC_N - 1) / TC_N)), 128, smem, h->stream>>>(m, img, hidden, in, B, part);
+            wide_sum_partials_kernel<float, H><<<(unsigned)((B * H + 7) / 8), 128, 0, h->stream>>>(part, nblk, B, hbar, in.mask);
+            ++h->launches;
             return 0;
         }
     }
@@ -1635,7 +1651,7 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     const int nblkC = (int)(((int64_t)n * G + ROWS1 - 1) / ROWS1), gx1 = nblkC + (n + ROWS1 - 1) / ROWS1;
     const int np_l = L.ec, np_1 = gx1, np_2 = L.uc, npart = np_l + np_1 + np_2;
     size_t bytes = wide_ctl_bytes(B) + sizeof(T) * (nB + 7 * nB * 3 + (size_t)7 * B * W_HP * 2 + (size_t)B * 15 + 2 * (size_t)B * npart +
-                                                    (size_t)L.nchunk * B * H) + sizeof(unsigned) * (size_t)B + 24 * 256;
+                                                    wide_part_rows(n, L) * B * H) + sizeof(unsigned) * (size_t)B + 24 * 256;
     char* base = nullptr;
     ENSURE(h, W_WIDE_B, bytes, base);
     Arena A{base};
@@ -1645,7 +1661,7 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     w.yb1 = A.take<T>((size_t)7 * B * W_HP); w.x2 = A.take<T>((size_t)7 * B * W_HP);
     w.h = A.take<T>(B); w.th = A.take<T>(7 * (size_t)B); w.hd = A.take<T>(7 * (size_t)B);
     w.part0 = A.take<T>((size_t)B * npart); w.part1 = A.take<T>((size_t)B * npart);
-    T* part = A.take<T>((size_t)L.nchunk * B * H);
+    T* part = A.take<T>(wide_part_rows(n, L) * B * H);
     unsigned* counters = A.take<unsigned>(B);
     if (!h->wide_counters_zeroed[1] || h->wide_counters_ptr[1] != counters) {
         CK(h, cudaMemsetAsync(counters, 0, sizeof(unsigned) * (size_t)B, st));
