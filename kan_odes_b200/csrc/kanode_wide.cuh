@@ -197,15 +197,15 @@ __device__ __forceinline__ void wide_reduce_tail(T (*red)[W_BT + 1], int b0, int
 }
 
 // dst[b][o] = sum_c part[c][b][o] as its own launch (tensor-core reduce kernel: many chunks, no last-block tail):
-// 16 lanes per value, each adds every 16th chunk, then a fixed-order shuffle tree
+// 32 lanes per value, each adds every 32nd chunk, then a fixed-order shuffle tree
 template <class T, int H>
 __global__ void __launch_bounds__(128) wide_sum_partials_kernel(const T* part, int nchunk, int64_t B, T* dst, const int* mask) {
-    const int64_t v = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 4);
-    const int g = threadIdx.x & 15;
+    const int64_t v = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int g = threadIdx.x & 31;
     T s = T(0);
-    if (v < B * H) for (int c = g; c < nchunk; c += 16) s += ld_cg(part + (int64_t)c * B * H + v);
+    if (v < B * H) for (int c = g; c < nchunk; c += 32) s += ld_cg(part + (int64_t)c * B * H + v);
 #pragma unroll
-    for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     if (g == 0 && v < B * H) { const int64_t b = v / H; if (!mask || mask[b]) dst[b * W_HP + (v - b * H)] = s; }
 }
 
@@ -793,6 +793,19 @@ __global__ void __launch_bounds__(W_GT) wide_gp1_kernel(const __grid_constant__ 
     const int row0 = (segW ? (int)blockIdx.x - nblkC : (int)blockIdx.x) * ROWS;       // row within the segment
     const int nrows = segW ? n : n * G;
     const T inv_h = (T)m.inv_h1;
+    // g_old of this thread's 5 element pairs first: the loads are in flight while the block builds its feature tile
+    const int64_t seg = segW ? m.offW1 : m.offC1;
+    const T* gold = nullptr; T* gnew = nullptr;
+    if (MODE == 0) { const int cur = a.cur[b]; gold = a.g + ((int64_t)b * 2 + cur) * m.np + seg + (int64_t)row0 * H; gnew = a.g + ((int64_t)b * 2 + (cur ^ 1)) * m.np + seg + (int64_t)row0 * H; }
+    const int E = (nrows - row0) * H;             // elements of this tile that exist
+    WVec2<T> g0[W_GK];
+    if (MODE == 0) {
+#pragma unroll
+        for (int k = 0; k < W_GK; ++k) {
+            const int el = 2 * tid + k * 2 * W_GT;
+            g0[k] = el < E ? *reinterpret_cast<const WVec2<T>*>(gold + el) : WVec2<T>{T(0), T(0)};
+        }
+    }
     if (!segW) {
         const int i0 = row0 / G;
         for (int idx = tid; idx < NS * UNITS; idx += W_GT) {
@@ -825,19 +838,7 @@ __global__ void __launch_bounds__(W_GT) wide_gp1_kernel(const __grid_constant__ 
             else { ab[s][k] = yb; at[s][k] = T(0); }
         }
     __syncthreads();
-    const int64_t seg = segW ? m.offW1 : m.offC1;
-    const T* gold = nullptr; T* gnew = nullptr;
-    if (MODE == 0) { const int cur = a.cur[b]; gold = a.g + ((int64_t)b * 2 + cur) * m.np + seg + (int64_t)row0 * H; gnew = a.g + ((int64_t)b * 2 + (cur ^ 1)) * m.np + seg + (int64_t)row0 * H; }
-    const int E = (nrows - row0) * H;             // elements of this tile that exist
     T es = T(0);
-    WVec2<T> g0[W_GK];
-    if (MODE == 0) {
-#pragma unroll
-        for (int k = 0; k < W_GK; ++k) {
-            const int el = 2 * tid + k * 2 * W_GT;
-            g0[k] = el < E ? *reinterpret_cast<const WVec2<T>*>(gold + el) : WVec2<T>{T(0), T(0)};
-        }
-    }
 #pragma unroll
     for (int k = 0; k < W_GK; ++k) {
         const int el = 2 * tid + k * 2 * W_GT;
@@ -1480,7 +1481,7 @@ int wide_l2_reverse(kanode_handle* h, const WideModel& m, const T* p, const T* h
             if (!attr_set) { CK(h, cudaFuncSetAttribute(wide_l2_vjp_tc_kernel<H, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
             const int nblk = m.n / TC_KB;
             wide_l2_vjp_tc_kernel<H, G><<<dim3(nblk, (unsigned)((B + TC_N - 1) / TC_N)), 128, smem, h->stream>>>(m, img, hidden, in, B, part);
-            wide_sum_partials_kernel<float, H><<<(unsigned)((B * H + 7) / 8), 128, 0, h->stream>>>(part, nblk, B, hbar, in.mask);
+            wide_sum_partials_kernel<float, H><<<(unsigned)((B * H + 3) / 4), 128, 0, h->stream>>>(part, nblk, B, hbar, in.mask);
             ++h->launches;
             return 0;
         }
