@@ -427,20 +427,30 @@ int loss_grad_host(kanode_handle* h, const T* u0, int64_t B, double t0, double t
         CK(h, cudaMemcpyAsync(d_tg, target, sizeof(T) * nout, cudaMemcpyHostToDevice, h->stream));
         if (int rc = loss_grad_dev<T>(h, d_u0, B, t0, t1, saveat, nsave, d_tg, abstol, reltol, d_loss, d_grad, d_du0,
                                       d_f, d_b, (T*)nullptr)) return rc;
-        std::vector<kanode_stats> f((size_t)B);
-        CK(h, cudaMemcpyAsync(f.data(), d_f, sizeof(kanode_stats) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+        // every result goes to ONE pinned staging block with async copies and a single synchronisation
+        const size_t o_f = 0, o_b = o_f + sizeof(kanode_stats) * (size_t)B, o_du = o_b + sizeof(kanode_stats) * (size_t)B,
+                     o_g = o_du + sizeof(T) * (size_t)B * h->n, o_l = (o_g + sizeof(T) * h->np + 7) / 8 * 8, total = o_l + 8;
+        if (h->stage_bytes < total) {
+            if (h->stage) { CK(h, cudaStreamSynchronize(h->stream)); cudaFreeHost(h->stage); h->stage = nullptr; h->stage_bytes = 0; }
+            CK(h, cudaMallocHost(&h->stage, total + total / 8));
+            h->stage_bytes = total + total / 8;
+        }
+        char* st = static_cast<char*>(h->stage);
+        CK(h, cudaMemcpyAsync(st + o_f, d_f, sizeof(kanode_stats) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+        if (bst) CK(h, cudaMemcpyAsync(st + o_b, d_b, sizeof(kanode_stats) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+        if (du0) CK(h, cudaMemcpyAsync(st + o_du, d_du0, sizeof(T) * (size_t)B * h->n, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(st + o_g, d_grad, sizeof(T) * h->np, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(st + o_l, d_loss, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(h, cudaStreamSynchronize(h->stream));
+        const kanode_stats* f = reinterpret_cast<const kanode_stats*>(st + o_f);
         bool overflow = false;
         for (int64_t b = 0; b < B; ++b) overflow |= (f[b].retcode == KANODE_RET_RECORD_OVERFLOW);
         if (overflow && attempt < 6) { h->rec_cap *= 4; continue; }   // grow the dense record and redo the step
-        double lsum = 0;
-        std::vector<T> gs(h->np);
-        CK(h, cudaMemcpyAsync(&lsum, d_loss, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaMemcpyAsync(gs.data(), d_grad, sizeof(T) * h->np, cudaMemcpyDeviceToHost, h->stream));
-        if (du0) CK(h, cudaMemcpyAsync(du0, d_du0, sizeof(T) * (size_t)B * h->n, cudaMemcpyDeviceToHost, h->stream));
-        if (bst) CK(h, cudaMemcpyAsync(bst, d_b, sizeof(kanode_stats) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaStreamSynchronize(h->stream));
-        if (fst) std::memcpy(fst, f.data(), sizeof(kanode_stats) * (size_t)B);
+        if (fst) std::memcpy(fst, st + o_f, sizeof(kanode_stats) * (size_t)B);
+        if (bst) std::memcpy(bst, st + o_b, sizeof(kanode_stats) * (size_t)B);
+        if (du0) std::memcpy(du0, st + o_du, sizeof(T) * (size_t)B * h->n);
+        const T* gs = reinterpret_cast<const T*>(st + o_g);
+        double lsum = 0; std::memcpy(&lsum, st + o_l, sizeof(double));
         *loss = (T)(lsum / ((double)B * nsave * h->n));
         for (size_t i = 0; i < h->np; ++i) grad[i] = (T)((double)gs[i] / (double)B);
         return 0;
@@ -509,6 +519,7 @@ int kanode_destroy(kanode_handle* h) {
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->aux_ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->wide_gp_ev) cudaEventDestroy(e);
+    if (h->stage) cudaFreeHost(h->stage);
     if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
