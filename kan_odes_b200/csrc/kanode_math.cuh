@@ -149,6 +149,20 @@ template <class T> __device__ __forceinline__ void basis_both(int kind, T a, T& 
     else { y = kdiv(T(1), T(1) + a * a); dy = T(-2) * a * y; }
 }
 
+// ---- packed fp32x2 FMA (Blackwell FFMA2: two IEEE fmas per issue slot) -----------------------------------
+// d0 += a0*b0, d1 += a1*b1.  The float overloads emit fma.rn.f32x2 (bit-identical to two scalar FFMAs; a broadcast
+// second operand costs no extra instruction); every other type falls back to two scalar FMAs.
+__device__ __forceinline__ void kfma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    unsigned long long ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rd) : "f"(d0), "f"(d1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rd) : "l"(ra), "l"(rb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rd));
+}
+template <class T> __device__ __forceinline__ void kfma2(T& d0, T& d1, T a0, T a1, T b0, T b1) { d0 += a0 * b0; d1 += a1 * b1; }
+template <class T> __device__ __forceinline__ void kfma2b(T& d0, T& d1, T a0, T a1, T c) { kfma2(d0, d1, a0, a1, c, c); }
+
 // ---- PI controller helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ float fastlog2f(float x) {
     const uint32_t bits = __float_as_uint(x);

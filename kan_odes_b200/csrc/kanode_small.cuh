@@ -264,8 +264,15 @@ __device__ __forceinline__ void small_vjp_sm(const P& p, const T* __restrict__ w
         const T* w = wsm + j * P::UW;
         T wl[NQ];
         T h = T(0);
+        if constexpr (sizeof(T) == 4 && NQ % 2 == 0) {          // two partial sums, one FFMA2 per pair of features
+            T h1 = T(0);
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) { wl[q] = w[q]; h += wl[q] * f[q]; }
+            for (int q = 0; q < NQ; q += 2) { wl[q] = w[q]; wl[q + 1] = w[q + 1]; kfma2(h, h1, wl[q], wl[q + 1], f[q], f[q + 1]); }
+            h += h1;
+        } else {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) { wl[q] = w[q]; h += wl[q] * f[q]; }
+        }
         const T xn = normalize<NORM>(h);
         T xnbar = T(0);
 #pragma unroll
@@ -284,8 +291,13 @@ __device__ __forceinline__ void small_vjp_sm(const P& p, const T* __restrict__ w
         const T hb = xnbar * normalize_deriv<NORM>(xn) + sbar * ds;
         rec[(off_h + j) * nthr] = h;
         rec[(off_hbar + j) * nthr] = hb;
+        if constexpr (NQ % 2 == 0) {
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) bb[q] += wl[q] * hb;
+            for (int q = 0; q < NQ; q += 2) kfma2b(bb[q], bb[q + 1], wl[q], wl[q + 1], hb);
+        } else {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) bb[q] += wl[q] * hb;
+        }
     }
 #pragma unroll
     for (int i = 0; i < I; ++i) {
@@ -926,7 +938,7 @@ __global__ void __launch_bounds__(KANODE_BWD_BT, LAT ? 1 : KANODE_BWD_MINB) smal
                         const T l = rec[(SR::LAM + o) * nthr];
                         const T ab = wb * l, at = wt * l;
 #pragma unroll
-                        for (int q = 0; q <= G; ++q) { vb[q][o] += ab * c[q]; vt[q][o] += at * c[q]; }
+                        for (int q = 0; q <= G; ++q) kfma2b(vb[q][o], vt[q][o], ab, at, c[q]);     // (vb, vt) += (ab, at) * c: one FFMA2
                     }
                 }
 #pragma unroll
@@ -959,7 +971,7 @@ __global__ void __launch_bounds__(KANODE_BWD_BT, LAT ? 1 : KANODE_BWD_MINB) smal
                         const T hb = rec[(SR::HBAR + o0 + oo) * nthr];
                         const T ab = wb * hb, at = wt * hb;
 #pragma unroll
-                        for (int q = 0; q <= G; ++q) { vb[q][oo] += ab * c[q]; vt[q][oo] += at * c[q]; }
+                        for (int q = 0; q <= G; ++q) kfma2b(vb[q][oo], vt[q][oo], ab, at, c[q]);
                     }
                 }
 #pragma unroll

@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(W_BT, 3) wide_l1_fwd_kernel(const __grid_const
 #pragma unroll
                 for (int q = 0; q < NQ; ++q)
 #pragma unroll
-                    for (int o = 0; o < H; ++o) acc[o] += w[q * H + o] * c[q];
+                    for (int o = 0; o < H; o += 2) kfma2b(acc[o], acc[o + 1], w[q * H + o], w[q * H + o + 1], c[q]);   // FFMA2
             }
 #pragma unroll
             for (int o = 0; o < H; ++o) {
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(W_BT, 3) wide_l2_vjp_kernel(const __grid_const
                     d[0] = v0.x; d[1] = v0.y; d[2] = v1.x; d[3] = v1.y;
                 }
 #pragma unroll
-                for (int bl = 0; bl < GB; ++bl) inner[bl] += wv * d[bl];
+                for (int bl = 0; bl < GB; bl += 2) kfma2b(inner[bl], inner[bl + 1], d[bl], d[bl + 1], wv);
             }
 #pragma unroll
             for (int bl = 0; bl < GB; ++bl) {
@@ -731,15 +731,29 @@ __global__ void __launch_bounds__(W_BT, 3) wide_l1_vjp_kernel(const __grid_const
                 const T y = kexp(-a * a);
                 const T db = T(-2) * a * y;
                 T bbar = T(0);
+                if constexpr (sizeof(T) == 4) {
+                    T b1 = T(0);
 #pragma unroll
-                for (int o = 0; o < H; ++o) bbar += w[g * H + o] * yb[o];
+                    for (int o = 0; o < H; o += 2) kfma2(bbar, b1, w[g * H + o], w[g * H + o + 1], yb[o], yb[o + 1]);
+                    bbar += b1;
+                } else {
+#pragma unroll
+                    for (int o = 0; o < H; ++o) bbar += w[g * H + o] * yb[o];
+                }
                 xnbar += db * inv_h * bbar;
             }
             T xb = xnbar * normalize_deriv_rt(m.norm1, xn);
             T sw, ds; swish_both(x, sw, ds);
             T sbar = T(0);
+            if constexpr (sizeof(T) == 4) {
+                T s1 = T(0);
 #pragma unroll
-            for (int o = 0; o < H; ++o) sbar += w[G * H + o] * yb[o];
+                for (int o = 0; o < H; o += 2) kfma2(sbar, s1, w[G * H + o], w[G * H + o + 1], yb[o], yb[o + 1]);
+                sbar += s1;
+            } else {
+#pragma unroll
+                for (int o = 0; o < H; ++o) sbar += w[G * H + o] * yb[o];
+            }
             xb += sbar * ds;
             dl[(int64_t)(b0 + bl0 + k) * n + i] = -xb;
         }
@@ -847,7 +861,7 @@ __global__ void __launch_bounds__(W_GT) wide_gp1_kernel(const __grid_constant__ 
         if (MODE == 0) {
             T vb0 = T(0), vb1 = T(0), vt0 = T(0), vt1 = T(0);
 #pragma unroll
-            for (int s = 0; s < 7; ++s) { const T c = C[s][rl]; vb0 += ab[s][0] * c; vb1 += ab[s][1] * c; vt0 += at[s][0] * c; vt1 += at[s][1] * c; }
+            for (int s = 0; s < 7; ++s) { const T c = C[s][rl]; kfma2b(vb0, vb1, ab[s][0], ab[s][1], c); kfma2b(vt0, vt1, at[s][0], at[s][1], c); }
             WVec2<T> g1;
             g1.x = g0[k].x + vb0; g1.y = g0[k].y + vb1;
             const T r0 = wdiv(vt0, a.abstol + kmax(kabs(g0[k].x), kabs(g1.x)) * a.reltol);
@@ -919,7 +933,7 @@ __global__ void __launch_bounds__(W_BT) wide_gp2_kernel(const __grid_constant__ 
                     }
                     T vb = T(0), vt = T(0);
 #pragma unroll
-                    for (int s = 0; s < 7; ++s) { vb += al[s] * fs[s]; vt += alt[s] * fs[s]; }
+                    for (int s = 0; s < 7; ++s) kfma2b(vb, vt, al[s], alt[s], fs[s]);
                     const T g1 = g0[q] + vb;
                     const T r = wdiv(vt, a.abstol + kmax(kabs(g0[q]), kabs(g1)) * a.reltol);
                     es += r * r;

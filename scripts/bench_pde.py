@@ -93,7 +93,7 @@ def main():
                        device=local, stream=stream.cuda_stream, dtype=ndt)
         ode.set_params(p)
         lib = ode.lib
-        lib.kanode_set_record_capacity(ode.h, 64)                  # *_dev entry points do not regrow the dense record
+        lib.kanode_set_record_capacity(ode.h, 512 if name == "source4096" else 64)   # *_dev entry points do not regrow the dense record
         with torch.cuda.stream(stream):
             d_u0 = torch.tensor(u0, dtype=tdt, device=dev); d_tg = torch.tensor(tg, dtype=tdt, device=dev)
             d_grad = torch.zeros(ode.np_, dtype=tdt, device=dev); d_loss = torch.zeros(1, dtype=torch.float64, device=dev)
