@@ -789,7 +789,7 @@ template <class T> __device__ __forceinline__ void gp_finalize(const T* gold, T*
 // Layer 1: its slice of g is one contiguous array of (n*G + n) rows x H (C1 rows (i,q), then the W1 rows i), streamed with
 // coalesced 2-element accesses.  A thread's output pair o0 = (2*tid) % H is the same in every iteration (2*W_GT % H == 0),
 // so its 2 x 7 x 2 weighted cotangents stay in registers; the 7 stage features of a row come from shared memory.
-constexpr int W_GT = 320, W_GK = 5;      // threads per block, iterations per block (tile = W_GK * 2 * W_GT elements)
+constexpr int W_GT = 320, W_GK = 10;      // threads per block, iterations per block (tile = W_GK * 2 * W_GT elements)
 template <class T> struct alignas(2 * sizeof(T)) WVec2 { T x, y; };
 
 // grid.x = nblkC blocks over the C1 rows (tiles aligned to whole input units) followed by the blocks over the W1 rows
@@ -853,11 +853,12 @@ __global__ void __launch_bounds__(W_GT) wide_gp1_kernel(const __grid_constant__ 
         }
     __syncthreads();
     T es = T(0);
+    const int rl0 = (2 * tid) / H;
 #pragma unroll
     for (int k = 0; k < W_GK; ++k) {
         const int el = 2 * tid + k * 2 * W_GT;
         if (el >= E) break;
-        const int rl = el / H;
+        const int rl = rl0 + k * (2 * W_GT / H);              // == el / H: a thread's rows are 64 apart
         if (MODE == 0) {
             T vb0 = T(0), vb1 = T(0), vt0 = T(0), vt1 = T(0);
 #pragma unroll
