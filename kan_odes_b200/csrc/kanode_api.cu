@@ -493,6 +493,8 @@ int kanode_create(const kanode_desc* desc, int device, void* stream, kanode_hand
     if (const char* e = std::getenv("KANODE_SCHEDULE")) h->schedule = std::atoi(e);
     if (const char* e = std::getenv("KANODE_WIDE")) h->wide = std::atoi(e);
     if (const char* e = std::getenv("KANODE_WIDE_TC")) h->wide_tc = std::atoi(e);
+    if (const char* e = std::getenv("KANODE_WIDE_GRAPH")) h->wide_graph = std::atoi(e);
+    if (const char* e = std::getenv("KANODE_WIDE_GRAPH_MAXN")) h->wide_graph_maxn = std::atoi(e);
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, KANODE_ERR_CUDA, "cudaSetDevice failed"); }
     if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
     else {
@@ -520,6 +522,7 @@ int kanode_destroy(kanode_handle* h) {
     for (auto& e : h->aux_ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->wide_gp_ev) cudaEventDestroy(e);
     if (h->stage) cudaFreeHost(h->stage);
+    for (auto& g : h->wide_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;

@@ -69,6 +69,12 @@ struct kanode_handle {
     uint64_t wide_w1t_version[2] = {~0ull, ~0ull};
     uint64_t wide_w2img_version = ~0ull, wide_w2timg_version = ~0ull;
     int wide_tc = 1;                         // fp32 layer-2 forward contraction on tcgen05 (KANODE_WIDE_TC=0: CUDA cores)
+    // one lockstep step attempt captured as a CUDA graph (forward-only, dense forward, backward) x (fp32, fp64): replayed
+    // per attempt while the kernel arguments (workspace pointers, sizes, tolerances) stay the same
+    struct WideGraph { cudaGraphExec_t exec = nullptr; std::vector<char> sig; int nodes = 0; };
+    WideGraph wide_graphs[6];
+    int wide_graph = 1;                      // KANODE_WIDE_GRAPH=0: launch every kernel directly
+    int wide_graph_maxn = 8192;              // larger states: direct launches (kernels are long, per-pass timing stays available)
     std::vector<cudaEvent_t> wide_gp_ev;     // event pairs around the g passes of the last wide loss_grad call
     int wide_gp_used = 0;
     bool wide_counters_zeroed[2] = {false, false};

@@ -1423,6 +1423,29 @@ inline WideCtl wide_ctl_carve(Arena& A, int64_t B) {
     return c;
 }
 
+// Graph of one step attempt: `body` enqueues the attempt's kernels on h->stream.  The instantiated graph is kept per
+// (kind, dtype) and reused while the signature (every pointer / size / scalar the kernels receive) is unchanged.
+template <class Body>
+inline int wide_attempt_graph(kanode_handle* h, int slot, const std::vector<char>& sig, Body&& body, cudaGraphExec_t* out) {
+    kanode_handle::WideGraph& g = h->wide_graphs[slot];
+    if (!g.exec || g.sig != sig) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        const int64_t l0 = h->launches;
+        CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        const int64_t n0 = body();
+        cudaGraph_t graph = nullptr;
+        CK(h, cudaStreamEndCapture(h->stream, &graph));
+        const int64_t extra = h->launches - l0;          // launches the helpers counted on the handle directly
+        h->launches = l0;
+        CK(h, cudaGraphInstantiate(&g.exec, graph, 0));
+        cudaGraphDestroy(graph);
+        g.sig = sig; g.nodes = (int)(n0 + extra);
+    }
+    *out = g.exec;
+    return 0;
+}
+template <class U> inline void sig_add(std::vector<char>& sig, const U& v) { const char* q = reinterpret_cast<const char*>(&v); sig.insert(sig.end(), q, q + sizeof(U)); }
+
 // wait until no IC is active; polls the device flags (the host only decides how many more attempts to enqueue)
 inline int wide_any_active(kanode_handle* h, const int* d_active, int64_t B, bool& any) {
     std::vector<int> act((size_t)B);
@@ -1599,7 +1622,8 @@ int wide_forward(kanode_handle* h, const WideModel& m, const T* p, WideFwd<T> a,
     const int slot = dense ? 1 : 0;
     const int expect = h->wide_iters[slot];          // attempts the previous call of this kind needed
     bool any = a.t0 < a.t1;
-    while (any) {
+    auto attempt = [&]() -> int64_t {
+        const int64_t l0 = launches;
         for (int s = 1; s < 7; ++s) {
             T coef[7];
             for (int j = 0; j < s; ++j) coef[j] = (T)A_[s][j];
@@ -1609,6 +1633,20 @@ int wide_forward(kanode_handle* h, const WideModel& m, const T* p, WideFwd<T> a,
         wide_fwd_ctl_kernel<T><<<(unsigned)B, 128, 0, st>>>(c, a, n, 2);
         wide_fwd_accept_kernel<T><<<ge, W_ET, 0, st>>>(c, a, n, B);
         launches += 3;
+        return launches - l0;
+    };
+    cudaGraphExec_t gexec = nullptr;
+    if (h->wide_graph && n <= h->wide_graph_maxn && any) {
+        std::vector<char> sig;
+        sig_add(sig, m); sig_add(sig, a); sig_add(sig, c); sig_add(sig, L); sig_add(sig, B); sig_add(sig, p); sig_add(sig, w1t);
+        sig_add(sig, hidden); sig_add(sig, part); sig_add(sig, counters); sig_add(sig, h->wide_tc); sig_add(sig, h->ws[kanode_handle::W_W2IMG].p);
+        const int64_t l0 = launches;
+        if (int rc = wide_attempt_graph(h, (dense ? 1 : 0) * 2 + (sizeof(T) == 8), sig, attempt, &gexec)) return rc;
+        launches = l0;
+    }
+    while (any) {
+        if (gexec) { CK(h, cudaGraphLaunch(gexec, st)); launches += h->wide_graphs[(dense ? 1 : 0) * 2 + (sizeof(T) == 8)].nodes; }
+        else attempt();
         ++iters;
         if (iters >= expect) {
             if (int rc = wide_any_active(h, c.active, B, any)) return rc;
@@ -1715,13 +1753,15 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
         cudaEventRecord(h->wide_gp_ev[h->wide_gp_used++], st);
     };
     auto gpass = [&](int mode, T* dst) {
+        const bool timed = mode == 0;
         WideGp<T> q1 = gpa, q2 = gpa;
         if (mode == 0) gp_event();
+        if (mode == 3) mode = 0;                                        // inside a graph capture: no timing events
         q1.es_part = dst; q1.off = np_l; q2.es_part = dst; q2.off = np_l + np_1;
         if (mode == 0) { wide_gp1_kernel<T, H, G, 0><<<gg1, W_GT, 0, st>>>(m, q1, B, nblkC); wide_gp2_kernel<T, H, G, 0><<<gg2, W_BT, 0, st>>>(m, q2, B); }
         else if (mode == 1) { wide_gp1_kernel<T, H, G, 1><<<gg1, W_GT, 0, st>>>(m, q1, B, nblkC); wide_gp2_kernel<T, H, G, 1><<<gg2, W_BT, 0, st>>>(m, q2, B); }
         else { wide_gp1_kernel<T, H, G, 2><<<gg1, W_GT, 0, st>>>(m, q1, B, nblkC); wide_gp2_kernel<T, H, G, 2><<<gg2, W_BT, 0, st>>>(m, q2, B); }
-        if (mode == 0) gp_event();
+        if (timed) gp_event();
         launches += 2;
     };
     wide_bwd_ctl_kernel<T><<<(unsigned)B, 128, 0, st>>>(c, w, n, B, -1);
@@ -1739,7 +1779,9 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     int iters = 0;
     const int expect = h->wide_iters[2];
     bool any = t0 < t1;
-    while (any) {
+    bool capturing = false;
+    auto attempt = [&]() -> int64_t {
+        const int64_t l0 = launches;
         adj(0, 0, nullptr, c.do_s0);                                   // only the ICs whose lambda jumped at a save time
         for (int s = 1; s < 7; ++s) {
             T coef[7];
@@ -1747,10 +1789,28 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
             adj(s, s, coef, c.active);
         }
         wide_err_kernel<T><<<ge, W_ET, 0, st>>>(w.lam, w.yb2 + (size_t)6 * nB, w.kl, n, B, w.h, w.abstol, w.reltol, c.active, w.part0, npart, 0);
-        gpass(0, w.part0);
+        gpass(capturing ? 3 : 0, w.part0);
         wide_bwd_ctl_kernel<T><<<(unsigned)B, 128, 0, st>>>(c, w, n, B, 2);
         wide_bwd_accept_kernel<T><<<ge, W_ET, 0, st>>>(c, w, n, B);
         launches += 3;
+        return launches - l0;
+    };
+    cudaGraphExec_t gexec = nullptr;
+    const int gslot = 4 + (sizeof(T) == 8);
+    if (h->wide_graph && n <= h->wide_graph_maxn && any) {
+        std::vector<char> sig;
+        sig_add(sig, m); sig_add(sig, w); sig_add(sig, c); sig_add(sig, L); sig_add(sig, B); sig_add(sig, p); sig_add(sig, w1t); sig_add(sig, g);
+        sig_add(sig, part); sig_add(sig, counters); sig_add(sig, npart); sig_add(sig, h->wide_tc); sig_add(sig, h->ws[kanode_handle::W_W2TIMG].p);
+        const int64_t l0 = launches;
+        capturing = true;
+        const int rc = wide_attempt_graph(h, gslot, sig, attempt, &gexec);
+        capturing = false;
+        if (rc) return rc;
+        launches = l0;
+    }
+    while (any) {
+        if (gexec) { CK(h, cudaGraphLaunch(gexec, st)); launches += h->wide_graphs[gslot].nodes; }
+        else attempt();
         ++iters;
         if (iters >= expect) {
             if (int rc = wide_any_active(h, c.active, B, any)) return rc;
