@@ -309,6 +309,28 @@ __device__ void g_vjp(const GenericModel& m, const T* p, const T* y, const T* la
     // source model: rec holds kg[np] = sum_j lam_j dkan(y_j)/dp ; np <= GEN_FEAT
     const int n = m.n, np = (int)m.np;
     const T ls = (T)m.lap_scale;
+    if (np <= GEN_ACC) {
+        // the reference's shape (1 -> 1, np = G + 1 = 11): every thread accumulates its nodes' contributions privately and the
+        // block adds them once, in a fixed order (shared-memory atomics on 11 addresses serialised the whole block)
+        T acc[GEN_ACC];
+#pragma unroll
+        for (int k = 0; k < GEN_ACC; ++k) acc[k] = T(0);
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            T xs[KANODE_MAX_LAYERS * GEN_PW];
+            pw_forward<T>(m, p, y[j], xs);
+            const T lj = lam[j];
+            const T xb = pw_reverse<T>(m, p, xs, lj, [&](long long jj, T v) {
+#pragma unroll
+                for (int k = 0; k < GEN_ACC; ++k) if (k == (int)jj) acc[k] += v;
+            });
+            const T lm = lam[(j + n - 1) % n], lp = lam[(j + 1) % n];               // the Laplacian is symmetric
+            ubar[j] = ls * (lm - T(2) * lj + lp) + xb;
+        }
+        block_reduce<T, GEN_ACC>(acc, sm);
+        if (threadIdx.x < np) rec[threadIdx.x] = sm.res[threadIdx.x];
+        __syncthreads();
+        return;
+    }
     __syncthreads();
     for (int j = threadIdx.x; j < np; j += blockDim.x) sm.feat[j] = T(0);
     __syncthreads();
