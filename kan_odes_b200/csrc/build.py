@@ -15,7 +15,7 @@ BUILD = HERE / "_build"
 COMMON = ["kanode_host.h", "kanode_math.cuh", "kanode_wide_api.h", "../../include/kanode.h"]
 UNITS = {
     "kanode_api.cu": ["kanode_small.cuh", "kanode_small_ls.cuh", "kanode_generic.cuh"],
-    "kanode_wide.cu": ["kanode_wide.cuh"],
+    "kanode_wide.cu": ["kanode_wide.cuh", "kanode_wsrc.cuh"],
 }
 SOURCES = list(UNITS)
 NVCC_FLAGS = ["-std=c++20", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",

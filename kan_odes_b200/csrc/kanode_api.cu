@@ -188,6 +188,9 @@ int solve_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double t1, 
     WideKey wk;
     if (h->wide && wide_match(h->desc, wk) && (int64_t)B * h->n * 8 < (1ll << 31))
         return wide_solve(h, wk, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);
+    int sg = 0;
+    if (h->wide && wsrc_match(h->desc, sg) && (int64_t)B * h->n * 8 < (1ll << 31))
+        return wsrc_solve(h, sg, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);
     return generic_solve<T>(h, d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);
 }
 
@@ -341,6 +344,10 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
     WideKey wk;
     if (h->wide && wide_match(h->desc, wk) && (int64_t)B * h->n * 8 < (1ll << 31))
         return wide_loss_grad(h, wk, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum,
+                              d_grad_sum, d_du0, d_fst, d_bst, d_out_opt);
+    int sg = 0;
+    if (h->wide && wsrc_match(h->desc, sg) && (int64_t)B * h->n * 8 < (1ll << 31))
+        return wsrc_loss_grad(h, sg, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum,
                               d_grad_sum, d_du0, d_fst, d_bst, d_out_opt);
     return generic_loss_grad<T>(h, d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum, d_grad_sum,
                                 d_du0, d_fst, d_bst, d_out_opt);

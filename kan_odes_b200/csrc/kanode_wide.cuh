@@ -1204,7 +1204,24 @@ template <class T> struct WideBwd {
     const T* dg; T* g; long long np;
     T* part0; T* part1; int npart;
     T* du0; kanode_stats* stats;
+    // hidden-source model (kanode_wsrc.cuh): dg/dt of the few pointwise-KAN parameters is kept per stage as block partials
+    const T* kg_part;  // [7][B][nkg][W_HP] or null
+    int nkg;
+    T* gsrc;           // [B][W_HP] gradient state of the source model
 };
+
+// hidden-source model: g terms of the control decisions.  kg[s][q] = sum of the block partials of stage s; the block's
+// threads add them into shared memory, thread 0 then evaluates the few parameters.
+template <class T> __device__ __forceinline__ void wsrc_sum_kg(const WideBwd<T>& a, int b, int64_t B, int nslots, T (*skg)[W_HP]) {
+    for (int v = threadIdx.x; v < nslots * W_HP; v += blockDim.x) {
+        const int s = v / W_HP, q = v - s * W_HP;
+        const T* src = a.kg_part + (((int64_t)s * B + b) * a.nkg) * W_HP + q;
+        T t = T(0);
+        for (int ch = 0; ch < a.nkg; ++ch) t += src[(int64_t)ch * W_HP];
+        skg[s][q] = t;
+    }
+    __syncthreads();
+}
 
 template <class T> __device__ __forceinline__ void wb_stage_time(const WideCtl& c, const WideBwd<T>& a, int b, int64_t B, int s, double ts) {
     const double* rt = a.rec_t + (int64_t)b * a.cap;
@@ -1248,8 +1265,10 @@ template <class T> __device__ void wb_begin(const WideCtl& c, const WideBwd<T>& 
 template <class T>
 __global__ void __launch_bounds__(128) wide_bwd_ctl_kernel(const WideCtl c, const WideBwd<T> a, int n, int64_t B, int phase) {
     __shared__ T sred[33];
+    __shared__ T skg[7][W_HP];
     const int b = blockIdx.x;
     const int NZ = n + (int)a.np;
+    const bool src = a.kg_part != nullptr;
     if (phase == -1) {           // state at t1: jumps at the end time (PresetTimeCallback fires at init), stage-0 time
         if (threadIdx.x) return;
         const int ok = a.retcode[b] == RET_SUCCESS && a.nsteps[b] > 0;
@@ -1266,8 +1285,10 @@ __global__ void __launch_bounds__(128) wide_bwd_ctl_kernel(const WideCtl c, cons
     if (phase == 0) {            // d0, d1 of initdt on the augmented state -> dt0, stage-1 time
         if (!c.active[b]) return;
         const T v0 = sum_partials<T>(a.part0 + (int64_t)b * a.npart, a.npart, sred);
-        const T v1 = sum_partials<T>(a.part1 + (int64_t)b * a.npart, a.npart, sred);
+        T v1 = sum_partials<T>(a.part1 + (int64_t)b * a.npart, a.npart, sred);
+        if (src) wsrc_sum_kg<T>(a, b, B, 1, skg);
         if (threadIdx.x) return;
+        if (src) for (int q = 0; q < (int)a.np; ++q) { const T x1 = skg[0][q] / a.abstol; v1 += x1 * x1; }
         const double d0 = sqrt((double)v0 / NZ), d1 = sqrt((double)v1 / NZ), dtmax = fabs(a.t1 - a.t0);
         double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
         dt0 = fmin(dt0, dtmax);
@@ -1278,8 +1299,10 @@ __global__ void __launch_bounds__(128) wide_bwd_ctl_kernel(const WideCtl c, cons
     }
     if (phase == 1) {
         if (!c.active[b]) return;
-        const T s2 = sum_partials<T>(a.part1 + (int64_t)b * a.npart, a.npart, sred);
+        T s2 = sum_partials<T>(a.part1 + (int64_t)b * a.npart, a.npart, sred);
+        if (src) wsrc_sum_kg<T>(a, b, B, 2, skg);
         if (threadIdx.x) return;
+        if (src) for (int q = 0; q < (int)a.np; ++q) { const T x2 = (skg[1][q] - skg[0][q]) / a.abstol; s2 += x2 * x2; }
         const double dt0 = c.dt0[b], d1 = c.d1[b], dtmax = fabs(a.t1 - a.t0), dtmin0 = fmax(eps_of(a.t0), eps_of(a.t1));
         const double d2 = sqrt((double)s2 / NZ) / dt0, mx = fmax(d1, d2);
         const double dt1 = (mx <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / 5.0);
@@ -1289,8 +1312,22 @@ __global__ void __launch_bounds__(128) wide_bwd_ctl_kernel(const WideCtl c, cons
         return;
     }
     if (!c.active[b]) { if (threadIdx.x == 0) { c.acc_now[b] = 0; c.do_s0[b] = 0; } return; }
-    const T es = sum_partials<T>(a.part0 + (int64_t)b * a.npart, a.npart, sred);
+    T es = sum_partials<T>(a.part0 + (int64_t)b * a.npart, a.npart, sred);
+    if (src) wsrc_sum_kg<T>(a, b, B, 7, skg);
     if (threadIdx.x) return;
+    T gnew[W_HP];
+    if (src) {                   // the few parameters of the pointwise KAN: g_new = g_old + sum_s wb_s kg_s and its error terms
+        const T hh = a.h[b];
+        for (int q = 0; q < (int)a.np; ++q) {
+            T vb = T(0), vt = T(0);
+#pragma unroll
+            for (int st = 0; st < 7; ++st) { vb += (-hh * Tab<T>::b(st)) * skg[st][q]; vt += (-hh * Tab<T>::bt(st)) * skg[st][q]; }
+            const T g0 = a.gsrc[(int64_t)b * W_HP + q], g1 = g0 + vb;
+            const T r = vt / (a.abstol + kmax(kabs(g0), kabs(g1)) * a.reltol);
+            es += r * r;
+            gnew[q] = g1;
+        }
+    }
     c.acc_now[b] = 0;
     c.nf[b] += c.do_s0[b] ? 7 : 6;
     const double EEst = (double)ksqrt(es / T(NZ));
@@ -1312,6 +1349,7 @@ __global__ void __launch_bounds__(128) wide_bwd_ctl_kernel(const WideCtl c, cons
         c.dtpropose[b] = fmax(fmin(dtmax, fabs(dtnew)), fmax(eps_of(tnew), dtmin0));
         c.t[b] = tnew;
         c.cur[b] ^= 1;
+        if (src) for (int q = 0; q < (int)a.np; ++q) a.gsrc[(int64_t)b * W_HP + q] = gnew[q];
         c.s_hi[b] = sp;
         while (sp >= 0 && a.saveat[sp] == tnew) --sp;
         c.s_lo[b] = sp + 1; c.sidx[b] = sp;
