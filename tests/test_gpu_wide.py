@@ -142,3 +142,39 @@ def test_wide_tensor_core_kernels_match_cuda_core_fp32(n, G, B, monkeypatch):
     assert _relmax(a["grad"], b["grad"]) < tol, (same, _relmax(a["grad"], b["grad"]))
     ref = orc.loss_grad(p, u0, tspan, saveat, tg)
     assert _relmax(a["grad"], ref["grad"]) < 2e-2 and abs(a["loss"] - ref["loss"]) < 5e-3 * abs(ref["loss"])
+
+
+@pytest.mark.parametrize("n,G,B", [(300, 5, 7), (41, 10, 3)])
+def test_hidden_source_lockstep_matches_block_per_trajectory(n, G, B, monkeypatch):
+    """Hidden-source model (periodic Laplacian + pointwise KDense(1,1,G); Allen-Cahn_Source.jl:50-54,90-99) through the
+    lockstep engine of csrc/kanode_wsrc.cuh against the block-per-trajectory kernels and the oracle: ragged n (block-edge
+    neighbours, periodic wrap inside a partial block), ICs with different step counts, save time at the end."""
+    from conftest import source_chain
+    from kan_odes_b200 import abi
+    chain = source_chain(G)
+    p = glorot_params(chain, seed=G)
+    kw = dict(rhs_kind=abi.RHS_SOURCE_LAPLACIAN, n_state=n, lap_coef=2e-4, dx=2.0 / (n - 1))
+    x = np.linspace(-1, 1, n)
+    amp = np.random.default_rng(n).uniform(0.3, 2.0, (B, 1))
+    u0 = amp * (x**2 * np.cos(np.pi * x))[None, :]
+    tspan, saveat = (0.0, 0.5), np.linspace(0, 0.5, 6)
+    tg = u0[:, None, :] * np.exp(0.5 * saveat)[None, :, None]
+    res = {}
+    for wide in (1, 0):
+        monkeypatch.setenv("KANODE_WIDE", str(wide))
+        ode = K.KanOde(chain, kw["rhs_kind"], n, kw["lap_coef"], kw["dx"], dtype=np.float64); ode.set_params(p)
+        l0 = ode.launch_count()
+        sol = ode.solve(u0, tspan, saveat); r = ode.loss_grad(u0, tspan, saveat, tg)
+        res[wide] = (sol, r, ode.launch_count() - l0)
+        ode.close()
+    (sw, rw, lw), (sg, rg, lg) = res[1], res[0]
+    assert lw > 10 * lg                                                 # the lockstep engine really ran
+    for a, b in ((sw.stats, sg.stats), (rw["fwd_stats"], rg["fwd_stats"]), (rw["bwd_stats"], rg["bwd_stats"])):
+        assert (a.naccept == b.naccept).all() and (a.nreject == b.nreject).all() and (a.nf == b.nf).all() and (a.retcode == 0).all()
+    assert _relmax(sw.array, sg.array) < 1e-12 and _relmax(rw["grad"], rg["grad"]) < 1e-9 and _relmax(rw["du0"], rg["du0"]) < 1e-9
+    ref = Oracle(chain.desc(**kw), np.float64).loss_grad(p, u0, tspan, saveat, tg)
+    assert (rw["bwd_stats"].naccept == ref["bwd_stats"][:, 0]).all() and _relmax(rw["grad"], ref["grad"]) < 1e-7
+    monkeypatch.setenv("KANODE_WIDE", "1")
+    ode = K.KanOde(chain, kw["rhs_kind"], n, kw["lap_coef"], kw["dx"], dtype=np.float32); ode.set_params(p)
+    r32 = ode.loss_grad(u0, tspan, saveat, tg); ode.close()
+    assert (r32["bwd_stats"].retcode == 0).all() and _relmax(r32["grad"], ref["grad"]) < 2e-2
