@@ -52,8 +52,9 @@ struct WideCtl {
     int *iter, *accept, *acc_now, *fail_now, *active, *modified, *do_s0, *sidx, *s_lo, *s_hi, *nrec, *naccept, *nreject, *nf,
         *ret, *cur;
     int* ridx;   // [7][B] dense-record index of every backward stage time
+    int* mask7;  // [7][B] backward: which (stage, IC) pairs are evaluated in this attempt (stage 0 only after a jump)
 };
-constexpr int W_NCTL_D = 10, W_NCTL_I = 16 + 7;
+constexpr int W_NCTL_D = 10, W_NCTL_I = 16 + 7 + 7;
 
 template <class T> __device__ __forceinline__ T ld_cg(const T* p) { return __ldcg(p); }
 // ratio for the error norm: fp32 uses rcp.approx (1 ulp; it only feeds EEst), fp64 the IEEE quotient
@@ -99,6 +100,7 @@ template <class T, int G> __device__ __forceinline__ void w_dfeatures(int norm, 
 template <class T> struct WideIn {
     const T* base; const T* ks; const T* hs; T coef[7]; int ncoef;
     const T* rec; int cap; const int* ridx; const T* th; const T* hd;
+    int brec;            // > 0: b indexes (stage, IC) pairs laid out [7][brec]; the dense record of pair b belongs to IC b % brec
     T* xstore;           // optional copy of x: [B][n]
     const int* mask;     // per-IC, 0 = skip (may be null)
 };
@@ -134,7 +136,8 @@ __device__ __forceinline__ void wide_inputs(const WideIn<T>& in, int b0, int b1,
         for (int bl = 0; bl < NB; ++bl) {
             const int b = on[bl] ? b0 + bl : b0;
             th[bl] = in.th[b]; hd[bl] = in.hd[b];
-            r[bl] = in.rec + ((int64_t)b * in.cap + in.ridx[b]) * 8 * (int64_t)n + i;
+            const int brow = in.brec > 0 ? b % in.brec : b;
+            r[bl] = in.rec + ((int64_t)brow * in.cap + in.ridx[b]) * 8 * (int64_t)n + i;
         }
 #pragma unroll
         for (int bl = 0; bl < NB; ++bl)
@@ -1237,6 +1240,7 @@ template <class T> __device__ __forceinline__ void wb_stage_time(const WideCtl& 
 
 template <class T> __device__ void wb_begin(const WideCtl& c, const WideBwd<T>& a, int b, int64_t B) {
     c.do_s0[b] = 0;
+    for (int s = 0; s < 7; ++s) c.mask7[(int64_t)s * B + b] = 0;
     if (!c.active[b]) return;
     const double t = c.t[b], t0 = a.t0, t1 = a.t1;
     if (!(t > t0)) { c.active[b] = 0; return; }
@@ -1258,6 +1262,8 @@ template <class T> __device__ void wb_begin(const WideCtl& c, const WideBwd<T>& 
     if (ret != RET_SUCCESS) { c.ret[b] = ret; c.active[b] = 0; return; }
     a.h[b] = (T)(-dt);
     c.do_s0[b] = c.modified[b];
+    c.mask7[b] = c.modified[b];
+    for (int s = 1; s < 7; ++s) c.mask7[(int64_t)s * B + b] = 1;
     c.modified[b] = 0;
     for (int s = 0; s < 7; ++s) wb_stage_time<T>(c, a, b, B, s, t - tab_c(s) * dt);
 }
@@ -1458,6 +1464,7 @@ inline WideCtl wide_ctl_carve(Arena& A, int64_t B) {
                   &c.naccept, &c.nreject, &c.nf, &c.ret, &c.cur};
     for (auto pp : ii) *pp = A.take<int>(B);
     c.ridx = A.take<int>(7 * B);
+    c.mask7 = A.take<int>(7 * B);
     return c;
 }
 
@@ -1743,7 +1750,7 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     const int nblkC = (int)(((int64_t)n * G + ROWS1 - 1) / ROWS1), gx1 = nblkC + (n + ROWS1 - 1) / ROWS1;
     const int np_l = L.ec, np_1 = gx1, np_2 = L.uc, npart = np_l + np_1 + np_2;
     size_t bytes = wide_ctl_bytes(B) + sizeof(T) * (nB + 7 * nB * 3 + (size_t)7 * B * W_HP * 2 + (size_t)B * 15 + 2 * (size_t)B * npart +
-                                                    wide_part_rows(n, L) * B * H) + sizeof(unsigned) * (size_t)B + 24 * 256;
+                                                    wide_part_rows(n, L) * 7 * B * H) + sizeof(unsigned) * (size_t)7 * B + 24 * 256;
     char* base = nullptr;
     ENSURE(h, W_WIDE_B, bytes, base);
     Arena A{base};
@@ -1753,10 +1760,10 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     w.yb1 = A.take<T>((size_t)7 * B * W_HP); w.x2 = A.take<T>((size_t)7 * B * W_HP);
     w.h = A.take<T>(B); w.th = A.take<T>(7 * (size_t)B); w.hd = A.take<T>(7 * (size_t)B);
     w.part0 = A.take<T>((size_t)B * npart); w.part1 = A.take<T>((size_t)B * npart);
-    T* part = A.take<T>(wide_part_rows(n, L) * B * H);
-    unsigned* counters = A.take<unsigned>(B);
+    T* part = A.take<T>(wide_part_rows(n, L) * 7 * B * H);
+    unsigned* counters = A.take<unsigned>(7 * B);
     if (!h->wide_counters_zeroed[1] || h->wide_counters_ptr[1] != counters) {
-        CK(h, cudaMemsetAsync(counters, 0, sizeof(unsigned) * (size_t)B, st));
+        CK(h, cudaMemsetAsync(counters, 0, sizeof(unsigned) * (size_t)7 * B, st));
         h->wide_counters_zeroed[1] = true; h->wide_counters_ptr[1] = counters;
     }
     w.t0 = t0; w.t1 = t1; w.saveat = d_saveat; w.nsave = nsave; w.abstol = (T)abstol; w.reltol = (T)reltol; w.maxiters = 100000;
@@ -1769,18 +1776,32 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     int64_t launches = 0;
     static const double A_[7][8] = KANODE_TSIT5_A;
     // adjoint rhs of stage slot s: records x_l / ybar_l, kl[s] = -(df/du)^T lambda_s
-    auto adj = [&](int s, int ncoef, const T* coef, const int* mask) {
+    const WideLaunch L7 = wide_launch(n, 7 * B, GB);       // all 7 stages of an attempt as (stage, IC) pairs
+    // layer-1 forward of EVERY stage of the attempt in one launch: sol(t_s) does not depend on lambda, and the stage times are
+    // known when the attempt opens, so the 7 x B (stage, IC) pairs share each unit's weights in one pass
+    auto l1_all_stages = [&]() {
         WideIn<T> in{};
-        in.rec = w.rec; in.cap = cap; in.ridx = c.ridx + (size_t)s * B; in.th = w.th + (size_t)s * B; in.hd = w.hd + (size_t)s * B;
-        in.xstore = w.x1 + (size_t)s * nB; in.mask = mask;
-        wide_l1_fwd_kernel<T, H, G, 1><<<gr, W_BT, 0, st>>>(m, w1t, in, B, L.P, L.bt_red, part, w.x2 + (size_t)s * B * W_HP, counters);
+        in.rec = w.rec; in.cap = cap; in.ridx = c.ridx; in.th = w.th; in.hd = w.hd; in.brec = (int)B;
+        in.xstore = w.x1; in.mask = c.mask7;
+        wide_l1_fwd_kernel<T, H, G, 1><<<dim3(L7.nchunk, L7.nbt_red), W_BT, 0, st>>>(m, w1t, in, 7 * B, L7.P, L7.bt_red, part, w.x2, counters);
+        ++launches;
+    };
+    // adjoint rhs of stage slot s: records x_l / ybar_l, kl[s] = -(df/du)^T lambda_s
+    auto adj = [&](int s, int ncoef, const T* coef, const int* mask, bool with_l1) {
+        if (with_l1) {
+            WideIn<T> in{};
+            in.rec = w.rec; in.cap = cap; in.ridx = c.ridx + (size_t)s * B; in.th = w.th + (size_t)s * B; in.hd = w.hd + (size_t)s * B;
+            in.xstore = w.x1 + (size_t)s * nB; in.mask = mask;
+            wide_l1_fwd_kernel<T, H, G, 1><<<gr, W_BT, 0, st>>>(m, w1t, in, B, L.P, L.bt_red, part, w.x2 + (size_t)s * B * W_HP, counters);
+            ++launches;
+        }
         WideIn<T> il{};
         il.base = w.lam; il.ks = w.kl; il.hs = w.h; il.ncoef = ncoef;
         for (int j = 0; j < ncoef; ++j) il.coef[j] = coef[j];
         il.xstore = w.yb2 + (size_t)s * nB; il.mask = mask;
         wide_l2_reverse<T, H, G>(h, m, p, w.x2 + (size_t)s * B * W_HP, il, B, L, part, w.yb1 + (size_t)s * B * W_HP, counters);
         wide_l1_vjp_kernel<T, H, G><<<gp, W_BT, 0, st>>>(m, w1t, w.x1 + (size_t)s * nB, w.yb1 + (size_t)s * B * W_HP, w.kl + (size_t)s * nB, mask, B, L.bt_par);
-        launches += 3;
+        launches += 2;
     };
     WideGp<T> gpa{};
     gpa.x1 = w.x1; gpa.yb1 = w.yb1; gpa.x2 = w.x2; gpa.yb2 = w.yb2; gpa.g = g; gpa.cur = c.cur; gpa.h = w.h; gpa.mask = c.active;
@@ -1804,12 +1825,12 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     };
     wide_bwd_ctl_kernel<T><<<(unsigned)B, 128, 0, st>>>(c, w, n, B, -1);
     wide_bwd_init_kernel<T><<<ge, W_ET, 0, st>>>(c, w, n);
-    adj(0, 0, nullptr, c.active);
+    adj(0, 0, nullptr, c.active, true);
     wide_norm_kernel<T, 1><<<ge, W_ET, 0, st>>>(w.lam, w.kl, nullptr, n, w.abstol, w.reltol, c.active, w.part0, w.part1, npart, 0);
     gpass(1, w.part1);
     wide_bwd_ctl_kernel<T><<<(unsigned)B, 128, 0, st>>>(c, w, n, B, 0);
     const T one[1] = {T(1)};
-    adj(1, 1, one, c.active);
+    adj(1, 1, one, c.active, true);
     wide_norm_kernel<T, 2><<<ge, W_ET, 0, st>>>(w.lam, w.kl, w.kl + nB, n, w.abstol, w.reltol, c.active, w.part0, w.part1, npart, 0);
     gpass(2, w.part1);
     wide_bwd_ctl_kernel<T><<<(unsigned)B, 128, 0, st>>>(c, w, n, B, 1);
@@ -1820,11 +1841,12 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     bool capturing = false;
     auto attempt = [&]() -> int64_t {
         const int64_t l0 = launches;
-        adj(0, 0, nullptr, c.do_s0);                                   // only the ICs whose lambda jumped at a save time
+        l1_all_stages();
+        adj(0, 0, nullptr, c.do_s0, false);                            // only the ICs whose lambda jumped at a save time
         for (int s = 1; s < 7; ++s) {
             T coef[7];
             for (int j = 0; j < s; ++j) coef[j] = (T)A_[s][j];
-            adj(s, s, coef, c.active);
+            adj(s, s, coef, c.active, false);
         }
         wide_err_kernel<T><<<ge, W_ET, 0, st>>>(w.lam, w.yb2 + (size_t)6 * nB, w.kl, n, B, w.h, w.abstol, w.reltol, c.active, w.part0, npart, 0);
         gpass(capturing ? 3 : 0, w.part0);
