@@ -60,14 +60,14 @@ struct kanode_handle {
     void* stage = nullptr; size_t stage_bytes = 0;   // pinned host staging block for the results of the host entry points
     // grow-only device workspace, keyed by purpose
     enum { W_U0, W_OUT, W_TARGET, W_STATS_F, W_STATS_B, W_SAVEAT, W_REC_T, W_REC, W_NSTEPS, W_RET, W_DG, W_FAC, W_G,
-           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_WPK32, W_WPK64, W_LAM, W_GEN, W_GEN2, W_LS, W_ATT, W_ORDER, W_WIDE_F, W_WIDE_B, W_W1T32, W_W1T64, W_W2IMG, W_W2TIMG, W_WIDE_R, W_COUNT };
+           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_WPK32, W_WPK64, W_LAM, W_GEN, W_GEN2, W_LS, W_ATT, W_ORDER, W_WIDE_F, W_WIDE_B, W_W1T32, W_W1T64, W_W2IMG, W_W2TIMG, W_W1IMG, W_WIDE_R, W_COUNT };
     DevBuf ws[W_COUNT];
     kanode::GenericModel gm{};               // layer table for the generic kernels
     // wide (batched lockstep) engine: attempts the last forward-only / dense-forward / backward call needed, counter state
     int wide = 1;                            // 0: force the block-per-trajectory kernels (KANODE_WIDE=0)
     int wide_iters[3] = {0, 0, 0};
     uint64_t wide_w1t_version[2] = {~0ull, ~0ull};
-    uint64_t wide_w2img_version = ~0ull, wide_w2timg_version = ~0ull;
+    uint64_t wide_w2img_version = ~0ull, wide_w2timg_version = ~0ull, wide_w1img_version = ~0ull;
     int wide_tc = 1;                         // fp32 layer-2 forward contraction on tcgen05 (KANODE_WIDE_TC=0: CUDA cores)
     // one lockstep step attempt captured as a CUDA graph (forward-only, dense forward, backward) x (fp32, fp64): replayed
     // per attempt while the kernel arguments (workspace pointers, sizes, tolerances) stay the same

@@ -540,6 +540,164 @@ __global__ void __launch_bounds__(W_BT, 3) wide_l2_vjp_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// layer 1 forward on tcgen05 (fp32, n % 64 == 0) for the (stage, IC) pairs of a backward attempt — the fused
+// basis-expansion + contraction kernel:  hidden[v][o] = sum_i sum_q c_q(y_v[i]) * w1[i][q][o]
+//   M = 128 rows v (one thread each), N = 16 (H padded), K = 8 units x KU features per pass (KU = G+1 padded to a multiple of 4).
+// Every thread forms sol(t_s) of its row for the pass's 8 units (vector loads from the dense record), expands the RBF / SiLU
+// features in registers and writes them — TF32 hi/lo split — straight into the K-major UMMA operand layout in shared memory
+// (one conflict-free STS.128 per 4 features); the features never exist in HBM.  The weight operand of the pass (12 KB) arrives
+// by TMA from an image in the same layout.  D accumulates in TMEM over the block's passes; partial sums over the unit blocks
+// go to wide_sum_partials_kernel.  Two blocks per SM overlap one block's feature generation with the other's MMAs.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TC1_UC = 8, TC1_N = 16;
+template <int H, int G>
+__global__ void __launch_bounds__(256) wide_w1_image_kernel(const __grid_constant__ WideModel m, const float* __restrict__ p, float* __restrict__ img) {
+    constexpr int NQ = G + 1, KU = (NQ + 3) / 4 * 4, KC = TC1_UC * KU / 4;
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int nblk = m.n / TC1_UC;
+    if (idx >= (int64_t)nblk * KC * TC1_N * 4) return;
+    const int kk = (int)(idx & 3), o = (int)((idx >> 2) % TC1_N), kc = (int)((idx / (4 * TC1_N)) % KC), ub = (int)(idx / ((int64_t)4 * TC1_N * KC));
+    const int k = kc * 4 + kk, u = k / KU, q = k - u * KU;
+    const int64_t i = (int64_t)ub * TC1_UC + u;
+    float v = 0.f;
+    if (o < H && q < NQ) v = q < G ? p[m.offC1 + (i * G + q) * H + o] : p[m.offW1 + i * H + o];
+    const float hi = w_tf32_hi(v);
+    float* base = img + (int64_t)ub * 2 * KC * TC1_N * 4;
+    base[((int64_t)kc * TC1_N + o) * 4 + kk] = hi;
+    base[(int64_t)KC * TC1_N * 4 + ((int64_t)kc * TC1_N + o) * 4 + kk] = v - hi;
+}
+
+template <int H, int G>
+__global__ void __launch_bounds__(128, 2) wide_l1_fwd_tc_kernel(const __grid_constant__ WideModel m, const float* __restrict__ img, const WideIn<float> in,
+                                                                int64_t BV, int P, float* part) {
+    constexpr int NQ = G + 1, KU = (NQ + 3) / 4 * 4, K = TC1_UC * KU, KC = K / 4, KSTEPS = KC / 2, CU = KU / 4;
+    constexpr uint32_t A_BYTES = KC * TC_M * 16, B_BYTES = KC * TC1_N * 16;
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    float* a_hi = reinterpret_cast<float*>(tc_smem);
+    float* a_lo = reinterpret_cast<float*>(tc_smem + A_BYTES);
+    float* b_hi = reinterpret_cast<float*>(tc_smem + 2 * A_BYTES);
+    uint64_t* bar_b = reinterpret_cast<uint64_t*>(tc_smem + 2 * A_BYTES + 2 * B_BYTES);
+    uint64_t* bar_mma = bar_b + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_b + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n = m.n;
+    const int64_t v = (int64_t)blockIdx.y * TC_M + tid;                      // this thread's (stage, IC) pair
+    const bool on = v < BV && (!in.mask || in.mask[v]);
+    const int nblk = n / TC1_UC;
+    const int npass = min(P, nblk - (int)blockIdx.x * P);
+    if (tid == 0) {
+        w_mbar_init(bar_b, 1); w_mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(w_smem_u32(tmem_slot)), "n"(32) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // row constants: dense-record row and interpolation weights of sol(t_s)
+    float bw[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, hd = 0.f;
+    const float* rrow = in.rec;
+    if (on) {
+        interp_weights(in.th[v], bw);
+        hd = in.hd[v];
+        const int64_t brow = in.brec > 0 ? v % in.brec : v;
+        rrow = in.rec + (brow * in.cap + in.ridx[v]) * 8 * (int64_t)n;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const float inv_h = m.inv_h1;
+    for (int pass = 0; pass < npass; ++pass) {
+        const int ub = blockIdx.x * P + pass, i0 = ub * TC1_UC;
+        if (pass > 0) { w_mbar_wait(bar_mma, (pass - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+        if (tid == 0) {
+            w_mbar_expect_tx(bar_b, 2 * B_BYTES);
+            w_tma_load_1d(b_hi, img + (int64_t)ub * 2 * KC * TC1_N * 4, 2 * B_BYTES, bar_b);
+        }
+        if (on) {
+            float4 r0[8], r1[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                r0[j] = *reinterpret_cast<const float4*>(rrow + (int64_t)j * n + i0);
+                r1[j] = *reinterpret_cast<const float4*>(rrow + (int64_t)j * n + i0 + 4);
+            }
+            float x[8];
+            {
+                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    a0.x += bw[j] * r0[1 + j].x; a0.y += bw[j] * r0[1 + j].y; a0.z += bw[j] * r0[1 + j].z; a0.w += bw[j] * r0[1 + j].w;
+                    a1.x += bw[j] * r1[1 + j].x; a1.y += bw[j] * r1[1 + j].y; a1.z += bw[j] * r1[1 + j].z; a1.w += bw[j] * r1[1 + j].w;
+                }
+                x[0] = r0[0].x + hd * a0.x; x[1] = r0[0].y + hd * a0.y; x[2] = r0[0].z + hd * a0.z; x[3] = r0[0].w + hd * a0.w;
+                x[4] = r1[0].x + hd * a1.x; x[5] = r1[0].y + hd * a1.y; x[6] = r1[0].z + hd * a1.z; x[7] = r1[0].w + hd * a1.w;
+            }
+            if (in.xstore) {
+                *reinterpret_cast<float4*>(in.xstore + v * n + i0) = make_float4(x[0], x[1], x[2], x[3]);
+                *reinterpret_cast<float4*>(in.xstore + v * n + i0 + 4) = make_float4(x[4], x[5], x[6], x[7]);
+            }
+#pragma unroll
+            for (int u = 0; u < TC1_UC; ++u) {
+                float c[KU];
+                {
+                    float cc[NQ];
+                    w_features<float, G>(m.norm1, inv_h, m.grid1, x[u], cc);
+#pragma unroll
+                    for (int q = 0; q < KU; ++q) c[q] = q < NQ ? cc[q] : 0.f;
+                }
+#pragma unroll
+                for (int cq = 0; cq < CU; ++cq) {
+                    const float4 f = make_float4(c[4 * cq], c[4 * cq + 1], c[4 * cq + 2], c[4 * cq + 3]);
+                    const float4 hi = make_float4(w_tf32_hi(f.x), w_tf32_hi(f.y), w_tf32_hi(f.z), w_tf32_hi(f.w));
+                    const float4 lo = make_float4(f.x - hi.x, f.y - hi.y, f.z - hi.z, f.w - hi.w);
+                    const int kc = u * CU + cq;
+                    *reinterpret_cast<float4*>(a_hi + (kc * TC_M + tid) * 4) = hi;
+                    *reinterpret_cast<float4*>(a_lo + (kc * TC_M + tid) * 4) = lo;
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (warp == 0) {
+            w_mbar_wait(bar_b, pass & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC1_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+                const uint32_t ah = w_smem_u32(a_hi), al = w_smem_u32(a_lo), bh = w_smem_u32(b_hi), blo = bh + B_BYTES;
+#pragma unroll 1
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                    const uint32_t ao = ks * 2 * TC_M * 16, bo = ks * 2 * TC1_N * 16;
+                    const uint64_t dah = w_umma_desc(ah + ao, TC_M * 16, 128), dal = w_umma_desc(al + ao, TC_M * 16, 128);
+                    const uint64_t dbh = w_umma_desc(bh + bo, TC1_N * 16, 128), dbl = w_umma_desc(blo + bo, TC1_N * 16, 128);
+                    w_umma_tf32(tmem, dal, dbh, idesc, (pass > 0 || ks > 0) ? 1u : 0u);
+                    w_umma_tf32(tmem, dah, dbl, idesc, 1u);
+                    w_umma_tf32(tmem, dah, dbh, idesc, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(w_smem_u32(bar_mma)) : "memory");
+            }
+            __syncwarp();
+        }
+    }
+    w_mbar_wait(bar_mma, (npass - 1) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t d[TC1_N];
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]), "=r"(d[10]),
+                   "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (v < BV) {
+#pragma unroll
+        for (int o = 0; o < H; ++o) part[((int64_t)blockIdx.x * BV + v) * H + o] = __uint_as_float(d[o]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(32) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // layer 2 reverse on tcgen05 (fp32, n % 128 == 0):  S[r][b] = sum_o W2t[r][o] * lam[b][o]   (M = 128 rows r = (j,q), 110 used;
 // N = 32 ICs; K = o, 128 per pass, accumulated in TMEM over the P passes of the block), then hbar[b][j] = sum_q S[(j,q)][b] * d2[b][(j,q)].
 // A (weights) arrives by TMA from an image in the UMMA layout; B (lambda at the stage = lam + h*sum a*kl, also recorded as
@@ -1547,8 +1705,23 @@ template <int H, int G> int wide_w2t_image(kanode_handle* h, const WideModel& m,
     return 0;
 }
 
+template <int H, int G> int wide_w1_image(kanode_handle* h, const WideModel& m, const float* p, const float** out) {
+    constexpr int KU = (G + 1 + 3) / 4 * 4, KC = TC1_UC * KU / 4;
+    float* d = nullptr;
+    const size_t cnt = (size_t)(m.n / TC1_UC) * 2 * KC * TC1_N * 4;
+    ENSURE(h, W_W1IMG, sizeof(float) * cnt, d);
+    if (h->wide_w1img_version != h->params_version) {
+        wide_w1_image_kernel<H, G><<<(unsigned)((cnt / 2 + 255) / 256), 256, 0, h->stream>>>(m, p, d);
+        ++h->launches;
+        CK(h, cudaGetLastError());
+        h->wide_w1img_version = h->params_version;
+    }
+    *out = d;
+    return 0;
+}
+
 // partial-sum rows the reduce kernels may need: CUDA-core kernels <= W_MAXCH, the tensor-core reverse kernel n / 64
-inline size_t wide_part_rows(int n, const WideLaunch& L) { return (size_t)std::max(L.nchunk, n / TC_KB + 1); }
+inline size_t wide_part_rows(int n, const WideLaunch& L) { return (size_t)std::max(std::max(L.nchunk, n / TC_KB + 1), 600); }
 
 // hbar = layer-2 reverse of lambda_s: tcgen05 kernel for fp32 when n is a multiple of 128, CUDA cores otherwise
 template <class T, int H, int G>
@@ -1779,10 +1952,35 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     const WideLaunch L7 = wide_launch(n, 7 * B, GB);       // all 7 stages of an attempt as (stage, IC) pairs
     // layer-1 forward of EVERY stage of the attempt in one launch: sol(t_s) does not depend on lambda, and the stage times are
     // known when the attempt opens, so the 7 x B (stage, IC) pairs share each unit's weights in one pass
+    const float* w1img = nullptr;
+    bool l1_tc = false;
+    if constexpr (sizeof(T) == 4) {
+        if (h->wide_tc && n % 64 == 0) {
+            constexpr int KU = (G + 1 + 3) / 4 * 4, KC = TC1_UC * KU / 4;
+            constexpr size_t smem1 = 2 * (size_t)KC * TC_M * 16 + 2 * (size_t)KC * TC1_N * 16 + 64;
+            if (int rc = wide_w1_image<H, G>(h, m, p, &w1img)) return rc;
+            static bool attr_set = false;
+            if (!attr_set) { CK(h, cudaFuncSetAttribute(wide_l1_fwd_tc_kernel<H, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1)); attr_set = true; }
+            l1_tc = true;
+        }
+    }
     auto l1_all_stages = [&]() {
         WideIn<T> in{};
         in.rec = w.rec; in.cap = cap; in.ridx = c.ridx; in.th = w.th; in.hd = w.hd; in.brec = (int)B;
         in.xstore = w.x1; in.mask = c.mask7;
+        if constexpr (sizeof(T) == 4) {
+            if (l1_tc) {
+                constexpr int KU = (G + 1 + 3) / 4 * 4, KC = TC1_UC * KU / 4;
+                constexpr size_t smem1 = 2 * (size_t)KC * TC_M * 16 + 2 * (size_t)KC * TC1_N * 16 + 64;
+                const int nblk = n / TC1_UC, nmt = (int)((7 * B + TC_M - 1) / TC_M);
+                int P1 = (int)(((int64_t)nblk * nmt + 591) / 592); P1 = P1 < 1 ? 1 : P1;
+                const int nch = (nblk + P1 - 1) / P1;                       // <= 592 partial rows
+                wide_l1_fwd_tc_kernel<H, G><<<dim3(nch, nmt), 128, smem1, st>>>(m, w1img, in, 7 * B, P1, part);
+                wide_sum_partials_kernel<float, H><<<(unsigned)((7 * B * H + 3) / 4), 128, 0, st>>>(part, nch, 7 * B, w.x2, c.mask7);
+                launches += 2;
+                return;
+            }
+        }
         wide_l1_fwd_kernel<T, H, G, 1><<<dim3(L7.nchunk, L7.nbt_red), W_BT, 0, st>>>(m, w1t, in, 7 * B, L7.P, L7.bt_red, part, w.x2, counters);
         ++launches;
     };
@@ -1861,6 +2059,7 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
         std::vector<char> sig;
         sig_add(sig, m); sig_add(sig, w); sig_add(sig, c); sig_add(sig, L); sig_add(sig, B); sig_add(sig, p); sig_add(sig, w1t); sig_add(sig, g);
         sig_add(sig, part); sig_add(sig, counters); sig_add(sig, npart); sig_add(sig, h->wide_tc); sig_add(sig, h->ws[kanode_handle::W_W2TIMG].p);
+        sig_add(sig, w1img); sig_add(sig, l1_tc);
         const int64_t l0 = launches;
         capturing = true;
         const int rc = wide_attempt_graph(h, gslot, sig, attempt, &gexec);
