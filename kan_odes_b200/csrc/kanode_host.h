@@ -68,7 +68,7 @@ struct kanode_handle {
     int wide_iters[3] = {0, 0, 0};
     uint64_t wide_w1t_version[2] = {~0ull, ~0ull};
     uint64_t wide_w2img_version = ~0ull, wide_w2timg_version = ~0ull, wide_w1img_version = ~0ull;
-    int wide_tc = 1;                         // fp32 layer-2 forward contraction on tcgen05 (KANODE_WIDE_TC=0: CUDA cores)
+    int wide_tc = 1;                         // fp32: 1 = layer-2 contractions on tcgen05, 2 = also the batched layer-1 forward, 0 = CUDA cores (KANODE_WIDE_TC)
     // one lockstep step attempt captured as a CUDA graph (forward-only, dense forward, backward) x (fp32, fp64): replayed
     // per attempt while the kernel arguments (workspace pointers, sizes, tolerances) stay the same
     struct WideGraph { cudaGraphExec_t exec = nullptr; std::vector<char> sig; int nodes = 0; };

@@ -606,31 +606,38 @@ __global__ void __launch_bounds__(128, 2) wide_l1_fwd_tc_kernel(const __grid_con
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     const float inv_h = m.inv_h1;
+    // dense-record values of the row for one pass: 8 arrays x 8 units; the loads of pass p+1 are issued before the features
+    // of pass p are expanded, so their latency hides behind the MUFU work, the barrier and the MMAs
+    float4 r0[8], r1[8];
+    auto load_raw = [&](int pass) {
+        const int i0 = (blockIdx.x * P + pass) * TC1_UC;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            r0[j] = *reinterpret_cast<const float4*>(rrow + (int64_t)j * n + i0);
+            r1[j] = *reinterpret_cast<const float4*>(rrow + (int64_t)j * n + i0 + 4);
+        }
+    };
+    if (on) load_raw(0);
     for (int pass = 0; pass < npass; ++pass) {
         const int ub = blockIdx.x * P + pass, i0 = ub * TC1_UC;
+        float x[8];
+        if (on) {
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                a0.x += bw[j] * r0[1 + j].x; a0.y += bw[j] * r0[1 + j].y; a0.z += bw[j] * r0[1 + j].z; a0.w += bw[j] * r0[1 + j].w;
+                a1.x += bw[j] * r1[1 + j].x; a1.y += bw[j] * r1[1 + j].y; a1.z += bw[j] * r1[1 + j].z; a1.w += bw[j] * r1[1 + j].w;
+            }
+            x[0] = r0[0].x + hd * a0.x; x[1] = r0[0].y + hd * a0.y; x[2] = r0[0].z + hd * a0.z; x[3] = r0[0].w + hd * a0.w;
+            x[4] = r1[0].x + hd * a1.x; x[5] = r1[0].y + hd * a1.y; x[6] = r1[0].z + hd * a1.z; x[7] = r1[0].w + hd * a1.w;
+            if (pass + 1 < npass) load_raw(pass + 1);
+        }
         if (pass > 0) { w_mbar_wait(bar_mma, (pass - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
         if (tid == 0) {
             w_mbar_expect_tx(bar_b, 2 * B_BYTES);
             w_tma_load_1d(b_hi, img + (int64_t)ub * 2 * KC * TC1_N * 4, 2 * B_BYTES, bar_b);
         }
         if (on) {
-            float4 r0[8], r1[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                r0[j] = *reinterpret_cast<const float4*>(rrow + (int64_t)j * n + i0);
-                r1[j] = *reinterpret_cast<const float4*>(rrow + (int64_t)j * n + i0 + 4);
-            }
-            float x[8];
-            {
-                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-#pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    a0.x += bw[j] * r0[1 + j].x; a0.y += bw[j] * r0[1 + j].y; a0.z += bw[j] * r0[1 + j].z; a0.w += bw[j] * r0[1 + j].w;
-                    a1.x += bw[j] * r1[1 + j].x; a1.y += bw[j] * r1[1 + j].y; a1.z += bw[j] * r1[1 + j].z; a1.w += bw[j] * r1[1 + j].w;
-                }
-                x[0] = r0[0].x + hd * a0.x; x[1] = r0[0].y + hd * a0.y; x[2] = r0[0].z + hd * a0.z; x[3] = r0[0].w + hd * a0.w;
-                x[4] = r1[0].x + hd * a1.x; x[5] = r1[0].y + hd * a1.y; x[6] = r1[0].z + hd * a1.z; x[7] = r1[0].w + hd * a1.w;
-            }
             if (in.xstore) {
                 *reinterpret_cast<float4*>(in.xstore + v * n + i0) = make_float4(x[0], x[1], x[2], x[3]);
                 *reinterpret_cast<float4*>(in.xstore + v * n + i0 + 4) = make_float4(x[4], x[5], x[6], x[7]);
@@ -1954,8 +1961,11 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     // known when the attempt opens, so the 7 x B (stage, IC) pairs share each unit's weights in one pass
     const float* w1img = nullptr;
     bool l1_tc = false;
+    // opt-in (KANODE_WIDE_TC=2): measured on B200 it only ties the CUDA-core kernel (Schrodinger x 32: 181 vs ~175 us per attempt;
+    // slower on Allen-Cahn-4096): with N = 16 the 36 small MMAs of a pass keep the tensor pipe 5 % busy and the block waits on
+    // their completion before it may overwrite the feature operand (profiles/r01w_tc1_ncu_summary.md)
     if constexpr (sizeof(T) == 4) {
-        if (h->wide_tc && n % 64 == 0) {
+        if (h->wide_tc >= 2 && n % 64 == 0) {
             constexpr int KU = (G + 1 + 3) / 4 * 4, KC = TC1_UC * KU / 4;
             constexpr size_t smem1 = 2 * (size_t)KC * TC_M * 16 + 2 * (size_t)KC * TC1_N * 16 + 64;
             if (int rc = wide_w1_image<H, G>(h, m, p, &w1img)) return rc;

@@ -122,7 +122,7 @@ def test_wide_tensor_core_kernels_match_cuda_core_fp32(n, G, B, monkeypatch):
     chain, p, u0, tspan, saveat, tg = _problem(n, G, B, seed=n + 1)
     orc = Oracle(chain.desc(), np.float64)
     res = {}
-    for tc in (1, 0):
+    for tc in (2, 1, 0):                                                   # 2: also the fused basis-expansion + contraction kernel
         monkeypatch.setenv("KANODE_WIDE", "1"); monkeypatch.setenv("KANODE_WIDE_TC", str(tc))
         ode = K.KanOde(chain, dtype=np.float32); ode.set_params(p)
         rhs = ode.rhs(u0)
@@ -130,18 +130,23 @@ def test_wide_tensor_core_kernels_match_cuda_core_fp32(n, G, B, monkeypatch):
         ode.close()
         res[tc] = (rhs, r)
     ref_rhs = orc.rhs(p, u0)
-    for tc in (1, 0):
+    for tc in (2, 1, 0):
         assert _relmax(res[tc][0], ref_rhs) < 2e-5, tc                      # RHS arithmetic within the fp32 parity budget
     assert _relmax(res[1][0], res[0][0]) < 5e-6
-    a, b = res[1][1], res[0][1]
+    for a, b in ((res[1][1], res[0][1]), (res[2][1], res[0][1])):
+        _compare_tc(a, b)
+    ref = orc.loss_grad(p, u0, tspan, saveat, tg)
+    a = res[2][1]
+    assert _relmax(a["grad"], ref["grad"]) < 2e-2 and abs(a["loss"] - ref["loss"]) < 5e-3 * abs(ref["loss"])
+
+
+def _compare_tc(a, b):
     assert (a["fwd_stats"].retcode == 0).all() and (a["bwd_stats"].retcode == 0).all()
     same = (a["fwd_stats"].naccept == b["fwd_stats"].naccept).all() and (a["bwd_stats"].naccept == b["bwd_stats"].naccept).all() \
         and (a["bwd_stats"].nreject == b["bwd_stats"].nreject).all()
     tol = 2e-4 if same else 2e-2                                            # different fp32 step sequences: solver accuracy only
     assert abs(a["loss"] - b["loss"]) < tol * abs(b["loss"])
     assert _relmax(a["grad"], b["grad"]) < tol, (same, _relmax(a["grad"], b["grad"]))
-    ref = orc.loss_grad(p, u0, tspan, saveat, tg)
-    assert _relmax(a["grad"], ref["grad"]) < 2e-2 and abs(a["loss"] - ref["loss"]) < 5e-3 * abs(ref["loss"])
 
 
 @pytest.mark.parametrize("n,G,B", [(300, 5, 7), (41, 10, 3)])
