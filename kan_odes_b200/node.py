@@ -143,22 +143,31 @@ class KanOde:
         abi.check(self.lib, self.h, rc, "kanode_solve")
         return ODESolution(sa, out, Stats.from_raw(stats))
 
-    def loss_grad(self, u0, tspan, saveat, target, abstol=1e-6, reltol=1e-3):
+    def loss_grad(self, u0, tspan, saveat, target, abstol=1e-6, reltol=1e-3, want_du0=True, want_stats=True):
+        """loss = mean(abs2, target - predict) and d loss / d p (what `Zygote.gradient(loss, p)[1]` returns in the reference,
+        LV_driver_KANODE.jl:197-203,284).  `want_du0` / `want_stats` add d loss / d u0 and the per-trajectory solver
+        statistics to the result (two more device-to-host copies of batch-sized arrays)."""
         u0 = self._arr(u0).reshape(-1, self.n)
         B = u0.shape[0]
         sa = np.ascontiguousarray(saveat, dtype=np.float64).reshape(-1)
         target = self._arr(target).reshape(B, sa.size, self.n)
         loss = self._real(0)
-        grad = np.empty(self.np_, self.dtype); du0 = np.empty_like(u0)
-        fst = (abi.Stats * B)(); bst = (abi.Stats * B)()
+        grad = np.empty(self.np_, self.dtype)
+        du0 = np.empty_like(u0) if want_du0 else None
+        fst = (abi.Stats * B)() if want_stats else None
+        bst = (abi.Stats * B)() if want_stats else None
         f = self._fn("kanode_loss_grad")
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_void_p,
                       self._real, self._real, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         rc = f(self.h, _ptr(u0), B, float(tspan[0]), float(tspan[1]), _ptr(sa), sa.size, _ptr(target), abstol, reltol,
                C.byref(loss), _ptr(grad), _ptr(du0), fst, bst)
         abi.check(self.lib, self.h, rc, "kanode_loss_grad")
-        return dict(loss=float(loss.value), grad=grad, du0=du0, fwd_stats=Stats.from_raw(fst),
-                    bwd_stats=Stats.from_raw(bst))
+        out = dict(loss=float(loss.value), grad=grad)
+        if want_du0:
+            out["du0"] = du0
+        if want_stats:
+            out["fwd_stats"] = Stats.from_raw(fst); out["bwd_stats"] = Stats.from_raw(bst)
+        return out
 
     def launch_count(self) -> int:
         return int(self.lib.kanode_launch_count(self.h))

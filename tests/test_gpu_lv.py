@@ -252,3 +252,16 @@ def test_scheduled_backward_with_long_trajectory_warps_matches_plain(lv_saveat):
     ode32 = K.KanOde(chain, dtype=np.float32); ode32.set_params(p)
     a = ode32.loss_grad(u0, TSPAN, lv_saveat, tg); b = ode32.loss_grad(u0, TSPAN, lv_saveat, tg)
     assert _relmax(b["grad"], a["grad"].astype(np.float64)) < 1e-4
+
+
+def test_lean_loss_grad_call_matches_full(lv_saveat):
+    """`want_du0=False, want_stats=False` (the Zygote.gradient(loss, p) shape of the call) returns the same loss / gradient."""
+    chain = lv_chain()
+    p = glorot_params(chain, seed=0)
+    u0 = np.random.default_rng(5).uniform(0.5, 2.0, (300, 2))
+    tg = lv_targets(u0[:1], lv_saveat).repeat(300, axis=0)
+    ode = K.KanOde(chain, dtype=np.float32); ode.set_params(p)
+    full = ode.loss_grad(u0, TSPAN, lv_saveat, tg)
+    lean = ode.loss_grad(u0, TSPAN, lv_saveat, tg, want_du0=False, want_stats=False)
+    ode.close()
+    assert set(lean) == {"loss", "grad"} and lean["loss"] == full["loss"] and np.array_equal(lean["grad"], full["grad"])
