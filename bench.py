@@ -266,6 +266,16 @@ def run_ours(args):
     h2d = h_u0.nbytes + h_tg.nbytes + SAVEAT.nbytes + npar * esz
     d2h = 8 + npar * esz + B * 16                                  # loss sum, gradient, forward retcodes (dense-record overflow check)
 
+    # per-rank device times and SM clocks: the job's step time is the max over ranks, so a slower GPU (clock / power) shows here
+    per_rank = None
+    if world > 1:
+        mine = sampler.result()
+        loc = torch.tensor([float(k_ms[:, 0].mean()), float(k_ms[:, 1].mean()), float(k_ms[:, 2].mean()),
+                            float(mine["sm_mhz"] or 0.0)], dtype=torch.float64, device=dev)
+        allv = [torch.zeros_like(loc) for _ in range(world)]
+        dist.all_gather(allv, loc)
+        per_rank = {"forward_ms": [round(float(v[0]), 4) for v in allv], "backward_ms": [round(float(v[1]), 4) for v in allv],
+                    "sm_mhz": [float(v[3]) for v in allv]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -315,6 +325,8 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if per_rank is not None:
+        line["per_rank"] = per_rank
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(chain, p, u0, tg)
     emit(line)
