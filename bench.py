@@ -226,13 +226,23 @@ def run_ours(args):
             evs[i][0].record(stream)
             step(False)
             evs[i][1].record(stream)
-            lib.kanode_last_timing(ode.h, ms3)                     # per-kernel CUDA-event times of this step
-            k_ms[i] = [ms3[0], ms3[1], ms3[2]]
+            if world == 1:
+                lib.kanode_last_timing(ode.h, ms3)                 # per-kernel CUDA-event times of this step (blocks until it finished)
+                k_ms[i] = [ms3[0], ms3[1], ms3[2]]
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         sampler.stop_flag = True; sampler.join()
         launches = ode.launch_count() - launches0
+        if world > 1:
+            # N > 1: the timed loop above never blocks the host (8 ranks share the box's cores; a per-step read-back exposes the
+            # launch latency of every rank to the all-reduce).  Per-kernel times come from extra, untimed steps.
+            for i in range(args.steps):
+                step(False)
+                lib.kanode_last_timing(ode.h, ms3)
+                k_ms[i] = [ms3[0], ms3[1], ms3[2]]
+            torch.cuda.synchronize()
+            dist.barrier()
         total_ms = sum(a.elapsed_time(b) for a, b in evs)
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         if world > 1:
