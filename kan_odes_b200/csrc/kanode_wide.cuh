@@ -567,25 +567,25 @@ __global__ void __launch_bounds__(256) wide_w1_image_kernel(const __grid_constan
     base[(int64_t)KC * TC1_N * 4 + ((int64_t)kc * TC1_N + o) * 4 + kk] = v - hi;
 }
 
+// 256 threads: thread = (row v, half of the pass's 8 units).  Two operand buffers: the features of pass p+1 are generated while
+// the MMAs of pass p run (tcgen05.commit -> one mbarrier per buffer guards the overwrite two passes later).
 template <int H, int G>
-__global__ void __launch_bounds__(128, 2) wide_l1_fwd_tc_kernel(const __grid_constant__ WideModel m, const float* __restrict__ img, const WideIn<float> in,
+__global__ void __launch_bounds__(256, 1) wide_l1_fwd_tc_kernel(const __grid_constant__ WideModel m, const float* __restrict__ img, const WideIn<float> in,
                                                                 int64_t BV, int P, float* part) {
-    constexpr int NQ = G + 1, KU = (NQ + 3) / 4 * 4, K = TC1_UC * KU, KC = K / 4, KSTEPS = KC / 2, CU = KU / 4;
-    constexpr uint32_t A_BYTES = KC * TC_M * 16, B_BYTES = KC * TC1_N * 16;
+    constexpr int NQ = G + 1, KU = (NQ + 3) / 4 * 4, K = TC1_UC * KU, KC = K / 4, KSTEPS = KC / 2, CU = KU / 4, UH = TC1_UC / 2;
+    constexpr uint32_t A_BYTES = KC * TC_M * 16, B_BYTES = KC * TC1_N * 16, STAGE = 2 * A_BYTES + 2 * B_BYTES;
     extern __shared__ __align__(128) unsigned char tc_smem[];
-    float* a_hi = reinterpret_cast<float*>(tc_smem);
-    float* a_lo = reinterpret_cast<float*>(tc_smem + A_BYTES);
-    float* b_hi = reinterpret_cast<float*>(tc_smem + 2 * A_BYTES);
-    uint64_t* bar_b = reinterpret_cast<uint64_t*>(tc_smem + 2 * A_BYTES + 2 * B_BYTES);
-    uint64_t* bar_mma = bar_b + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_b + 2);
+    uint64_t* bar_b = reinterpret_cast<uint64_t*>(tc_smem + 2 * STAGE);      // [2]
+    uint64_t* bar_mma = bar_b + 2;                                          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_b + 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n = m.n;
-    const int64_t v = (int64_t)blockIdx.y * TC_M + tid;                      // this thread's (stage, IC) pair
+    const int row = tid & (TC_M - 1), uh = tid >> 7;                        // row of the tile, which 4 of the 8 units
+    const int64_t v = (int64_t)blockIdx.y * TC_M + row;                      // this thread's (stage, IC) pair
     const bool on = v < BV && (!in.mask || in.mask[v]);
     const int nblk = n / TC1_UC;
     const int npass = min(P, nblk - (int)blockIdx.x * P);
     if (tid == 0) {
-        w_mbar_init(bar_b, 1); w_mbar_init(bar_mma, 1);
+        w_mbar_init(bar_b, 1); w_mbar_init(bar_b + 1, 1); w_mbar_init(bar_mma, 1); w_mbar_init(bar_mma + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -599,51 +599,42 @@ __global__ void __launch_bounds__(128, 2) wide_l1_fwd_tc_kernel(const __grid_con
         interp_weights(in.th[v], bw);
         hd = in.hd[v];
         const int64_t brow = in.brec > 0 ? v % in.brec : v;
-        rrow = in.rec + (brow * in.cap + in.ridx[v]) * 8 * (int64_t)n;
+        rrow = in.rec + (brow * in.cap + in.ridx[v]) * 8 * (int64_t)n + uh * UH;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     const float inv_h = m.inv_h1;
-    // dense-record values of the row for one pass: 8 arrays x 8 units; the loads of pass p+1 are issued before the features
-    // of pass p are expanded, so their latency hides behind the MUFU work, the barrier and the MMAs
-    float4 r0[8], r1[8];
+    float4 r0[8];                                                            // dense-record values of this thread's 4 units (8 arrays)
     auto load_raw = [&](int pass) {
         const int i0 = (blockIdx.x * P + pass) * TC1_UC;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            r0[j] = *reinterpret_cast<const float4*>(rrow + (int64_t)j * n + i0);
-            r1[j] = *reinterpret_cast<const float4*>(rrow + (int64_t)j * n + i0 + 4);
-        }
+        for (int j = 0; j < 8; ++j) r0[j] = *reinterpret_cast<const float4*>(rrow + (int64_t)j * n + i0);
     };
     if (on) load_raw(0);
     for (int pass = 0; pass < npass; ++pass) {
-        const int ub = blockIdx.x * P + pass, i0 = ub * TC1_UC;
-        float x[8];
+        const int sb = pass & 1, ub = blockIdx.x * P + pass, i0 = ub * TC1_UC + uh * UH;
+        float* a_hi = reinterpret_cast<float*>(tc_smem + sb * STAGE);
+        float* a_lo = reinterpret_cast<float*>(tc_smem + sb * STAGE + A_BYTES);
+        float* b_hi = reinterpret_cast<float*>(tc_smem + sb * STAGE + 2 * A_BYTES);
+        float x[UH];
         if (on) {
-            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < 7; ++j) {
-                a0.x += bw[j] * r0[1 + j].x; a0.y += bw[j] * r0[1 + j].y; a0.z += bw[j] * r0[1 + j].z; a0.w += bw[j] * r0[1 + j].w;
-                a1.x += bw[j] * r1[1 + j].x; a1.y += bw[j] * r1[1 + j].y; a1.z += bw[j] * r1[1 + j].z; a1.w += bw[j] * r1[1 + j].w;
-            }
+            for (int j = 0; j < 7; ++j) { a0.x += bw[j] * r0[1 + j].x; a0.y += bw[j] * r0[1 + j].y; a0.z += bw[j] * r0[1 + j].z; a0.w += bw[j] * r0[1 + j].w; }
             x[0] = r0[0].x + hd * a0.x; x[1] = r0[0].y + hd * a0.y; x[2] = r0[0].z + hd * a0.z; x[3] = r0[0].w + hd * a0.w;
-            x[4] = r1[0].x + hd * a1.x; x[5] = r1[0].y + hd * a1.y; x[6] = r1[0].z + hd * a1.z; x[7] = r1[0].w + hd * a1.w;
-            if (pass + 1 < npass) load_raw(pass + 1);
+            if (pass + 1 < npass) load_raw(pass + 1);                        // in flight behind the feature expansion below
         }
-        if (pass > 0) { w_mbar_wait(bar_mma, (pass - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+        if (pass >= 2) { w_mbar_wait(bar_mma + sb, ((pass >> 1) - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
         if (tid == 0) {
-            w_mbar_expect_tx(bar_b, 2 * B_BYTES);
-            w_tma_load_1d(b_hi, img + (int64_t)ub * 2 * KC * TC1_N * 4, 2 * B_BYTES, bar_b);
+            w_mbar_expect_tx(bar_b + sb, 2 * B_BYTES);
+            w_tma_load_1d(b_hi, img + (int64_t)ub * 2 * KC * TC1_N * 4, 2 * B_BYTES, bar_b + sb);
         }
         if (on) {
-            if (in.xstore) {
-                *reinterpret_cast<float4*>(in.xstore + v * n + i0) = make_float4(x[0], x[1], x[2], x[3]);
-                *reinterpret_cast<float4*>(in.xstore + v * n + i0 + 4) = make_float4(x[4], x[5], x[6], x[7]);
-            }
+            if (in.xstore) *reinterpret_cast<float4*>(in.xstore + v * n + i0) = make_float4(x[0], x[1], x[2], x[3]);
 #pragma unroll
-            for (int u = 0; u < TC1_UC; ++u) {
+            for (int u = 0; u < UH; ++u) {
                 float c[KU];
                 {
                     float cc[NQ];
@@ -656,9 +647,9 @@ __global__ void __launch_bounds__(128, 2) wide_l1_fwd_tc_kernel(const __grid_con
                     const float4 f = make_float4(c[4 * cq], c[4 * cq + 1], c[4 * cq + 2], c[4 * cq + 3]);
                     const float4 hi = make_float4(w_tf32_hi(f.x), w_tf32_hi(f.y), w_tf32_hi(f.z), w_tf32_hi(f.w));
                     const float4 lo = make_float4(f.x - hi.x, f.y - hi.y, f.z - hi.z, f.w - hi.w);
-                    const int kc = u * CU + cq;
-                    *reinterpret_cast<float4*>(a_hi + (kc * TC_M + tid) * 4) = hi;
-                    *reinterpret_cast<float4*>(a_lo + (kc * TC_M + tid) * 4) = lo;
+                    const int kc = (uh * UH + u) * CU + cq;
+                    *reinterpret_cast<float4*>(a_hi + (kc * TC_M + row) * 4) = hi;
+                    *reinterpret_cast<float4*>(a_lo + (kc * TC_M + row) * 4) = lo;
                 }
             }
         }
@@ -667,7 +658,7 @@ __global__ void __launch_bounds__(128, 2) wide_l1_fwd_tc_kernel(const __grid_con
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (warp == 0) {
-            w_mbar_wait(bar_b, pass & 1);
+            w_mbar_wait(bar_b + sb, (pass >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC1_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
@@ -681,23 +672,25 @@ __global__ void __launch_bounds__(128, 2) wide_l1_fwd_tc_kernel(const __grid_con
                     w_umma_tf32(tmem, dah, dbl, idesc, 1u);
                     w_umma_tf32(tmem, dah, dbh, idesc, 1u);
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(w_smem_u32(bar_mma)) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(w_smem_u32(bar_mma + sb)) : "memory");
             }
             __syncwarp();
         }
     }
-    w_mbar_wait(bar_mma, (npass - 1) & 1);
+    w_mbar_wait(bar_mma + ((npass - 1) & 1), ((npass - 1) >> 1) & 1);       // the last commit covers every earlier MMA
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    uint32_t d[TC1_N];
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]), "=r"(d[10]),
-                   "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
-                 : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (v < BV) {
+    if (warp < 4) {
+        uint32_t d[TC1_N];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]), "=r"(d[10]),
+                       "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
+                     : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (v < BV) {
 #pragma unroll
-        for (int o = 0; o < H; ++o) part[((int64_t)blockIdx.x * BV + v) * H + o] = __uint_as_float(d[o]);
+            for (int o = 0; o < H; ++o) part[((int64_t)blockIdx.x * BV + v) * H + o] = __uint_as_float(d[o]);
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -861,7 +854,7 @@ __global__ void __launch_bounds__(128) wide_l2_vjp_tc_kernel(const __grid_consta
 // layer 1 reverse: dl[b][i] = -( dnorm * sum_g db_g/h * (w1[g][:] . hbar[b]) + dswish * (W1[i][:] . hbar[b]) )
 // ---------------------------------------------------------------------------------------------------------
 template <class T, int H, int G>
-__global__ void __launch_bounds__(W_BT, 3) wide_l1_vjp_kernel(const __grid_constant__ WideModel m, const T* __restrict__ w1t, const T* x1, const T* hbar,
+__global__ void __launch_bounds__(W_BT, 2) wide_l1_vjp_kernel(const __grid_constant__ WideModel m, const T* __restrict__ w1t, const T* x1, const T* hbar,
                                                            T* dl, const int* mask, int64_t B, int btile) {
     constexpr int NW = H * (G + 1), PF = 8;
     __shared__ T hb[W_PT][W_HP];
@@ -1967,7 +1960,7 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
     if constexpr (sizeof(T) == 4) {
         if (h->wide_tc >= 2 && n % 64 == 0) {
             constexpr int KU = (G + 1 + 3) / 4 * 4, KC = TC1_UC * KU / 4;
-            constexpr size_t smem1 = 2 * (size_t)KC * TC_M * 16 + 2 * (size_t)KC * TC1_N * 16 + 64;
+            constexpr size_t smem1 = 2 * (2 * (size_t)KC * TC_M * 16 + 2 * (size_t)KC * TC1_N * 16) + 64;
             if (int rc = wide_w1_image<H, G>(h, m, p, &w1img)) return rc;
             static bool attr_set = false;
             if (!attr_set) { CK(h, cudaFuncSetAttribute(wide_l1_fwd_tc_kernel<H, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1)); attr_set = true; }
@@ -1981,11 +1974,11 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
         if constexpr (sizeof(T) == 4) {
             if (l1_tc) {
                 constexpr int KU = (G + 1 + 3) / 4 * 4, KC = TC1_UC * KU / 4;
-                constexpr size_t smem1 = 2 * (size_t)KC * TC_M * 16 + 2 * (size_t)KC * TC1_N * 16 + 64;
+                constexpr size_t smem1 = 2 * (2 * (size_t)KC * TC_M * 16 + 2 * (size_t)KC * TC1_N * 16) + 64;
                 const int nblk = n / TC1_UC, nmt = (int)((7 * B + TC_M - 1) / TC_M);
-                int P1 = (int)(((int64_t)nblk * nmt + 591) / 592); P1 = P1 < 1 ? 1 : P1;
-                const int nch = (nblk + P1 - 1) / P1;                       // <= 592 partial rows
-                wide_l1_fwd_tc_kernel<H, G><<<dim3(nch, nmt), 128, smem1, st>>>(m, w1img, in, 7 * B, P1, part);
+                int P1 = (int)(((int64_t)nblk * nmt + 295) / 296); P1 = P1 < 2 ? 2 : P1;        // one block per SM, two waves
+                const int nch = (nblk + P1 - 1) / P1;                       // <= 296 partial rows
+                wide_l1_fwd_tc_kernel<H, G><<<dim3(nch, nmt), 256, smem1, st>>>(m, w1img, in, 7 * B, P1, part);
                 wide_sum_partials_kernel<float, H><<<(unsigned)((7 * B * H + 3) / 4), 128, 0, st>>>(part, nch, 7 * B, w.x2, c.mask7);
                 launches += 2;
                 return;
