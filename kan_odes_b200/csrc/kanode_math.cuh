@@ -162,6 +162,15 @@ __device__ __forceinline__ void kfma2(float& d0, float& d1, float a0, float a1, 
 }
 template <class T> __device__ __forceinline__ void kfma2(T& d0, T& d1, T a0, T a1, T b0, T b1) { d0 += a0 * b0; d1 += a1 * b1; }
 template <class T> __device__ __forceinline__ void kfma2b(T& d0, T& d1, T a0, T a1, T c) { kfma2(d0, d1, a0, a1, c, c); }
+// packed multiply (FMUL2): d0 = a0*b0, d1 = a1*b1
+__device__ __forceinline__ void kmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    unsigned long long ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rd));
+}
+template <class T> __device__ __forceinline__ void kmul2(T& d0, T& d1, T a0, T a1, T b0, T b1) { d0 = a0 * b0; d1 = a1 * b1; }
 
 // ---- PI controller helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ float fastlog2f(float x) {

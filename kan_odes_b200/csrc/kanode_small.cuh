@@ -197,6 +197,43 @@ __device__ __forceinline__ void stage_weights(T* wsm, uint64_t* bar, const T* __
     mbar_wait(bar, 0);
 }
 
+// Gaussian RBF of one normalised input on all G grid points, two grid points per packed instruction (FFMA2 / FMUL2):
+//   na[g] = gs[g] - xn*hs  (the NEGATED scaled argument: its square and the products below are bit-identical to the scalar form),
+//   b[g] = exp2(-na[g]^2);  ndb[g] = (dk * a) * b = ((-dk) * na) * b when WITH_DB
+template <bool WITH_DB, class T, class P>
+__device__ __forceinline__ void rbf_eval(const P& p, T xn, T (&b)[P::G], T (&db)[P::G]) {
+    constexpr int G = P::G;
+    if constexpr (sizeof(T) == 4) {
+        const T nhs = -p.hs, ndk = -p.dk;
+        T na[G], t[G];
+#pragma unroll
+        for (int g = 0; g + 1 < G; g += 2) {
+            na[g] = p.gs[g]; na[g + 1] = p.gs[g + 1];
+            kfma2b(na[g], na[g + 1], nhs, nhs, xn);
+            kmul2(t[g], t[g + 1], na[g], na[g + 1], na[g], na[g + 1]);
+        }
+        if constexpr (G % 2 == 1) { na[G - 1] = fmaf(nhs, xn, p.gs[G - 1]); t[G - 1] = na[G - 1] * na[G - 1]; }
+#pragma unroll
+        for (int g = 0; g < G; ++g) b[g] = kex2(-t[g]);
+        if constexpr (WITH_DB) {
+#pragma unroll
+            for (int g = 0; g + 1 < G; g += 2) {
+                T m0, m1;
+                kmul2(m0, m1, ndk, ndk, na[g], na[g + 1]);
+                kmul2(db[g], db[g + 1], m0, m1, b[g], b[g + 1]);
+            }
+            if constexpr (G % 2 == 1) db[G - 1] = (ndk * na[G - 1]) * b[G - 1];
+        }
+    } else {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const T a = xn * p.hs - p.gs[g];
+            b[g] = krbf_scaled(a);
+            if constexpr (WITH_DB) db[g] = p.dk * a * b[g];
+        }
+    }
+}
+
 // features of the state components: f[i*G+g] = basis_g(norm(u_i)), f[I*G+i] = swish(u_i)  (layout of the packed C1|W1)
 template <int NORM, class T, class P>
 __device__ __forceinline__ void input_features(const P& p, const T (&u)[P::I], T (&f)[P::NQ]) {
@@ -204,8 +241,10 @@ __device__ __forceinline__ void input_features(const P& p, const T (&u)[P::I], T
 #pragma unroll
     for (int i = 0; i < I; ++i) {
         const T xn = normalize<NORM>(u[i]);
+        T bb[G], dummy[G];
+        rbf_eval<false>(p, xn, bb, dummy);
 #pragma unroll
-        for (int g = 0; g < G; ++g) f[i * G + g] = krbf_scaled(xn * p.hs - p.gs[g]);
+        for (int g = 0; g < G; ++g) f[i * G + g] = bb[g];
         swish_fwd(u[i], f[I * G + i]);
     }
 }
@@ -225,11 +264,12 @@ __device__ __forceinline__ void small_rhs_sm(const P& p, const T* __restrict__ w
 #pragma unroll
         for (int q = 0; q < NQ; ++q) h += w[q] * f[q];
         const T xn = normalize<NORM>(h);
+        T bb[G], dummy[G];
+        rbf_eval<false>(p, xn, bb, dummy);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const T b = krbf_scaled(xn * p.hs - p.gs[g]);
 #pragma unroll
-            for (int o = 0; o < I; ++o) du[o] += w[NQ + g * I + o] * b;
+            for (int o = 0; o < I; ++o) du[o] += w[NQ + g * I + o] * bb[g];
         }
         T s; swish_fwd(h, s);
 #pragma unroll
@@ -248,12 +288,12 @@ __device__ __forceinline__ void small_vjp_sm(const P& p, const T* __restrict__ w
     for (int i = 0; i < I; ++i) {
         const T xn = normalize<NORM>(y[i]);
         const T dn = normalize_deriv<NORM>(xn);
+        T bb[G], dbb[G];
+        rbf_eval<true>(p, xn, bb, dbb);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const T a = xn * p.hs - p.gs[g];
-            const T b = krbf_scaled(a);
-            f[i * G + g] = b;
-            df[i * G + g] = p.dk * a * b * dn;                           // utils.jl:18 * d(arg)/d(xn) * norm'
+            f[i * G + g] = bb[g];
+            df[i * G + g] = dbb[g] * dn;                                 // utils.jl:18 * d(arg)/d(xn) * norm'
         }
         swish_both(y[i], f[I * G + i], df[I * G + i]);
     }
@@ -275,14 +315,14 @@ __device__ __forceinline__ void small_vjp_sm(const P& p, const T* __restrict__ w
         }
         const T xn = normalize<NORM>(h);
         T xnbar = T(0);
+        T bb[G], dbb[G];
+        rbf_eval<true>(p, xn, bb, dbb);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const T a = xn * p.hs - p.gs[g];
-            const T b = krbf_scaled(a);
             T bbar = T(0);
 #pragma unroll
             for (int o = 0; o < I; ++o) bbar += w[NQ + g * I + o] * lam[o];
-            xnbar += (p.dk * a * b) * bbar;
+            xnbar += dbb[g] * bbar;
         }
         T s, ds; swish_both(h, s, ds);
         T sbar = T(0);
@@ -654,8 +694,10 @@ __device__ __forceinline__ void small_vjp_h(const P& p, const T (&y)[P::I], cons
 template <int NORM, class T, class P>
 __device__ __forceinline__ void unit_features(const P& p, T x, T (&c)[P::G + 1]) {
     const T xn = normalize<NORM>(x);
+    T bb[P::G], dummy[P::G];
+    rbf_eval<false>(p, xn, bb, dummy);
 #pragma unroll
-    for (int g = 0; g < P::G; ++g) c[g] = krbf_scaled(xn * p.hs - p.gs[g]);
+    for (int g = 0; g < P::G; ++g) c[g] = bb[g];
     swish_fwd(x, c[P::G]);
 }
 
