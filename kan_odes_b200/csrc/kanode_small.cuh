@@ -288,12 +288,12 @@ __device__ __forceinline__ void small_vjp_sm(const P& p, const T* __restrict__ w
     for (int i = 0; i < I; ++i) {
         const T xn = normalize<NORM>(y[i]);
         const T dn = normalize_deriv<NORM>(xn);
-        T bb[G], dbb[G];
-        rbf_eval<true>(p, xn, bb, dbb);
+        T rb[G], rdb[G];
+        rbf_eval<true>(p, xn, rb, rdb);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            f[i * G + g] = bb[g];
-            df[i * G + g] = dbb[g] * dn;                                 // utils.jl:18 * d(arg)/d(xn) * norm'
+            f[i * G + g] = rb[g];
+            df[i * G + g] = rdb[g] * dn;                                 // utils.jl:18 * d(arg)/d(xn) * norm'
         }
         swish_both(y[i], f[I * G + i], df[I * G + i]);
     }
@@ -315,14 +315,14 @@ __device__ __forceinline__ void small_vjp_sm(const P& p, const T* __restrict__ w
         }
         const T xn = normalize<NORM>(h);
         T xnbar = T(0);
-        T bb[G], dbb[G];
-        rbf_eval<true>(p, xn, bb, dbb);
+        T rb[G], rdb[G];                                                 // (the outer bb[] accumulates sum_j w1[q][j] * hbar_j)
+        rbf_eval<true>(p, xn, rb, rdb);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             T bbar = T(0);
 #pragma unroll
             for (int o = 0; o < I; ++o) bbar += w[NQ + g * I + o] * lam[o];
-            xnbar += dbb[g] * bbar;
+            xnbar += rdb[g] * bbar;
         }
         T s, ds; swish_both(h, s, ds);
         T sbar = T(0);
