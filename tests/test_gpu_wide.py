@@ -183,3 +183,24 @@ def test_hidden_source_lockstep_matches_block_per_trajectory(n, G, B, monkeypatc
     ode = K.KanOde(chain, kw["rhs_kind"], n, kw["lap_coef"], kw["dx"], dtype=np.float32); ode.set_params(p)
     r32 = ode.loss_grad(u0, tspan, saveat, tg); ode.close()
     assert (r32["bwd_stats"].retcode == 0).all() and _relmax(r32["grad"], ref["grad"]) < 2e-2
+
+
+def test_gpass_timing_entry_point(monkeypatch):
+    """kanode_last_gpass_timing: available after a wide-engine step launched directly (KANODE_WIDE_GRAPH=0), an error after an
+    LV (thread-per-trajectory) step; kanode_last_timing works for both."""
+    import ctypes as C
+    from conftest import lv_chain
+    monkeypatch.setenv("KANODE_WIDE", "1"); monkeypatch.setenv("KANODE_WIDE_GRAPH", "0")
+    chain, p, u0, tspan, saveat, tg = _problem(256, 5, 4, seed=2)
+    ode = K.KanOde(chain, dtype=np.float32); ode.set_params(p)
+    r = ode.loss_grad(u0, tspan, saveat, tg)
+    ms, passes, m3 = C.c_float(), C.c_int32(), (C.c_float * 3)()
+    assert ode.lib.kanode_last_gpass_timing(ode.h, C.byref(ms), C.byref(passes)) == 0
+    assert passes.value >= int(r["bwd_stats"].naccept.max()) and ms.value > 0
+    assert ode.lib.kanode_last_timing(ode.h, m3) == 0 and m3[1] > ms.value
+    ode.close()
+    lv = lv_chain()
+    ode = K.KanOde(lv, dtype=np.float32); ode.set_params(glorot_params(lv, seed=0))
+    ode.loss_grad(np.ones((4, 2)), (0.0, 1.0), [0.5, 1.0], np.ones((4, 2, 2)))
+    assert ode.lib.kanode_last_gpass_timing(ode.h, C.byref(ms), C.byref(passes)) != 0
+    ode.close()
