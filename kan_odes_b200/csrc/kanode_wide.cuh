@@ -105,10 +105,28 @@ template <class T> struct WideIn {
     const int* mask;     // per-IC, 0 = skip (may be null)
 };
 
+// Per-tile table of the dense-output data of its ICs (MODE 1): interpolation weights b_1..b_7(theta), the step size and the
+// record row, computed once per block instead of once per (unit, IC) pair.
+template <class T, int NB> struct WideInterpTab { T bw[NB][8]; const T* row[NB]; };
+template <class T, int NB>
+__device__ __forceinline__ void wide_interp_tab(const WideIn<T>& in, int b0, int b1, int n, WideInterpTab<T, NB>& tab) {
+    if (threadIdx.x < NB) {
+        const int bl = threadIdx.x, b = b0 + bl < b1 ? b0 + bl : b0;
+        T bw[7]; interp_weights(in.th[b], bw);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) tab.bw[bl][j] = bw[j];
+        tab.bw[bl][7] = in.hd[b];
+        const int brow = in.brec > 0 ? b % in.brec : b;
+        tab.row[bl] = in.rec + ((int64_t)brow * in.cap + in.ridx[b]) * 8 * (int64_t)n;
+    }
+    __syncthreads();
+}
+
 // Inputs of unit i for the NB ICs b0..b0+NB of a tile.  All global loads are issued before the first dependent FMA (the
 // loop is written in phases and fully unrolled), so one memory latency covers the whole tile.
 template <class T, int MODE, int NB>
-__device__ __forceinline__ void wide_inputs(const WideIn<T>& in, int b0, int b1, int i, bool valid, int n, int64_t B, T (&xs)[NB], bool (&on)[NB]) {
+__device__ __forceinline__ void wide_inputs(const WideIn<T>& in, int b0, int b1, int i, bool valid, int n, int64_t B, T (&xs)[NB], bool (&on)[NB],
+                                            const WideInterpTab<T, NB>* tab = nullptr) {
 #pragma unroll
     for (int bl = 0; bl < NB; ++bl) { const int b = b0 + bl; on[bl] = valid && b < b1 && (!in.mask || in.mask[b]); }
     if (MODE == 0) {
@@ -130,26 +148,19 @@ __device__ __forceinline__ void wide_inputs(const WideIn<T>& in, int b0, int b1,
             xs[bl] = in.ncoef > 0 ? base[bl] + hs[bl] * acc : base[bl];
         }
     } else {
-        T th[NB], hd[NB], raw[NB][8];
-        const T* r[NB];
+        T raw[NB][8];
 #pragma unroll
         for (int bl = 0; bl < NB; ++bl) {
-            const int b = on[bl] ? b0 + bl : b0;
-            th[bl] = in.th[b]; hd[bl] = in.hd[b];
-            const int brow = in.brec > 0 ? b % in.brec : b;
-            r[bl] = in.rec + ((int64_t)brow * in.cap + in.ridx[b]) * 8 * (int64_t)n + i;
+            const T* r = tab->row[bl] + i;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) raw[bl][j] = on[bl] ? r[j * n] : T(0);
         }
 #pragma unroll
-        for (int bl = 0; bl < NB; ++bl)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) raw[bl][j] = on[bl] ? r[bl][j * n] : T(0);
-#pragma unroll
         for (int bl = 0; bl < NB; ++bl) {
-            T bw[7]; interp_weights(th[bl], bw);
             T acc = T(0);
 #pragma unroll
-            for (int j = 0; j < 7; ++j) acc += bw[j] * raw[bl][1 + j];
-            xs[bl] = raw[bl][0] + hd[bl] * acc;
+            for (int j = 0; j < 7; ++j) acc += tab->bw[bl][j] * raw[bl][1 + j];
+            xs[bl] = raw[bl][0] + tab->bw[bl][7] * acc;
         }
     }
 }
@@ -225,11 +236,13 @@ __global__ void __launch_bounds__(W_BT, 3) wide_l1_fwd_kernel(const __grid_const
     const int tid = threadIdx.x, n = m.n;
     const int b0 = blockIdx.y * btile, b1 = (int)min((int64_t)(b0 + btile), B);
     const T inv_h = (T)m.inv_h1;
+    __shared__ WideInterpTab<T, GB> itab;
+    if (MODE == 1) wide_interp_tab<T, GB>(in, b0, b1, n, itab);
     for (int pass = 0; pass < P; ++pass) {
         const int i = (blockIdx.x * P + pass) * W_BT + tid;
         const bool valid = i < n;
         T xs[GB]; bool on[GB];
-        wide_inputs<T, MODE, GB>(in, b0, b1, i, valid, n, B, xs, on);
+        wide_inputs<T, MODE, GB>(in, b0, b1, i, valid, n, B, xs, on, &itab);
         T w[NW];
 #pragma unroll
         for (int k = 0; k < NW; ++k) w[k] = valid ? w1t[k * n + i] : T(0);               // [NW][n]: coalesced over the units

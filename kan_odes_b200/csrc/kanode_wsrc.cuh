@@ -65,8 +65,17 @@ __global__ void __launch_bounds__(W_ET) wsrc_vjp_kernel(const __grid_constant__ 
                                                         const WideIn<T> inl /* lambda combination */, int64_t B, T* dl, T* lstore, T* kg_part /* [B][nkg][W_HP] of this stage */) {
     __shared__ T ls_[W_ET];
     __shared__ T red[W_ET / 32][W_HP];
+    __shared__ T sbw[8];                       // interpolation weights b_1..b_7(theta) and the step of this IC's record row
+    __shared__ const T* srow;
     const int b = blockIdx.y, tid = threadIdx.x, n = m.n, i = blockIdx.x * W_ET + tid;
     if (inl.mask && !inl.mask[b]) return;
+    if (tid == 0) {
+        T bw[7]; interp_weights(iny.th[b], bw);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) sbw[j] = bw[j];
+        sbw[7] = iny.hd[b];
+        srow = iny.rec + ((int64_t)b * iny.cap + iny.ridx[b]) * 8 * (int64_t)n;
+    }
     const bool valid = i < n;
     const T l = valid ? wsrc_comb<T>(inl, b, i, n, B) : T(0);
     ls_[tid] = l;
@@ -77,7 +86,10 @@ __global__ void __launch_bounds__(W_ET) wsrc_vjp_kernel(const __grid_constant__ 
     if (valid) {
         const T ll = tid > 0 ? ls_[tid - 1] : wsrc_comb<T>(inl, b, (i + n - 1) % n, n, B);     // the Laplacian is symmetric
         const T lr = (tid + 1 < W_ET && i + 1 < n) ? ls_[tid + 1] : wsrc_comb<T>(inl, b, (i + 1) % n, n, B);
-        const T y = wsrc_interp<T>(iny, b, i, n);
+        T yacc = T(0);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) yacc += sbw[j] * srow[(int64_t)(1 + j) * n + i];
+        const T y = srow[i] + sbw[7] * yacc;
         // forward features and their derivatives (utils.jl:15-21, NNlib activation rules)
         const T inv_h = (T)m.inv_h;
         const T xn = normalize_rt(m.norm, y);
