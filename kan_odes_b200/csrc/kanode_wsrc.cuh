@@ -26,15 +26,6 @@ template <class T> __device__ __forceinline__ T wsrc_comb(const WideIn<T>& in, i
     for (int j = 0; j < in.ncoef; ++j) acc += in.coef[j] * in.ks[(int64_t)j * B * n + e];
     return in.ncoef > 0 ? in.base[e] + in.hs[b] * acc : in.base[e];
 }
-template <class T> __device__ __forceinline__ T wsrc_interp(const WideIn<T>& in, int b, int i, int n) {
-    T bw[7]; interp_weights(in.th[b], bw);
-    const T* r = in.rec + ((int64_t)b * in.cap + in.ridx[b]) * 8 * (int64_t)n;
-    T acc = T(0);
-#pragma unroll
-    for (int j = 0; j < 7; ++j) acc += bw[j] * r[(int64_t)(1 + j) * n + i];
-    return r[i] + in.hd[b] * acc;
-}
-
 // k[b][i] = ls * (x[i-1] - 2 x[i] + x[i+1]) + kan(x[i]),  x = uprev + h * sum a_sj k_j
 template <class T, int G>
 __global__ void __launch_bounds__(W_ET) wsrc_rhs_kernel(const __grid_constant__ SrcModel m, const T* __restrict__ p, const WideIn<T> in, int64_t B,
