@@ -201,8 +201,9 @@ def run_ours(args):
                 d_loss.data_ptr(), d_grad.data_ptr(), None,
                 d_fst.data_ptr() if with_stats else None, d_bst.data_ptr() if with_stats else None)
         abi.check(lib, ode.h, rc, "kanode_loss_grad_dev")
-        if world > 1:                                              # the only collective: gradient + loss sums
+        if world > 1 and not os.environ.get("KANODE_BENCH_NO_ALLREDUCE"):  # the only collective: gradient + loss sums
             combine_loss_grad(d_loss, d_grad, B, SAVEAT.size, 2, sync=False)   # no host read-back inside the timed loop
+            # (KANODE_BENCH_NO_ALLREDUCE=1 is a diagnostic: it isolates the collective's share of the step at N > 1; not a bench mode)
 
     ms3 = (C.c_float * 3)()
     with torch.cuda.stream(stream):
