@@ -156,10 +156,18 @@ def main():
                     "failed": int((fst[:, 3] != 0).sum() + (bst[:, 3] != 0).sum()), "loss": loss, "gpu_launches": int(launches)}
             if wide and gp.mean() > 0:
                 alg = attempts * 2 * ode.np_ * esz
+                traffic = None                                  # DRAM bytes of one gp1+gp2 launch pair from the committed ncu capture
+                try:
+                    tj = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+                    if name == "schrodinger16384" and B == 32 and not f64:
+                        traffic = tj["wide_gp1_kernel_bytes_schrodinger16384_b32"] + tj["wide_gp2_kernel_bytes_schrodinger16384_b32"]
+                except Exception:
+                    pass
                 ach = alg / (gp.mean() / 1e3) / 1e9
                 line["roofline"] = {"kernel": "wide_gp1_kernel+wide_gp2_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                                     "frac": ach / hbm_peak, "algorithmic_bytes": alg, "ms": float(gp.mean()), "passes": int(gpn.mean()),
-                                    "share_of_backward": float(gp.mean() / k[1]), "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
+                                    "share_of_backward": float(gp.mean() / k[1]), "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                                    "traffic": traffic}
             print(json.dumps(line), flush=True)
         ode.close()
     if world > 1:
