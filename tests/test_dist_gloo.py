@@ -43,7 +43,9 @@ def _worker(rank, world, port, batch, q):
     nloc = hi - lo
     loss_sum = torch.tensor([r["loss"] * nloc * sa.size * 2], dtype=torch.float64)     # unnormalised, as the C ABI returns
     grad_sum = torch.tensor(r["grad"] * nloc, dtype=torch.float64)
+    loss2, grad2, cnt2 = combine_loss_grad(loss_sum.clone(), grad_sum.clone(), nloc, sa.size, 2, sync=False)   # device-only variant
     loss, grad, total = combine_loss_grad(loss_sum, grad_sum, nloc, sa.size, 2)
+    assert torch.equal(loss2, loss) and torch.equal(grad2, grad) and int(cnt2.item()) == total
     if rank == 0:
         q.put((float(loss), grad.numpy(), total))
     dist.barrier()
