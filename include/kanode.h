@@ -202,6 +202,26 @@ int kanode_loss_grad_dev_f64(kanode_handle* h, const double* d_u0, int64_t batch
                              double* d_loss_sum, double* d_grad_sum, double* d_du0,
                              kanode_stats* d_fwd_stats, kanode_stats* d_bwd_stats);
 
+/* ---- dt-replay (parity tooling; SURVEY.md §7.3 "replay reference dt sequence") ------------------------------------
+ * Same result as kanode_loss_grad, but the step-size controller of BOTH solves is bypassed: the forward solve takes the
+ * accepted steps whose END times are fwd_t[b][0..] (ascending, NaN-padded to max_steps), the adjoint solve those of
+ * bwd_t[b][0..] (descending, the save times among them).  Feeding the fp64 oracle's sequences to the fp32 kernels separates
+ * arithmetic parity from controller parity: what [EXT OrdinaryDiffEqCore] decides (a12-a14 of SURVEY.md §8a) is taken from
+ * the reference run, what remains is the kernels' arithmetic.  out (optional) receives the predictions [batch][nsave][n].
+ * Only the small-model ensemble kernels implement it (KANODE_ERR_UNSUPPORTED otherwise). */
+int kanode_loss_grad_replay(kanode_handle* h, const float* u0, int64_t batch,
+                            double t0, double t1, const double* saveat, int32_t nsave,
+                            const float* target, float abstol, float reltol,
+                            const double* fwd_t, const double* bwd_t, int32_t max_steps,
+                            float* loss, float* grad, float* du0 /* or NULL */, float* out /* or NULL */,
+                            kanode_stats* fwd_stats /* or NULL */, kanode_stats* bwd_stats /* or NULL */);
+int kanode_loss_grad_replay_f64(kanode_handle* h, const double* u0, int64_t batch,
+                                double t0, double t1, const double* saveat, int32_t nsave,
+                                const double* target, double abstol, double reltol,
+                                const double* fwd_t, const double* bwd_t, int32_t max_steps,
+                                double* loss, double* grad, double* du0, double* out,
+                                kanode_stats* fwd_stats, kanode_stats* bwd_stats);
+
 /* Flux.Adam(eta, (beta1, beta2), eps) + update!(opt, p, grad)  (LV_driver_KANODE.jl:219,287; [EXT Flux 0.14.22]):
  *   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g^2;  p -= eta * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps),  g = grad_scale*d_grad.
  * All pointers are device pointers of np floats; t is the 1-based iteration count.  grad_scale lets a data-parallel

@@ -60,6 +60,7 @@ EXPORTED_SYMBOLS = (
     "kanode_launch_count", "kanode_set_record_capacity",
     "kanode_set_params_f64", "kanode_rhs_f64", "kanode_vjp_f64", "kanode_solve_f64", "kanode_loss_grad_f64",
     "kanode_loss_grad_dev_f64", "kanode_last_timing", "kanode_adam_step_dev", "kanode_last_gpass_timing",
+    "kanode_loss_grad_replay", "kanode_loss_grad_replay_f64",
 )
 
 _lib = None

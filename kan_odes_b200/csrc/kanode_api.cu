@@ -15,6 +15,7 @@
 #include "kanode_host.h"
 #include "kanode_small.cuh"
 #include "kanode_small_ls.cuh"
+#include "kanode_small_lg.cuh"
 #include "kanode_generic.cuh"
 #include "kanode_wide_api.h"
 
@@ -82,6 +83,36 @@ template <class T, class P> int upload_packed(kanode_handle* h, const T** out) {
         CK(h, cudaMemcpyAsync(d, pk.data(), sizeof(T) * pk.size(), cudaMemcpyHostToDevice, h->stream));
         CK(h, cudaStreamSynchronize(h->stream));                       // pk is a stack-lifetime staging buffer
         h->wpk_version[sizeof(T) == 4 ? 0 : 1] = h->params_version;
+    }
+    *out = d;
+    return 0;
+}
+
+// packed weights in LANE blocks for the lane-group backward kernel (layout: LgSmem::LW): block `lig` holds the UPL hidden
+// units of lane `lig`, each in the SmallParams::UW layout
+template <class T, class P, int UPL> int upload_packed_lg(kanode_handle* h, const T** out) {
+    using SMP = LgSmem<T, P, UPL>;
+    constexpr int I = P::I, G = P::G, NQ = P::NQ, LPT = LgGeom<P, UPL>::LPT;
+    T* d = nullptr;
+    const int slot = sizeof(T) == 4 ? 0 : 1;
+    if (slot == 0) ENSURE(h, W_WLG32, sizeof(T) * SMP::WLG, d); else ENSURE(h, W_WLG64, sizeof(T) * SMP::WLG, d);
+    if (h->wlg_version[slot] != h->params_version) {
+        std::vector<T> pk((size_t)SMP::WLG, T(0));
+        for (int l = 0; l < LPT; ++l)
+            for (int u = 0; u < UPL; ++u) {
+                const int j = UPL * l + u;
+                T* w = pk.data() + (size_t)l * SMP::LW + (size_t)u * P::UW;
+                for (int i = 0; i < I; ++i) {
+                    for (int g = 0; g < G; ++g) w[i * G + g] = (T)h->params[P::OC1 + (i * G + g) * P::H + j];
+                    w[I * G + i] = (T)h->params[P::OW1 + i * P::H + j];
+                }
+                for (int g = 0; g < G; ++g)
+                    for (int o = 0; o < I; ++o) w[NQ + g * I + o] = (T)h->params[P::OC2 + (j * G + g) * I + o];
+                for (int o = 0; o < I; ++o) w[NQ + G * I + o] = (T)h->params[P::OW2 + j * I + o];
+            }
+        CK(h, cudaMemcpyAsync(d, pk.data(), sizeof(T) * pk.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));                       // pk is a stack-lifetime staging buffer
+        h->wlg_version[slot] = h->params_version;
     }
     *out = d;
     return 0;
@@ -197,7 +228,8 @@ int solve_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double t1, 
 template <class T>
 int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double t1, const double* saveat, int nsave,
                   const T* d_target, double abstol, double reltol, double* d_loss_sum, T* d_grad_sum, T* d_du0,
-                  kanode_stats* d_fst, kanode_stats* d_bst, T* d_out_opt) {
+                  kanode_stats* d_fst, kanode_stats* d_bst, T* d_out_opt, const double* d_rp_fwd = nullptr,
+                  const double* d_rp_bwd = nullptr, int rp_cap = 0) {
     if (!h->have_params) return fail(h, KANODE_ERR_INVALID, "parameters not set");
     if (int rc = check_saveat(h, t0, t1, saveat, nsave)) return rc;
     if (nsave < 1) return fail(h, KANODE_ERR_INVALID, "loss needs at least one save time");
@@ -210,6 +242,56 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
     auto run = [&]<class P, int NORM>() -> int {
         constexpr int I = P::I;
         P prm; fill_small<T>(h, prm);
+        if (h->bwd_lg || d_rp_fwd || d_rp_bwd) {
+            // Lane-group adjoint kernel (kanode_small_lg.cuh): a group of lanes per trajectory, gradient state in registers,
+            // stage factors in shared memory; array-of-structures dense record; per-warp gradient sums reduced in fp64.
+            constexpr int UPL = sizeof(T) == 4 ? 2 : 1, WPB = KANODE_LG_WPB, MINB = sizeof(T) == 4 ? KANODE_LG_MINB : 2;
+            using GM = LgGeom<P, UPL>; using SMP = LgSmem<T, P, UPL>; using RL = RecLayout<T, I>;
+            constexpr int NSLAB = 32;
+            const int cap = h->rec_cap;
+            const int64_t nwarps = (B + GM::TPW - 1) / GM::TPW;
+            const unsigned nblk = (unsigned)((nwarps + WPB - 1) / WPB);
+            T *rec = nullptr, *dg = nullptr, *gpart = nullptr; double* slab = nullptr;
+            int *nsteps = nullptr, *retc = nullptr;
+            ENSURE(h, W_REC, sizeof(T) * (size_t)cap * RL::RS * B, rec);
+            ENSURE(h, W_NSTEPS, sizeof(int) * (size_t)B, nsteps);
+            ENSURE(h, W_RET, sizeof(int) * (size_t)B, retc);
+            ENSURE(h, W_DG, sizeof(T) * (size_t)nsave * I * B, dg);
+            ENSURE(h, W_GPART, sizeof(T) * (size_t)nblk * WPB * P::NP, gpart);
+            ENSURE(h, W_SLAB, sizeof(double) * (size_t)NSLAB * P::NP, slab);
+            SmallFwdArgs<T> a{};
+            if (int rcw = upload_packed<T, P>(h, &a.wpk)) return rcw;
+            a.u0 = d_u0; a.B = B; a.t0 = t0; a.t1 = t1; a.saveat = d_saveat; a.nsave = nsave;
+            a.abstol = (T)abstol; a.reltol = (T)reltol; a.maxiters = 100000; a.out = d_out_opt; a.stats = d_fst;
+            a.rec_t = nullptr; a.rec = rec; a.cap = cap; a.nsteps = nsteps; a.retcode = retc;
+            a.target = d_target; a.dg = dg; a.loss_sum = d_loss_sum; a.rp_t = d_rp_fwd; a.rp_cap = rp_cap;
+            LgBwdArgs<T> bw{};
+            if (int rcw = upload_packed_lg<T, P, UPL>(h, &bw.wpk)) return rcw;
+            bw.B = B; bw.t0 = t0; bw.t1 = t1; bw.saveat = d_saveat; bw.nsave = nsave;
+            bw.abstol = (T)abstol; bw.reltol = (T)reltol; bw.maxiters = h->bwd_maxiters;
+            bw.rec = rec; bw.cap = cap; bw.nsteps = nsteps; bw.retcode = retc; bw.dg = dg; bw.gpart = gpart;
+            bw.du0 = d_du0; bw.stats = d_bst; bw.attempts = nullptr; bw.rp_t = d_rp_bwd; bw.rp_cap = rp_cap;
+            const size_t smem = SMP::bytes(WPB);
+            auto kern = small_backward_lg_kernel<T, P, NORM, UPL, WPB, MINB>;
+            const int abit = sizeof(T) == 4 ? 1 : 2;
+            if (!(h->attr_done & abit)) {
+                CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                h->attr_done |= abit;
+            }
+            cudaEventRecord(h->ev[0], h->stream);
+            small_forward_kernel<T, P, NORM, true, true><<<blocks_for(B, 64), 64, 0, h->stream>>>(prm, a);
+            cudaEventRecord(h->ev[1], h->stream);
+            kern<<<nblk, 32 * WPB, smem, h->stream>>>(prm, bw);
+            cudaEventRecord(h->ev[2], h->stream);
+            reduce_partials_kernel<T><<<dim3(NSLAB, (P::NP + 255) / 256), 256, 0, h->stream>>>(gpart, (int64_t)nblk * WPB, P::NP, slab);
+            reduce_slabs_kernel<T><<<(P::NP + 255) / 256, 256, 0, h->stream>>>(slab, NSLAB, P::NP, d_grad_sum, 1.0);
+            cudaEventRecord(h->ev[3], h->stream);
+            h->launches += 4;
+            h->ev_valid = true;
+            CK(h, cudaGetLastError());
+            return 0;
+        }
+        if (d_rp_fwd || d_rp_bwd) return fail(h, KANODE_ERR_UNSUPPORTED, "dt-replay needs the lane-group kernels (KANODE_BWD=1)");
         const int cap = h->rec_cap;
         double* rec_t = nullptr; T *rec = nullptr, *dg = nullptr, *fac = nullptr, *g = nullptr;
         int *nsteps = nullptr, *retc = nullptr;
@@ -233,7 +315,7 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
         bw.abstol = (T)abstol; bw.reltol = (T)reltol; bw.maxiters = 100000;
         bw.rec_t = rec_t; bw.rec = rec; bw.cap = cap; bw.nsteps = nsteps; bw.retcode = retc; bw.dg = dg;
         bw.fac = nullptr; bw.g = g; bw.du0 = d_du0; bw.stats = d_bst;
-        if (const char* e = std::getenv("KANODE_BWD_MAXIT")) bw.maxiters = std::atoi(e);   // timing experiments only
+        bw.maxiters = h->bwd_maxiters;
         // the lockstep engine is opt-in (KANODE_LOCKSTEP=1): measured slower than the monolithic kernel on B200 because its
         // stage records and per-trajectory state round-trip through L2/HBM every step
         const bool lockstep = h->lockstep > 0 && (int64_t)B * 7 * StageRec<P>::N < (1ll << 31);
@@ -243,8 +325,7 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
             // gradient pass is spread over the lanes), launched ahead of the bulk, which follows on a second stream.
             // Their serial chain of steps then finishes well inside the bulk's run time instead of bounding the launch.
             constexpr int BT = KANODE_BWD_BT;                              // threads (= trajectories) per block
-            int kLongSlots = 256;
-            if (const char* e = std::getenv("KANODE_LONG_SLOTS")) kLongSlots = std::atoi(e);   // tuning experiments
+            const int kLongSlots = h->long_slots;
             const size_t smem = sizeof(T) * (7 * StageRec<P>::N * BT + P::WPK) + 16;   // stage records + packed weights + mbarrier
             CK(h, cudaFuncSetAttribute(small_backward_kernel<T, P, NORM, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const int slot = sizeof(T) == 4 ? 0 : 1;
@@ -416,9 +497,11 @@ int solve_host(kanode_handle* h, const T* u0, int64_t B, double t0, double t1, c
 template <class T>
 int loss_grad_host(kanode_handle* h, const T* u0, int64_t B, double t0, double t1, const double* saveat, int nsave,
                    const T* target, double abstol, double reltol, T* loss, T* grad, T* du0, kanode_stats* fst,
-                   kanode_stats* bst) {
+                   kanode_stats* bst, const double* rp_fwd = nullptr, const double* rp_bwd = nullptr, int rp_cap = 0,
+                   T* out = nullptr) {
     if (int rc = enter(h)) return rc;
     if (B <= 0 || !u0 || !target || !loss || !grad) return fail(h, KANODE_ERR_INVALID, "bad arguments");
+    if ((rp_fwd || rp_bwd) && (!rp_fwd || !rp_bwd || rp_cap < 1)) return fail(h, KANODE_ERR_INVALID, "replay needs both step sequences");
     const size_t nout = (size_t)B * nsave * h->n;
     for (int attempt = 0;; ++attempt) {
         T *d_u0 = nullptr, *d_tg = nullptr, *d_grad = nullptr, *d_du0 = nullptr; double* d_loss = nullptr;
@@ -432,8 +515,17 @@ int loss_grad_host(kanode_handle* h, const T* u0, int64_t B, double t0, double t
         ENSURE(h, W_STATS_B, sizeof(kanode_stats) * (size_t)B, d_b);
         CK(h, cudaMemcpyAsync(d_u0, u0, sizeof(T) * (size_t)B * h->n, cudaMemcpyHostToDevice, h->stream));
         CK(h, cudaMemcpyAsync(d_tg, target, sizeof(T) * nout, cudaMemcpyHostToDevice, h->stream));
+        double *d_rpf = nullptr, *d_rpb = nullptr; T* d_out = nullptr;
+        if (rp_fwd) {
+            ENSURE(h, W_RPF, sizeof(double) * (size_t)B * rp_cap, d_rpf);
+            ENSURE(h, W_RPB, sizeof(double) * (size_t)B * rp_cap, d_rpb);
+            CK(h, cudaMemcpyAsync(d_rpf, rp_fwd, sizeof(double) * (size_t)B * rp_cap, cudaMemcpyHostToDevice, h->stream));
+            CK(h, cudaMemcpyAsync(d_rpb, rp_bwd, sizeof(double) * (size_t)B * rp_cap, cudaMemcpyHostToDevice, h->stream));
+        }
+        if (out) ENSURE(h, W_OUT, sizeof(T) * (nout ? nout : 1), d_out);
         if (int rc = loss_grad_dev<T>(h, d_u0, B, t0, t1, saveat, nsave, d_tg, abstol, reltol, d_loss, d_grad, d_du0,
-                                      d_f, d_b, (T*)nullptr)) return rc;
+                                      d_f, d_b, d_out, d_rpf, d_rpb, rp_cap)) return rc;
+        if (out) CK(h, cudaMemcpyAsync(out, d_out, sizeof(T) * nout, cudaMemcpyDeviceToHost, h->stream));
         // every result goes to ONE pinned staging block with async copies and a single synchronisation
         const size_t o_f = 0, o_b = o_f + sizeof(kanode_stats) * (size_t)B, o_du = o_b + sizeof(kanode_stats) * (size_t)B,
                      o_g = o_du + sizeof(T) * (size_t)B * h->n, o_l = (o_g + sizeof(T) * h->np + 7) / 8 * 8, total = o_l + 8;
@@ -497,6 +589,9 @@ int kanode_create(const kanode_desc* desc, int device, void* stream, kanode_hand
     h->desc = *desc; h->device = device; h->np = np; h->n = desc->n_state;
     h->params.assign(np, 0.0);
     if (const char* e = std::getenv("KANODE_LOCKSTEP")) h->lockstep = std::atoi(e);
+    if (const char* e = std::getenv("KANODE_BWD")) h->bwd_lg = std::atoi(e);                 // 0: round-1 thread-per-trajectory adjoint (A/B)
+    if (const char* e = std::getenv("KANODE_BWD_MAXIT")) h->bwd_maxiters = std::atoi(e);     // timing experiments only
+    if (const char* e = std::getenv("KANODE_LONG_SLOTS")) h->long_slots = std::atoi(e);
     if (const char* e = std::getenv("KANODE_SCHEDULE")) h->schedule = std::atoi(e);
     if (const char* e = std::getenv("KANODE_WIDE")) h->wide = std::atoi(e);
     if (const char* e = std::getenv("KANODE_WIDE_TC")) h->wide_tc = std::atoi(e);
@@ -631,6 +726,22 @@ int kanode_loss_grad_f64(kanode_handle* h, const double* u0, int64_t batch, doub
                          double* du0, kanode_stats* fwd_stats, kanode_stats* bwd_stats) {
     return loss_grad_host<double>(h, u0, batch, t0, t1, saveat, nsave, target, abstol, reltol, loss, grad, du0,
                                   fwd_stats, bwd_stats);
+}
+int kanode_loss_grad_replay(kanode_handle* h, const float* u0, int64_t batch, double t0, double t1, const double* saveat,
+                            int32_t nsave, const float* target, float abstol, float reltol, const double* fwd_t,
+                            const double* bwd_t, int32_t max_steps, float* loss, float* grad, float* du0, float* out,
+                            kanode_stats* fwd_stats, kanode_stats* bwd_stats) {
+    if (!fwd_t || !bwd_t) return fail(h, KANODE_ERR_INVALID, "replay needs both step sequences");
+    return loss_grad_host<float>(h, u0, batch, t0, t1, saveat, nsave, target, abstol, reltol, loss, grad, du0,
+                                 fwd_stats, bwd_stats, fwd_t, bwd_t, max_steps, out);
+}
+int kanode_loss_grad_replay_f64(kanode_handle* h, const double* u0, int64_t batch, double t0, double t1, const double* saveat,
+                                int32_t nsave, const double* target, double abstol, double reltol, const double* fwd_t,
+                                const double* bwd_t, int32_t max_steps, double* loss, double* grad, double* du0, double* out,
+                                kanode_stats* fwd_stats, kanode_stats* bwd_stats) {
+    if (!fwd_t || !bwd_t) return fail(h, KANODE_ERR_INVALID, "replay needs both step sequences");
+    return loss_grad_host<double>(h, u0, batch, t0, t1, saveat, nsave, target, abstol, reltol, loss, grad, du0,
+                                  fwd_stats, bwd_stats, fwd_t, bwd_t, max_steps, out);
 }
 int kanode_loss_grad_dev(kanode_handle* h, const float* d_u0, int64_t batch, double t0, double t1, const double* saveat,
                          int32_t nsave, const float* d_target, float abstol, float reltol, double* d_loss_sum,

@@ -47,6 +47,11 @@ struct kanode_handle {
     bool have_params = false;
     uint64_t params_version = 0;     // bumped by set_params; derived device copies are refreshed lazily
     uint64_t wpk_version[2] = {~0ull, ~0ull};
+    uint64_t wlg_version[2] = {~0ull, ~0ull};   // lane-block weight image of the lane-group adjoint kernel
+    int bwd_lg = 1;                  // small path: 1 = lane-group adjoint kernel, 0 = round-1 thread-per-trajectory kernel (KANODE_BWD)
+    int bwd_maxiters = 100000;       // KANODE_BWD_MAXIT (timing experiments)
+    int long_slots = 256;            // KANODE_LONG_SLOTS (round-1 kernel)
+    unsigned attr_done = 0;          // per-handle (= per-device) one-time cudaFuncSetAttribute bits
     int rec_cap = 32;
     int64_t order_B[2] = {0, 0};     // batch size the cached launch order (per dtype) was built for; 0 = none
     int schedule = 1;                // 1: reuse last call's step counts to launch long backward solves first
@@ -60,7 +65,7 @@ struct kanode_handle {
     void* stage = nullptr; size_t stage_bytes = 0;   // pinned host staging block for the results of the host entry points
     // grow-only device workspace, keyed by purpose
     enum { W_U0, W_OUT, W_TARGET, W_STATS_F, W_STATS_B, W_SAVEAT, W_REC_T, W_REC, W_NSTEPS, W_RET, W_DG, W_FAC, W_G,
-           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_WPK32, W_WPK64, W_LAM, W_GEN, W_GEN2, W_LS, W_ATT, W_ORDER, W_WIDE_F, W_WIDE_B, W_W1T32, W_W1T64, W_W2IMG, W_W2TIMG, W_W1IMG, W_WIDE_R, W_COUNT };
+           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_WPK32, W_WPK64, W_LAM, W_GEN, W_GEN2, W_LS, W_ATT, W_ORDER, W_WIDE_F, W_WIDE_B, W_W1T32, W_W1T64, W_W2IMG, W_W2TIMG, W_W1IMG, W_WIDE_R, W_WLG32, W_WLG64, W_GPART, W_SLAB, W_RPF, W_RPB, W_COT, W_COUNT };
     DevBuf ws[W_COUNT];
     kanode::GenericModel gm{};               // layer table for the generic kernels
     // wide (batched lockstep) engine: attempts the last forward-only / dense-forward / backward call needed, counter state

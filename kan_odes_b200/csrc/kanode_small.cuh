@@ -348,6 +348,42 @@ __device__ __forceinline__ void small_vjp_sm(const P& p, const T* __restrict__ w
     }
 }
 
+// ---- dense forward record, array of structures: [t (fp64) | dt | u(I) | k1..k7 (7*I) | pad] in units of T ----
+template <class T, int I_> struct RecLayout {
+    static constexpr int OT = 8 / (int)sizeof(T);                     // T slots taken by the fp64 start time
+    static constexpr int DT = OT, U = OT + 1, K = OT + 1 + I_;
+    static constexpr int V = 16 / (int)sizeof(T);                     // T per 16-byte vector
+    static constexpr int RS = ((OT + 1 + 8 * I_ + V - 1) / V) * V;    // record stride (T)
+};
+__device__ __forceinline__ double rec_get_time(const float* r) { return __hiloint2double(__float_as_int(r[1]), __float_as_int(r[0])); }
+__device__ __forceinline__ double rec_get_time(const double* r) { return r[0]; }
+__device__ __forceinline__ void rec_put_time(float* r, double t) { r[0] = __int_as_float(__double2loint(t)); r[1] = __int_as_float(__double2hiint(t)); }
+__device__ __forceinline__ void rec_put_time(double* r, double t) { r[0] = t; }
+
+// 16-byte vector copies between memory (shared or global, 16-byte aligned) and register arrays
+template <int N> __device__ __forceinline__ void ldv(const float* p, float (&v)[N]) {
+    static_assert(N % 4 == 0, "vector length");
+#pragma unroll
+    for (int k = 0; k < N; k += 4) { const float4 q = *reinterpret_cast<const float4*>(p + k); v[k] = q.x; v[k + 1] = q.y; v[k + 2] = q.z; v[k + 3] = q.w; }
+}
+template <int N> __device__ __forceinline__ void ldv(const double* p, double (&v)[N]) {
+    static_assert(N % 2 == 0, "vector length");
+#pragma unroll
+    for (int k = 0; k < N; k += 2) { const double2 q = *reinterpret_cast<const double2*>(p + k); v[k] = q.x; v[k + 1] = q.y; }
+}
+template <int N> __device__ __forceinline__ void stv(float* p, const float (&v)[N]) {
+    static_assert(N % 4 == 0, "vector length");
+#pragma unroll
+    for (int k = 0; k < N; k += 4) *reinterpret_cast<float4*>(p + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+}
+template <int N> __device__ __forceinline__ void stv(double* p, const double (&v)[N]) {
+    static_assert(N % 2 == 0, "vector length");
+#pragma unroll
+    for (int k = 0; k < N; k += 2) *reinterpret_cast<double2*>(p + k) = make_double2(v[k], v[k + 1]);
+}
+__device__ __forceinline__ float shfl_t(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shfl_t(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
 // ------------------------------------------------------------------------------------------------------
 // argument blocks
 // ------------------------------------------------------------------------------------------------------
@@ -370,8 +406,11 @@ template <class T> struct SmallFwdArgs {
     int* retcode;           // [B]
     // loss pieces (DENSE kernels)
     const T* target;        // [B][nsave][I]
-    T* dg;                  // [nsave][I][B]   dL/du(t_s)
+    T* dg;                  // dL/du(t_s): [nsave][I][B], or [B][nsave][I] in the AOS kernels
     double* loss_sum;       // scalar accumulator
+    // dt-replay (parity tooling): end times of the accepted steps of another run; the controller is bypassed
+    const double* rp_t;     // [B][rp_cap] ascending, NaN-padded; or null
+    int rp_cap;
 };
 
 template <class T> struct SmallBwdArgs {
@@ -401,7 +440,9 @@ template <class T> struct SmallBwdArgs {
 // forward: adaptive Tsit5 with saveat interpolation; DENSE additionally records every accepted step and
 // evaluates the loss / dL/du at the save times.
 // ------------------------------------------------------------------------------------------------------
-template <class T, class P, int NORM, bool DENSE>
+// AOS: the dense record is one RecLayout structure per accepted step ([B][cap][RS]) and dg is [B][nsave][I] — the layouts
+// the lane-group backward kernel reads (kanode_small_lg.cuh).
+template <class T, class P, int NORM, bool DENSE, bool AOS = false>
 __global__ void __launch_bounds__(64) small_forward_kernel(const __grid_constant__ P prm, const SmallFwdArgs<T> a) {
     constexpr int I = P::I;
     __shared__ __align__(16) T wsm[P::WPK];
@@ -453,6 +494,7 @@ __global__ void __launch_bounds__(64) small_forward_kernel(const __grid_constant
         double qold = Ctrl::qoldinit, q11 = 1.0, dtpropose = dt;
         bool accept = false;
         int iter = 0, sidx = 0, nrec = 0;
+        const double* rp = a.rp_t ? a.rp_t + b * (int64_t)a.rp_cap : nullptr;
         if (t0 == t1) {   // degenerate span: outputs are u0
             for (; sidx < a.nsave; ++sidx)
 #pragma unroll
@@ -467,8 +509,14 @@ __global__ void __launch_bounds__(64) small_forward_kernel(const __grid_constant
             ++iter;
             const double dtmin_t = fmax(eps_of(t), dtmin0);
             dt = fmin(fmax(fmin(fabs(dt), dtmax), dtmin_t), t1 - t);
+            double rp_next = t1;
+            if (rp) {                                                  // replay: the step ends where the recorded one ended
+                rp_next = naccept < a.rp_cap ? rp[naccept] : t1;
+                if (!(rp_next > t) || !(rp_next <= t1)) rp_next = t1;
+                dt = rp_next - t;
+            }
             if (iter > a.maxiters) { ret = RET_MAXITERS; break; }
-            if (!(dt > dtmin_t) && (t + dt < t1 || !accept) && iter > 1) { ret = RET_DTMIN; break; }
+            if (!rp && !(dt > dtmin_t) && (t + dt < t1 || !accept) && iter > 1) { ret = RET_DTMIN; break; }
             if (dt != dt) { ret = RET_UNSTABLE; break; }
             // ---- perform_step! ----
             const T h = (T)dt;
@@ -518,25 +566,42 @@ __global__ void __launch_bounds__(64) small_forward_kernel(const __grid_constant
             if (EEst != EEst || bad) { ret = RET_UNSTABLE; break; }
             // ---- loopfooter!: PI controller ----
             const double q = pi_q(EEst, qold, q11);
-            accept = EEst <= 1.0;
+            accept = rp ? true : (EEst <= 1.0);
             if (accept) {
                 ++naccept;
                 qold = fmax(EEst, Ctrl::qoldinit);
                 const double dtnew = dt / q;
                 double tnew = t + dt;
-                if (fabs(tnew - t1) < 100.0 * eps_of(fmax(fabs(t), fabs(t1)))) tnew = t1;
+                if (rp) tnew = rp_next;
+                else if (fabs(tnew - t1) < 100.0 * eps_of(fmax(fabs(t), fabs(t1)))) tnew = t1;
                 dtpropose = fmax(fmin(dtmax, fabs(dtnew)), fmax(eps_of(tnew), dtmin0));
                 if (DENSE) {
                     if (nrec >= a.cap) { ret = RET_OVERFLOW; break; }
-                    a.rec_t[(int64_t)nrec * B + b] = t;
-                    T* r = a.rec + (int64_t)nrec * (1 + 8 * I) * B + b;
-                    r[0] = h;
+                    if constexpr (AOS) {
+                        using RL = RecLayout<T, I>;
+                        T tmp[RL::RS];
 #pragma unroll
-                    for (int i = 0; i < I; ++i) r[(int64_t)(1 + i) * B] = uprev[i];
+                        for (int f = 0; f < RL::RS; ++f) tmp[f] = T(0);
+                        rec_put_time(tmp, t);
+                        tmp[RL::DT] = h;
 #pragma unroll
-                    for (int j = 0; j < 7; ++j)
+                        for (int i = 0; i < I; ++i) tmp[RL::U + i] = uprev[i];
 #pragma unroll
-                        for (int i = 0; i < I; ++i) r[(int64_t)(1 + I + j * I + i) * B] = k[j][i];
+                        for (int j = 0; j < 7; ++j)
+#pragma unroll
+                            for (int i = 0; i < I; ++i) tmp[RL::K + j * I + i] = k[j][i];
+                        stv(a.rec + (b * (int64_t)a.cap + nrec) * RL::RS, tmp);
+                    } else {
+                        a.rec_t[(int64_t)nrec * B + b] = t;
+                        T* r = a.rec + (int64_t)nrec * (1 + 8 * I) * B + b;
+                        r[0] = h;
+#pragma unroll
+                        for (int i = 0; i < I; ++i) r[(int64_t)(1 + i) * B] = uprev[i];
+#pragma unroll
+                        for (int j = 0; j < 7; ++j)
+#pragma unroll
+                            for (int i = 0; i < I; ++i) r[(int64_t)(1 + I + j * I + i) * B] = k[j][i];
+                    }
                     ++nrec;
                 }
                 // saveat: dense output inside (t, tnew]  (and t0 itself on the first step)
@@ -553,7 +618,7 @@ __global__ void __launch_bounds__(64) small_forward_kernel(const __grid_constant
                         if (DENSE) {
                             const T e = v - a.target[(b * a.nsave + sidx) * I + i];
                             lsum += (double)e * (double)e;
-                            a.dg[((int64_t)sidx * I + i) * B + b] = (T(2) / (T)((double)I * a.nsave)) * e;
+                            a.dg[AOS ? (b * a.nsave + sidx) * I + i : ((int64_t)sidx * I + i) * B + b] = (T(2) / (T)((double)I * a.nsave)) * e;
                         }
                     }
                     ++sidx;
@@ -570,7 +635,7 @@ __global__ void __launch_bounds__(64) small_forward_kernel(const __grid_constant
 #pragma unroll
                 for (int i = 0; i < I; ++i) {
                     if (a.out) a.out[(b * a.nsave + sidx) * I + i] = T(NAN);
-                    if (DENSE) a.dg[((int64_t)sidx * I + i) * B + b] = T(0);
+                    if (DENSE) a.dg[AOS ? (b * a.nsave + sidx) * I + i : ((int64_t)sidx * I + i) * B + b] = T(0);
                 }
         }
         if (a.stats) a.stats[b] = kanode_stats{naccept, nreject, nf, ret};

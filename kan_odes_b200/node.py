@@ -169,6 +169,30 @@ class KanOde:
             out["fwd_stats"] = Stats.from_raw(fst); out["bwd_stats"] = Stats.from_raw(bst)
         return out
 
+    def loss_grad_replay(self, u0, tspan, saveat, target, fwd_t, bwd_t, abstol=1e-6, reltol=1e-3):
+        """dt-replay: loss / gradient / predictions with the accepted-step END times of another run
+        (`fwd_t`, `bwd_t`: [batch, max_steps], NaN padded — e.g. the fp64 oracle's) instead of the step-size controller."""
+        u0 = self._arr(u0).reshape(-1, self.n)
+        B = u0.shape[0]
+        sa = np.ascontiguousarray(saveat, dtype=np.float64).reshape(-1)
+        target = self._arr(target).reshape(B, sa.size, self.n)
+        fwd_t = np.ascontiguousarray(fwd_t, dtype=np.float64).reshape(B, -1)
+        bwd_t = np.ascontiguousarray(bwd_t, dtype=np.float64).reshape(B, -1)
+        if fwd_t.shape != bwd_t.shape:
+            raise ValueError("fwd_t and bwd_t must have the same [batch, max_steps] shape")
+        loss = self._real(0)
+        grad = np.empty(self.np_, self.dtype); du0 = np.empty_like(u0); out = np.empty_like(target)
+        fst = (abi.Stats * B)(); bst = (abi.Stats * B)()
+        f = self._fn("kanode_loss_grad_replay")
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_void_p,
+                      self._real, self._real, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                      C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = f(self.h, _ptr(u0), B, float(tspan[0]), float(tspan[1]), _ptr(sa), sa.size, _ptr(target), abstol, reltol,
+               _ptr(fwd_t), _ptr(bwd_t), fwd_t.shape[1], C.byref(loss), _ptr(grad), _ptr(du0), _ptr(out), fst, bst)
+        abi.check(self.lib, self.h, rc, "kanode_loss_grad_replay")
+        return dict(loss=float(loss.value), grad=grad, du0=du0, out=out, fwd_stats=Stats.from_raw(fst),
+                    bwd_stats=Stats.from_raw(bst))
+
     def launch_count(self) -> int:
         return int(self.lib.kanode_launch_count(self.h))
 

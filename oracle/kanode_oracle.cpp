@@ -554,12 +554,16 @@ int solve_one(const Model<T>& m, const T* p, const T* u0, double t0, double t1, 
 template <class T>
 int loss_grad_one(const Model<T>& m, const T* p, const T* u0, double t0, double t1, const double* saveat, int nsave,
                   const T* target, const SolveOpts& o, double& loss_sum, T* grad /* [np], overwritten */,
-                  T* du0 /* [n] or null */, kanode_stats& fst, kanode_stats& bst, T* out_opt) {
+                  T* du0 /* [n] or null */, kanode_stats& fst, kanode_stats& bst, T* out_opt,
+                  double* fwd_t = nullptr, double* bwd_t = nullptr, int step_cap = 0) {
     const int n = m.n; const size_t np = m.np; const int N = n + (int)np;
     Dense<T> dense;
     std::vector<T> out((size_t)nsave * n);
     solve_one(m, p, u0, t0, t1, saveat, nsave, o, out.data(), fst, &dense);
     if (out_opt) std::copy(out.begin(), out.end(), out_opt);
+    if (fwd_t) for (int s = 0; s < step_cap; ++s)       // end time of each accepted forward step (dt-replay tooling)
+        fwd_t[s] = s < (int)dense.steps.size() ? (s + 1 < (int)dense.steps.size() ? dense.steps[s + 1].t : dense.t_end) : NAN;
+    if (bwd_t) std::fill(bwd_t, bwd_t + step_cap, (double)NAN);
     // loss = mean(abs2, X - pred)  => dL/dpred = 2 (pred - X) / (n*nsave)
     std::vector<T> dg((size_t)nsave * n);
     double ls = 0;
@@ -589,8 +593,11 @@ int loss_grad_one(const Model<T>& m, const T* p, const T* u0, double t0, double 
         for (int i = 0; i < n; ++i) zz[i] += dg[(size_t)s * n + i];   // lambda += dL/du(t_s)
         return true;
     };
-    auto on_accept = [](double, T, const T*, const T*) {};
+    // accepted adjoint steps: step k starts at tprev_k, so its end time is the start of step k+1 (t0 for the last one)
+    std::vector<double> bstart;
+    auto on_accept = [&](double tprev, T, const T*, const T*) { bstart.push_back(tprev); };
     tsit5_solve<T>(N, z.data(), t1, t0, o, f, preset, affect, on_accept, bst);
+    if (bwd_t) for (int s = 0; s < step_cap && s < (int)bstart.size(); ++s) bwd_t[s] = s + 1 < (int)bstart.size() ? bstart[s + 1] : t0;
     if (du0) std::copy(z.begin(), z.begin() + n, du0);
     std::copy(z.begin() + n, z.end(), grad);
     return 0;
@@ -631,7 +638,8 @@ template <class T> struct Api {
     }
     static int loss_grad(const kanode_desc* d, const T* p, const T* u0, int64_t batch, double t0, double t1,
                          const double* saveat, int nsave, const T* target, double abstol, double reltol,
-                         double* loss, T* grad, T* du0, kanode_stats* fst, kanode_stats* bst, T* out_opt) {
+                         double* loss, T* grad, T* du0, kanode_stats* fst, kanode_stats* bst, T* out_opt,
+                         double* fwd_t = nullptr, double* bwd_t = nullptr, int step_cap = 0) {
         Model<T> m; if (!build_model(d, m)) return KANODE_ERR_INVALID;
         SolveOpts o; o.abstol = abstol; o.reltol = reltol;
         std::vector<double> gsum(m.np, 0.0); double lsum = 0;
@@ -643,7 +651,8 @@ template <class T> struct Api {
                 kanode_stats f, bk; double ls = 0;
                 loss_grad_one(m, p, u0 + b * m.n, t0, t1, saveat, nsave, target + (size_t)b * nsave * m.n, o, ls,
                               g.data(), du0 ? du0 + b * m.n : nullptr, f, bk,
-                              out_opt ? out_opt + (size_t)b * nsave * m.n : nullptr);
+                              out_opt ? out_opt + (size_t)b * nsave * m.n : nullptr,
+                              fwd_t ? fwd_t + (size_t)b * step_cap : nullptr, bwd_t ? bwd_t + (size_t)b * step_cap : nullptr, step_cap);
                 ll += ls; for (size_t i = 0; i < m.np; ++i) gl[i] += (double)g[i];
                 if (fst) fst[b] = f;
                 if (bst) bst[b] = bk;
@@ -682,6 +691,15 @@ size_t kanode_oracle_param_count(const kanode_desc* d) { return param_count(d); 
                                       kanode_stats* bst, T* out_opt) {                                               \
         return Api<T>::loss_grad(d, p, u0, batch, t0, t1, saveat, nsave, target, abstol, reltol, loss, grad, du0,    \
                                  fst, bst, out_opt);                                                                 \
+    }                                                                                                                \
+    /* same, also returning the END times of the accepted forward / adjoint steps ([batch][step_cap], NaN padded) */  \
+    int kanode_oracle_loss_grad_steps_##SUF(const kanode_desc* d, const T* p, const T* u0, int64_t batch, double t0, \
+                                            double t1, const double* saveat, int nsave, const T* target,             \
+                                            double abstol, double reltol, double* loss, T* grad, T* du0,             \
+                                            kanode_stats* fst, kanode_stats* bst, T* out_opt, double* fwd_t,         \
+                                            double* bwd_t, int step_cap) {                                           \
+        return Api<T>::loss_grad(d, p, u0, batch, t0, t1, saveat, nsave, target, abstol, reltol, loss, grad, du0,    \
+                                 fst, bst, out_opt, fwd_t, bwd_t, step_cap);                                         \
     }
 
 ORACLE_DEFINE(f64, double)

@@ -82,7 +82,9 @@ class Oracle:
         st = np.frombuffer(stats, dtype=np.int32).reshape(B, 4).copy()
         return (out, st, step_t) if step_cap else (out, st)
 
-    def loss_grad(self, p, u0, tspan, saveat, target, abstol=1e-6, reltol=1e-3, want_out=False):
+    def loss_grad(self, p, u0, tspan, saveat, target, abstol=1e-6, reltol=1e-3, want_out=False, step_cap=0):
+        """step_cap > 0 additionally returns `fwd_t` / `bwd_t` [B, step_cap]: END times of the accepted forward / adjoint
+        steps (NaN padded) — the sequences kanode_loss_grad_replay takes."""
         u0 = self._a(u0).reshape(-1, self.n); p = self._a(p)
         B = u0.shape[0]
         sa = np.ascontiguousarray(saveat, dtype=np.float64)
@@ -91,16 +93,23 @@ class Oracle:
         grad = np.empty(self.np_, self.dtype); du0 = np.empty_like(u0)
         fst = (abi.Stats * B)(); bst = (abi.Stats * B)()
         out = np.empty((B, sa.size, self.n), self.dtype) if want_out else None
-        rc = self._fn("loss_grad")(C.byref(self.desc), _ptr(p), _ptr(u0), C.c_int64(B), C.c_double(tspan[0]),
-                                   C.c_double(tspan[1]), _ptr(sa), C.c_int(sa.size), _ptr(target),
-                                   C.c_double(abstol), C.c_double(reltol), C.byref(loss), _ptr(grad), _ptr(du0),
-                                   fst, bst, _ptr(out))
+        args = [C.byref(self.desc), _ptr(p), _ptr(u0), C.c_int64(B), C.c_double(tspan[0]), C.c_double(tspan[1]), _ptr(sa),
+                C.c_int(sa.size), _ptr(target), C.c_double(abstol), C.c_double(reltol), C.byref(loss), _ptr(grad),
+                _ptr(du0), fst, bst, _ptr(out)]
+        fwd_t = bwd_t = None
+        if step_cap:
+            fwd_t = np.full((B, step_cap), np.nan); bwd_t = np.full((B, step_cap), np.nan)
+            rc = self._fn("loss_grad_steps")(*args, _ptr(fwd_t), _ptr(bwd_t), C.c_int(step_cap))
+        else:
+            rc = self._fn("loss_grad")(*args)
         assert rc == 0, rc
         f = np.frombuffer(fst, dtype=np.int32).reshape(B, 4).copy()
         b = np.frombuffer(bst, dtype=np.int32).reshape(B, 4).copy()
         res = dict(loss=loss.value, grad=grad, du0=du0, fwd_stats=f, bwd_stats=b)
         if want_out:
             res["out"] = out
+        if step_cap:
+            res["fwd_t"] = fwd_t; res["bwd_t"] = bwd_t
         return res
 
     # small helpers for the unit tests
