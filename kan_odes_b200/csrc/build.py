@@ -14,7 +14,8 @@ OUT = HERE / "libkanode_b200.so"
 BUILD = HERE / "_build"
 COMMON = ["kanode_host.h", "kanode_math.cuh", "kanode_wide_api.h", "../../include/kanode.h"]
 UNITS = {
-    "kanode_api.cu": ["kanode_small.cuh", "kanode_small_ls.cuh", "kanode_generic.cuh"],
+    "kanode_api.cu": ["kanode_small.cuh", "kanode_small_host.h", "kanode_generic.cuh"],
+    "kanode_lg.cu": ["kanode_small.cuh", "kanode_small_host.h", "kanode_small_lg.cuh"],
     "kanode_wide.cu": ["kanode_wide.cuh", "kanode_wsrc.cuh"],
 }
 SOURCES = list(UNITS)

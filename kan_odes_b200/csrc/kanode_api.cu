@@ -13,9 +13,8 @@
 #include <vector>
 
 #include "kanode_host.h"
-#include "kanode_small.cuh"
+#include "kanode_small_host.h"
 #include "kanode_small_ls.cuh"
-#include "kanode_small_lg.cuh"
 #include "kanode_generic.cuh"
 #include "kanode_wide_api.h"
 
@@ -39,101 +38,6 @@ int check_saveat(kanode_handle* h, double t0, double t1, const double* saveat, i
     return 0;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// small-model registry: [I,H,I] chains with compile-time shapes (thread-per-trajectory kernels)
-// ---------------------------------------------------------------------------------------------------------
-struct SmallKey { int I, H, G, norm; };
-bool small_match(const kanode_desc& d, SmallKey& k) {
-    if (d.rhs_kind != KANODE_RHS_CHAIN || d.n_layers != 2) return false;
-    const kanode_layer_desc &a = d.layers[0], &b = d.layers[1];
-    if (a.basis != KANODE_BASIS_RBF || b.basis != KANODE_BASIS_RBF || !a.use_base_act || !b.use_base_act) return false;
-    if (a.grid_len != b.grid_len || a.normalizer != b.normalizer || a.grid_lo != b.grid_lo || a.grid_hi != b.grid_hi ||
-        a.denominator != b.denominator) return false;
-    k = SmallKey{a.in_dims, a.out_dims, a.grid_len, a.normalizer};
-    return true;
-}
-
-template <class T, class P> void fill_small(const kanode_handle* h, P& p) {
-    for (int i = 0; i < P::NP; ++i) p.w[i] = (T)h->params[i];
-    const kanode_layer_desc& s = h->desc.layers[0];
-    const double inv_h = (double)(1.0f / s.denominator);               // Float32 1/h (utils.jl:9)
-    const double sc = KRbfScale<T>::value;
-    p.hs = (T)(inv_h * sc);
-    for (int g = 0; g < P::G; ++g) p.gs[g] = (T)((double)grid_point(s, g) * inv_h * sc);
-    p.dk = (T)(-2.0 * inv_h / sc);
-}
-
-// packed per-hidden-unit weights for the shared-memory kernels (layout: SmallParams::UW), uploaded on demand
-template <class T, class P> int upload_packed(kanode_handle* h, const T** out) {
-    std::vector<T> pk((size_t)P::WPK, T(0));
-    constexpr int I = P::I, H = P::H, G = P::G, NQ = P::NQ;
-    for (int j = 0; j < H; ++j) {
-        T* w = pk.data() + (size_t)j * P::UW;
-        for (int i = 0; i < I; ++i) {
-            for (int g = 0; g < G; ++g) w[i * G + g] = (T)h->params[P::OC1 + (i * G + g) * H + j];
-            w[I * G + i] = (T)h->params[P::OW1 + i * H + j];
-        }
-        for (int g = 0; g < G; ++g)
-            for (int o = 0; o < I; ++o) w[NQ + g * I + o] = (T)h->params[P::OC2 + (j * G + g) * I + o];
-        for (int o = 0; o < I; ++o) w[NQ + G * I + o] = (T)h->params[P::OW2 + j * I + o];
-    }
-    T* d = nullptr;
-    if (sizeof(T) == 4) ENSURE(h, W_WPK32, sizeof(T) * pk.size(), d); else ENSURE(h, W_WPK64, sizeof(T) * pk.size(), d);
-    if (h->wpk_version[sizeof(T) == 4 ? 0 : 1] != h->params_version) {
-        CK(h, cudaMemcpyAsync(d, pk.data(), sizeof(T) * pk.size(), cudaMemcpyHostToDevice, h->stream));
-        CK(h, cudaStreamSynchronize(h->stream));                       // pk is a stack-lifetime staging buffer
-        h->wpk_version[sizeof(T) == 4 ? 0 : 1] = h->params_version;
-    }
-    *out = d;
-    return 0;
-}
-
-// packed weights in LANE blocks for the lane-group backward kernel (layout: LgSmem::LW): block `lig` holds the UPL hidden
-// units of lane `lig`, each in the SmallParams::UW layout
-template <class T, class P, int UPL> int upload_packed_lg(kanode_handle* h, const T** out) {
-    using SMP = LgSmem<T, P, UPL>;
-    constexpr int I = P::I, G = P::G, NQ = P::NQ, LPT = LgGeom<P, UPL>::LPT;
-    T* d = nullptr;
-    const int slot = sizeof(T) == 4 ? 0 : 1;
-    if (slot == 0) ENSURE(h, W_WLG32, sizeof(T) * SMP::WLG, d); else ENSURE(h, W_WLG64, sizeof(T) * SMP::WLG, d);
-    if (h->wlg_version[slot] != h->params_version) {
-        std::vector<T> pk((size_t)SMP::WLG, T(0));
-        for (int l = 0; l < LPT; ++l)
-            for (int u = 0; u < UPL; ++u) {
-                const int j = UPL * l + u;
-                T* w = pk.data() + (size_t)l * SMP::LW + (size_t)u * P::UW;
-                for (int i = 0; i < I; ++i) {
-                    for (int g = 0; g < G; ++g) w[i * G + g] = (T)h->params[P::OC1 + (i * G + g) * P::H + j];
-                    w[I * G + i] = (T)h->params[P::OW1 + i * P::H + j];
-                }
-                for (int g = 0; g < G; ++g)
-                    for (int o = 0; o < I; ++o) w[NQ + g * I + o] = (T)h->params[P::OC2 + (j * G + g) * I + o];
-                for (int o = 0; o < I; ++o) w[NQ + G * I + o] = (T)h->params[P::OW2 + j * I + o];
-            }
-        CK(h, cudaMemcpyAsync(d, pk.data(), sizeof(T) * pk.size(), cudaMemcpyHostToDevice, h->stream));
-        CK(h, cudaStreamSynchronize(h->stream));                       // pk is a stack-lifetime staging buffer
-        h->wlg_version[slot] = h->params_version;
-    }
-    *out = d;
-    return 0;
-}
-
-// Visitor: calls fn.template operator()<P, NORM>() for the instantiation matching the descriptor.
-#define KANODE_SMALL_CASES(X) X(2, 10, 5, NORM_TANH)
-
-template <class T, class Fn> bool small_dispatch(const kanode_handle* h, Fn&& fn, int& rc) {
-    SmallKey k;
-    if (!small_match(h->desc, k)) return false;
-#define X(I_, H_, G_, N_)                                                         \
-    if (k.I == I_ && k.H == H_ && k.G == G_ && k.norm == N_) {                     \
-        rc = fn.template operator()<SmallParams<T, I_, H_, G_>, N_>();             \
-        return true;                                                               \
-    }
-    KANODE_SMALL_CASES(X)
-#undef X
-    return false;
-}
-
 __global__ void __launch_bounds__(256) adam_update_kernel(float* __restrict__ p, const float* __restrict__ grad, float* __restrict__ m,
                                                           float* __restrict__ v, size_t n, float eta, float b1, float b2,
                                                           float eps, float c1, float c2, float gs) {
@@ -145,8 +49,6 @@ __global__ void __launch_bounds__(256) adam_update_kernel(float* __restrict__ p,
     m[i] = mi; v[i] = vi;
     p[i] -= eta * (mi * c1) / (sqrtf(vi * c2) + eps);
 }
-
-inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
 // ---------------------------------------------------------------------------------------------------------
 // templated implementations (T = float | double); all pointers are DEVICE pointers here
@@ -238,59 +140,17 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
     if (B <= 0) { CK(h, cudaMemsetAsync(d_grad_sum, 0, sizeof(T) * h->np, h->stream)); return 0; }
     const double* d_saveat = nullptr;
     if (int rc = put_saveat<T>(h, saveat, nsave, &d_saveat)) return rc;
+    if (h->bwd_lg || d_rp_fwd || d_rp_bwd) {
+        bool handled = false;
+        const int rcl = small_lg_loss_grad<T>(h, d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum, d_grad_sum,
+                                              d_du0, d_fst, d_bst, d_out_opt, d_rp_fwd, d_rp_bwd, rp_cap, &handled);
+        if (handled) return rcl;
+        if (d_rp_fwd || d_rp_bwd) return fail(h, KANODE_ERR_UNSUPPORTED, "dt-replay is implemented by the small-model ensemble kernels only");
+    }
     int rc = 0;
     auto run = [&]<class P, int NORM>() -> int {
         constexpr int I = P::I;
         P prm; fill_small<T>(h, prm);
-        if (h->bwd_lg || d_rp_fwd || d_rp_bwd) {
-            // Lane-group adjoint kernel (kanode_small_lg.cuh): a group of lanes per trajectory, gradient state in registers,
-            // stage factors in shared memory; array-of-structures dense record; per-warp gradient sums reduced in fp64.
-            constexpr int UPL = sizeof(T) == 4 ? 2 : 1, WPB = KANODE_LG_WPB, MINB = sizeof(T) == 4 ? KANODE_LG_MINB : 2;
-            using GM = LgGeom<P, UPL>; using SMP = LgSmem<T, P, UPL>; using RL = RecLayout<T, I>;
-            constexpr int NSLAB = 32;
-            const int cap = h->rec_cap;
-            const int64_t nwarps = (B + GM::TPW - 1) / GM::TPW;
-            const unsigned nblk = (unsigned)((nwarps + WPB - 1) / WPB);
-            T *rec = nullptr, *dg = nullptr, *gpart = nullptr; double* slab = nullptr;
-            int *nsteps = nullptr, *retc = nullptr;
-            ENSURE(h, W_REC, sizeof(T) * (size_t)cap * RL::RS * B, rec);
-            ENSURE(h, W_NSTEPS, sizeof(int) * (size_t)B, nsteps);
-            ENSURE(h, W_RET, sizeof(int) * (size_t)B, retc);
-            ENSURE(h, W_DG, sizeof(T) * (size_t)nsave * I * B, dg);
-            ENSURE(h, W_GPART, sizeof(T) * (size_t)nblk * WPB * P::NP, gpart);
-            ENSURE(h, W_SLAB, sizeof(double) * (size_t)NSLAB * P::NP, slab);
-            SmallFwdArgs<T> a{};
-            if (int rcw = upload_packed<T, P>(h, &a.wpk)) return rcw;
-            a.u0 = d_u0; a.B = B; a.t0 = t0; a.t1 = t1; a.saveat = d_saveat; a.nsave = nsave;
-            a.abstol = (T)abstol; a.reltol = (T)reltol; a.maxiters = 100000; a.out = d_out_opt; a.stats = d_fst;
-            a.rec_t = nullptr; a.rec = rec; a.cap = cap; a.nsteps = nsteps; a.retcode = retc;
-            a.target = d_target; a.dg = dg; a.loss_sum = d_loss_sum; a.rp_t = d_rp_fwd; a.rp_cap = rp_cap;
-            LgBwdArgs<T> bw{};
-            if (int rcw = upload_packed_lg<T, P, UPL>(h, &bw.wpk)) return rcw;
-            bw.B = B; bw.t0 = t0; bw.t1 = t1; bw.saveat = d_saveat; bw.nsave = nsave;
-            bw.abstol = (T)abstol; bw.reltol = (T)reltol; bw.maxiters = h->bwd_maxiters;
-            bw.rec = rec; bw.cap = cap; bw.nsteps = nsteps; bw.retcode = retc; bw.dg = dg; bw.gpart = gpart;
-            bw.du0 = d_du0; bw.stats = d_bst; bw.attempts = nullptr; bw.rp_t = d_rp_bwd; bw.rp_cap = rp_cap;
-            const size_t smem = SMP::bytes(WPB);
-            auto kern = small_backward_lg_kernel<T, P, NORM, UPL, WPB, MINB>;
-            const int abit = sizeof(T) == 4 ? 1 : 2;
-            if (!(h->attr_done & abit)) {
-                CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                h->attr_done |= abit;
-            }
-            cudaEventRecord(h->ev[0], h->stream);
-            small_forward_kernel<T, P, NORM, true, true><<<blocks_for(B, 64), 64, 0, h->stream>>>(prm, a);
-            cudaEventRecord(h->ev[1], h->stream);
-            kern<<<nblk, 32 * WPB, smem, h->stream>>>(prm, bw);
-            cudaEventRecord(h->ev[2], h->stream);
-            reduce_partials_kernel<T><<<dim3(NSLAB, (P::NP + 255) / 256), 256, 0, h->stream>>>(gpart, (int64_t)nblk * WPB, P::NP, slab);
-            reduce_slabs_kernel<T><<<(P::NP + 255) / 256, 256, 0, h->stream>>>(slab, NSLAB, P::NP, d_grad_sum, 1.0);
-            cudaEventRecord(h->ev[3], h->stream);
-            h->launches += 4;
-            h->ev_valid = true;
-            CK(h, cudaGetLastError());
-            return 0;
-        }
         if (d_rp_fwd || d_rp_bwd) return fail(h, KANODE_ERR_UNSUPPORTED, "dt-replay needs the lane-group kernels (KANODE_BWD=1)");
         const int cap = h->rec_cap;
         double* rec_t = nullptr; T *rec = nullptr, *dg = nullptr, *fac = nullptr, *g = nullptr;
@@ -316,10 +176,7 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
         bw.rec_t = rec_t; bw.rec = rec; bw.cap = cap; bw.nsteps = nsteps; bw.retcode = retc; bw.dg = dg;
         bw.fac = nullptr; bw.g = g; bw.du0 = d_du0; bw.stats = d_bst;
         bw.maxiters = h->bwd_maxiters;
-        // the lockstep engine is opt-in (KANODE_LOCKSTEP=1): measured slower than the monolithic kernel on B200 because its
-        // stage records and per-trajectory state round-trip through L2/HBM every step
-        const bool lockstep = h->lockstep > 0 && (int64_t)B * 7 * StageRec<P>::N < (1ll << 31);
-        if (!lockstep) {
+        {
             // Scheduling from the previous call's per-trajectory step counts (same batch size, same dtype): the
             // trajectories predicted to need the most steps get a warp each (small_backward_warp_kernel: the step-end
             // gradient pass is spread over the lanes), launched ahead of the bulk, which follows on a second stream.
@@ -378,44 +235,6 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
             reduce_rows_kernel<T, T><<<P::NP, 256, 0, h->stream>>>(g, B, d_grad_sum, 1.0);
             cudaEventRecord(h->ev[3], h->stream);
             h->launches += 3;
-        } else {
-            // lockstep engine: one (stage kernel, gradient-pass kernel) pair per step attempt of all trajectories
-            constexpr int NITEM = LsItems<P>::NITEM;
-            const size_t nd = 5, ni = 9, nT = (size_t)(3 * I + 7 * I + 1 + NITEM + 7 * StageRec<P>::N);
-            const size_t bytes = sizeof(double) * nd * B + sizeof(int) * (ni * B + 4) + sizeof(T) * nT * B + 64;
-            char* base = nullptr;
-            ENSURE(h, W_LS, bytes, base);
-            LsState<T> st{};
-            double* pd = reinterpret_cast<double*>(base);
-            st.t = pd; st.dt = pd + B; st.dtpropose = pd + 2 * B; st.qold = pd + 3 * B; st.q11 = pd + 4 * B;
-            T* pt = reinterpret_cast<T*>(pd + nd * B);
-            st.lam = pt; pt += (size_t)I * B; st.lprev = pt; pt += (size_t)I * B; st.lnew = pt; pt += (size_t)I * B;
-            st.kl = pt; pt += (size_t)7 * I * B; st.es_l = pt; pt += B; st.es_part = pt; pt += (size_t)NITEM * B;
-            st.rec = pt; pt += (size_t)7 * StageRec<P>::N * B;
-            int* pi = reinterpret_cast<int*>(pt);
-            st.iter = pi; st.sp = pi + B; st.cur = pi + 2 * B; st.naccept = pi + 3 * B; st.nreject = pi + 4 * B;
-            st.nf = pi + 5 * B; st.ret = pi + 6 * B; st.flags = pi + 7 * B; st.ridx = pi + 8 * B; st.active = pi + 9 * B;
-            CK(h, cudaMemsetAsync(st.active, 0, sizeof(int), h->stream));
-            const unsigned nb = blocks_for(B, 128);
-            ls_init_kernel<T, P, NORM><<<nb, 128, 0, h->stream>>>(prm, bw, st);
-            int launches = 4, active = 1, iters = 0;
-            int chunk = nsave + 8;                                         // every save time is a tstop: >= nsave attempts
-            const char* cap_env = std::getenv("KANODE_LS_MAXIT");      // timing experiments only
-            const int it_cap = cap_env ? std::atoi(cap_env) : bw.maxiters + 8;
-            while (active > 0 && iters < it_cap) {
-                for (int k = 0; k < chunk; ++k) {
-                    ls_step_kernel<T, P, NORM><<<blocks_for(B, KANODE_LS_BT), KANODE_LS_BT, 0, h->stream>>>(prm, bw, st);
-                    ls_gphase_kernel<T, P, NORM><<<dim3(nb, NITEM), 128, 0, h->stream>>>(prm, bw, st);
-                }
-                iters += chunk; launches += 2 * chunk;
-                CK(h, cudaMemcpyAsync(&active, st.active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-                CK(h, cudaStreamSynchronize(h->stream));
-                chunk = 4;
-            }
-            cudaEventRecord(h->ev[2], h->stream);
-            ls_reduce_kernel<T><<<P::NP, 256, 0, h->stream>>>(g, st.cur, st.ret, P::NP, B, d_grad_sum);
-            cudaEventRecord(h->ev[3], h->stream);
-            h->launches += launches;
         }
         h->ev_valid = true;
         CK(h, cudaGetLastError());
@@ -588,8 +407,8 @@ int kanode_create(const kanode_desc* desc, int device, void* stream, kanode_hand
     if (!h) return fail(nullptr, KANODE_ERR_NOMEM, "out of host memory");
     h->desc = *desc; h->device = device; h->np = np; h->n = desc->n_state;
     h->params.assign(np, 0.0);
-    if (const char* e = std::getenv("KANODE_LOCKSTEP")) h->lockstep = std::atoi(e);
     if (const char* e = std::getenv("KANODE_BWD")) h->bwd_lg = std::atoi(e);                 // 0: round-1 thread-per-trajectory adjoint (A/B)
+    if (const char* e = std::getenv("KANODE_LG_SHAPE")) h->lg_shape = std::atoi(e);
     if (const char* e = std::getenv("KANODE_BWD_MAXIT")) h->bwd_maxiters = std::atoi(e);     // timing experiments only
     if (const char* e = std::getenv("KANODE_LONG_SLOTS")) h->long_slots = std::atoi(e);
     if (const char* e = std::getenv("KANODE_SCHEDULE")) h->schedule = std::atoi(e);

@@ -55,7 +55,7 @@ struct kanode_handle {
     int rec_cap = 32;
     int64_t order_B[2] = {0, 0};     // batch size the cached launch order (per dtype) was built for; 0 = none
     int schedule = 1;                // 1: reuse last call's step counts to launch long backward solves first
-    int lockstep = -1;               // backward engine for the small path: -1 auto (by batch), 0 monolithic, 1 lockstep
+    int lg_shape = 0;                // launch shape of the lane-group adjoint kernel (KANODE_LG_SHAPE; 0 = default)
     int64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fwd start / bwd start / reduce start / end
     cudaStream_t aux_stream = nullptr;                           // concurrent launch of the predicted-long trajectories

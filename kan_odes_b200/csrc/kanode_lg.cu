@@ -1,0 +1,127 @@
+// kanode_lg.cu — front end of the lane-group adjoint engine for the small-model ensembles (its own translation unit:
+// compiles in parallel with kanode_api.cu).  One training step = dense forward Tsit5 solve (thread per trajectory, record
+// array-of-structures) + interpolating-adjoint backward solve (lane group per trajectory, kanode_small_lg.cuh) + a
+// deterministic fp64 sum of the per-warp gradient partials.
+//
+// Reference call being replaced: Zygote.gradient(loss, p) at Lotka-Volterra/LV_driver_KANODE.jl:284 with
+// loss = mean(abs2, X - predict(p)) (:197-203).
+#include "kanode_small_host.h"
+#include "kanode_small_lg.cuh"
+
+namespace kanode {
+
+// packed weights in LANE blocks for the lane-group backward kernel (layout: LgSmem::LW): block `lig` holds the UPL hidden
+// units of lane `lig`, each in the SmallParams::UW layout
+template <class T, class P, int UPL> int upload_packed_lg(kanode_handle* h, const T** out) {
+    using SMP = LgSmem<T, P, UPL>;
+    constexpr int I = P::I, G = P::G, NQ = P::NQ, LPT = LgGeom<P, UPL>::LPT;
+    T* d = nullptr;
+    const int slot = sizeof(T) == 4 ? 0 : 1;
+    if (slot == 0) ENSURE(h, W_WLG32, sizeof(T) * SMP::WLG, d); else ENSURE(h, W_WLG64, sizeof(T) * SMP::WLG, d);
+    if (h->wlg_version[slot] != h->params_version) {
+        std::vector<T> pk((size_t)SMP::WLG, T(0));
+        for (int l = 0; l < LPT; ++l)
+            for (int u = 0; u < UPL; ++u) {
+                const int j = UPL * l + u;
+                T* w = pk.data() + (size_t)l * SMP::LW + (size_t)u * P::UW;
+                for (int i = 0; i < I; ++i) {                          // w1: index q*I + i (q < G: C1, q = G: W1)
+                    for (int g = 0; g < G; ++g) w[g * I + i] = (T)h->params[P::OC1 + (i * G + g) * P::H + j];
+                    w[G * I + i] = (T)h->params[P::OW1 + i * P::H + j];
+                }
+                for (int g = 0; g < G; ++g)
+                    for (int o = 0; o < I; ++o) w[NQ + g * I + o] = (T)h->params[P::OC2 + (j * G + g) * I + o];
+                for (int o = 0; o < I; ++o) w[NQ + G * I + o] = (T)h->params[P::OW2 + j * I + o];
+            }
+        CK(h, cudaMemcpyAsync(d, pk.data(), sizeof(T) * pk.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));                       // pk is a stack-lifetime staging buffer
+        h->wlg_version[slot] = h->params_version;
+    }
+    *out = d;
+    return 0;
+}
+
+#ifndef KANODE_LG_NSLAB
+#define KANODE_LG_NSLAB 32
+#endif
+
+template <class T>
+int small_lg_loss_grad(kanode_handle* h, const T* d_u0, int64_t B, double t0, double t1, const double* d_saveat, int nsave,
+                       const T* d_target, double abstol, double reltol, double* d_loss_sum, T* d_grad_sum, T* d_du0,
+                       kanode_stats* d_fst, kanode_stats* d_bst, T* d_out_opt, const double* d_rp_fwd, const double* d_rp_bwd,
+                       int rp_cap, bool* handled) {
+    int rc = 0;
+    auto launch = [&]<class P, int NORM, int WPB, int MINB>() -> int {
+        constexpr int I = P::I;
+        P prm; fill_small<T>(h, prm);
+        constexpr int UPL = sizeof(T) == 4 ? 2 : 1;
+        using GM = LgGeom<P, UPL>; using SMP = LgSmem<T, P, UPL>; using RL = RecLayout<T, I>;
+        constexpr int NSLAB = KANODE_LG_NSLAB;
+        const int cap = h->rec_cap;
+        const int64_t nwarps = (B + GM::TPW - 1) / GM::TPW;
+        const unsigned nblk = (unsigned)((nwarps + WPB - 1) / WPB);
+        T *rec = nullptr, *dg = nullptr, *gpart = nullptr; double* slab = nullptr;
+        int *nsteps = nullptr, *retc = nullptr;
+        ENSURE(h, W_REC, sizeof(T) * (size_t)cap * RL::RS * B, rec);
+        ENSURE(h, W_NSTEPS, sizeof(int) * (size_t)B, nsteps);
+        ENSURE(h, W_RET, sizeof(int) * (size_t)B, retc);
+        ENSURE(h, W_DG, sizeof(T) * (size_t)nsave * I * B, dg);
+        ENSURE(h, W_GPART, sizeof(T) * (size_t)nblk * WPB * P::NP, gpart);
+        ENSURE(h, W_SLAB, sizeof(double) * (size_t)NSLAB * P::NP, slab);
+        SmallFwdArgs<T> a{};
+        if (int rcw = upload_packed<T, P>(h, &a.wpk)) return rcw;
+        a.u0 = d_u0; a.B = B; a.t0 = t0; a.t1 = t1; a.saveat = d_saveat; a.nsave = nsave;
+        a.abstol = (T)abstol; a.reltol = (T)reltol; a.maxiters = 100000; a.out = d_out_opt; a.stats = d_fst;
+        a.rec_t = nullptr; a.rec = rec; a.cap = cap; a.nsteps = nsteps; a.retcode = retc;
+        a.target = d_target; a.dg = dg; a.loss_sum = d_loss_sum; a.rp_t = d_rp_fwd; a.rp_cap = rp_cap;
+        LgBwdArgs<T> bw{};
+        if (int rcw = upload_packed_lg<T, P, UPL>(h, &bw.wpk)) return rcw;
+        bw.B = B; bw.t0 = t0; bw.t1 = t1; bw.saveat = d_saveat; bw.nsave = nsave;
+        bw.abstol = (T)abstol; bw.reltol = (T)reltol; bw.maxiters = h->bwd_maxiters;
+        bw.rec = rec; bw.cap = cap; bw.nsteps = nsteps; bw.retcode = retc; bw.dg = dg; bw.gpart = gpart;
+        bw.du0 = d_du0; bw.stats = d_bst; bw.attempts = nullptr; bw.rp_t = d_rp_bwd; bw.rp_cap = rp_cap;
+        const size_t smem = SMP::bytes(WPB);
+        auto kern = small_backward_lg_kernel<T, P, NORM, UPL, WPB, MINB>;
+        const unsigned abit = sizeof(T) == 4 ? 1u : 2u;                  // once per handle = per device and launch shape
+        if (!(h->attr_done & abit)) {
+            CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            h->attr_done |= abit;
+        }
+        cudaEventRecord(h->ev[0], h->stream);
+        small_forward_kernel<T, P, NORM, true, true><<<blocks_for(B, 64), 64, 0, h->stream>>>(prm, a);
+        cudaEventRecord(h->ev[1], h->stream);
+        kern<<<nblk, 32 * WPB, smem, h->stream>>>(prm, bw);
+        cudaEventRecord(h->ev[2], h->stream);
+        reduce_partials_kernel<T><<<dim3(NSLAB, (P::NP + 255) / 256), 256, 0, h->stream>>>(gpart, (int64_t)nblk * WPB, P::NP, slab);
+        reduce_slabs_kernel<T><<<(P::NP + 255) / 256, 256, 0, h->stream>>>(slab, NSLAB, P::NP, d_grad_sum, 1.0);
+        cudaEventRecord(h->ev[3], h->stream);
+        h->launches += 4;
+        h->ev_valid = true;
+        CK(h, cudaGetLastError());
+        return 0;
+    };
+    auto run = [&]<class P, int NORM>() -> int {
+        // launch shapes (warps per block, blocks per SM the kernel is compiled for): the default comes from B200 measurements
+        // (profiles/); KANODE_LG_SHAPE selects another one for A/B runs
+        if constexpr (sizeof(T) == 4) {
+            switch (h->lg_shape) {
+                case 1: return launch.template operator()<P, NORM, 4, 2>();
+                case 2: return launch.template operator()<P, NORM, 5, 2>();
+                case 3: return launch.template operator()<P, NORM, 3, 3>();
+                default: return launch.template operator()<P, NORM, KANODE_LG_WPB, KANODE_LG_MINB>();
+            }
+        } else {
+            return launch.template operator()<P, NORM, 4, 2>();
+        }
+    };
+    *handled = small_dispatch<T>(h, run, rc);
+    return rc;
+}
+
+template int small_lg_loss_grad<float>(kanode_handle*, const float*, int64_t, double, double, const double*, int, const float*, double,
+                                       double, double*, float*, float*, kanode_stats*, kanode_stats*, float*, const double*,
+                                       const double*, int, bool*);
+template int small_lg_loss_grad<double>(kanode_handle*, const double*, int64_t, double, double, const double*, int, const double*, double,
+                                        double, double*, double*, double*, kanode_stats*, kanode_stats*, double*, const double*,
+                                        const double*, int, bool*);
+
+}  // namespace kanode

@@ -1132,7 +1132,7 @@ __global__ void __launch_bounds__(KANODE_BWD_BT, LAT ? 1 : KANODE_BWD_MINB) smal
 // changing parameters, so the same trajectories are the long ones): a trajectory with more than mean+4 attempts is
 // appended to long_list (up to `cap` of them) and flagged so that the bulk launch skips it.
 // sched[0] = sum of attempts of the previous call, sched[1] = entries in long_list (may exceed cap; clamp when used).
-__global__ void __launch_bounds__(256) mark_long_kernel(const int* __restrict__ attempts, int64_t B, const unsigned long long* sched_sum,
+static __global__ void __launch_bounds__(256) mark_long_kernel(const int* __restrict__ attempts, int64_t B, const unsigned long long* sched_sum,
                                                         int* long_count, int cap, int* __restrict__ long_list,
                                                         unsigned char* __restrict__ long_flag) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1145,7 +1145,7 @@ __global__ void __launch_bounds__(256) mark_long_kernel(const int* __restrict__ 
     }
     long_flag[b] = f;
 }
-__global__ void clamp_count_kernel(int* c, int cap) { if (*c > cap) *c = cap; }
+static __global__ void clamp_count_kernel(int* c, int cap) { if (*c > cap) *c = cap; }
 
 // ------------------------------------------------------------------------------------------------------
 // batch RHS / VJP (kanode_rhs, kanode_vjp)

@@ -7,18 +7,22 @@
 //   * lane `lig` owns hidden units j = UPL*lig .. UPL*lig+UPL-1 and the 2*UPL*I*(G+1) gradient components that touch
 //     them (layer 2: C2[(j,g),o], W2[j,o]; layer 1: C1[(i,g),j], W1[i,j]) — the gradient state g lives in REGISTERS
 //     for the whole solve (240 values per trajectory = 48 per lane); nothing per-trajectory is kept in HBM;
-//   * the rank-1 factors of dg/dt a stage produces for those components (RBF/SiLU features of the lane's own hidden
-//     units, its hidden cotangents) are computed ONCE per stage evaluation by the lane that owns them and parked in a
-//     lane-private shared-memory slice until the step-end pass consumes them: no recomputation of activations in the
-//     step-end pass, no MUFU work done twice;
-//   * what the whole group needs of a stage (dense-output state y(t_s), its 12 input features and their derivatives)
-//     depends only on t_s, not on lambda, so all 7 stages are prepared up front, one stage per lane, and broadcast
-//     through shared memory;
+//   * an adjoint RHS evaluation splits into a lambda-INDEPENDENT part A (hidden pre-activations of y(t_s), RBF/SiLU
+//     features c2 of the lane's hidden units, the local Jacobian pieces J2 = d f_o / d h_j and dh = d h_j / d y_i) and a
+//     tiny lambda-dependent part B (hbar_j = sum_o ls_o J2[o][j], dl = -sum_j hbar_j dh_j, summed over the group by
+//     shuffles).  The stage loop is software-pipelined: A of stage s+1 is issued next to the serial chain B of stage s;
+//   * Tsit5 has c6 = c7 = 1 and the first stage time of an accepted step is the last one of the step before, so an
+//     attempt has only FIVE new stage times: part A (and the input features, one stage time per lane) is evaluated
+//     5 times per attempt instead of 7, and the step-end pass runs over 6 feature blocks with merged weights;
+//   * the rank-1 factors of dg/dt (features c2 in a lane-private shared-memory slice, hbar, stage adjoints) are parked
+//     in shared memory until the step-end pass consumes them: no recomputation of activations, no MUFU work twice;
+//   * the two dense-forward records around t live in shared memory (refilled one attempt ahead of use), the next
+//     lambda jump (save time, dL/du) is prefetched into registers: no global-memory latency inside an attempt;
 //   * the sequential part of a Runge-Kutta attempt (lambda stages, error norm of lambda, PI controller, accept/reject,
 //     tstops, jumps) is replicated on the lanes of the group from bit-identical inputs, so they agree on every branch;
 //     cross-lane sums (hidden -> input cotangent, error norm) are all-gathers by warp shuffle summed in a fixed order.
-// The dense forward record is array-of-structures (one 80-byte record per accepted step) so a lane fetches a step with
-// five 16-byte loads.  Per-warp gradient sums go to `gpart`; reduce_partials_kernel adds them in a fixed order in fp64.
+// The dense forward record is array-of-structures (one 80-byte record per accepted step).  Per-warp gradient sums go to
+// `gpart`; reduce_partials_kernel adds them in a fixed order in fp64.
 //
 // Reference semantics are those of kanode_small.cuh (same formulas; summation order differs at rounding level):
 //   InterpolatingAdjoint backward solve on z=[lambda; g], tstops + jumps at the save times, FSAL re-evaluation after a
@@ -67,34 +71,58 @@ template <class P, int UPL_> struct LgGeom {
     static constexpr int LPT = H / UPL;                 // lanes per trajectory
     static_assert(LPT <= 32, "group wider than a warp");
     static constexpr int TPW = 32 / LPT;                // trajectories per warp
-    static constexpr int NQ1 = I * (G + 1);             // input features of one stage
-    static constexpr int SB = UPL * (G + 1);            // layer-2 factor block of one lane and one stage
-    static constexpr int F1S = 2 * NQ1;                 // per stage: features then their input derivatives
+    static constexpr int NB = 6;                        // distinct stage times of a Tsit5 attempt (c6 = c7 = 1)
+    static constexpr int NQ1 = I * (G + 1);             // input features of one stage time, index q*I + i (q = G: SiLU)
+    static constexpr int SB = UPL * (G + 1);            // layer-2 factor block of one lane and one stage time
+    static constexpr int F1S = 2 * NQ1;                 // per stage time: features then their input derivatives
     static constexpr int NC2 = I * SB, NC1 = UPL * NQ1; // gradient components per lane: layer 2, layer 1
-    static_assert(NC2 + NC1 <= 7 * SB, "g scratch must fit into the consumed factor blocks");
-    static constexpr int FACN = 7 * SB + 7 * UPL;       // factors per lane: c2[7][SB] then hb[7][UPL]
+    static_assert((1 + I) * SB + NC1 <= (NB - 1) * SB, "g scratch must fit into the factor blocks 1..NB-2");
+    static constexpr int FACN = NB * SB + 7 * UPL;      // factors per lane: c2[NB][SB] then hb[7][UPL]
 };
+
+// weight image of one hidden unit (UW values, SmallParams::UW): [w1: q*I + i (q < G: C1[(i,q),j]; q = G: W1[i,j])] then
+// [w2: g*I + o (C2[(j,g),o]; g = G: W2[j,o])]
 
 // shared-memory plan of one block, in units of T (every region a multiple of 16 bytes)
 template <class T, class P, int UPL> struct LgSmem {
     using GM = LgGeom<P, UPL>;
+    using RL = RecLayout<T, P::I>;
     static constexpr int V = 16 / (int)sizeof(T);
     static constexpr int up(int x) { return (x + V - 1) / V * V; }
     // lane stride of the factor slices: padded so that the 16-byte accesses of a quarter warp hit distinct banks
     static constexpr int FACL = (sizeof(T) == 4) ? (up(GM::FACN) % 8 == 4 ? up(GM::FACN) : up(GM::FACN) + 4)
                                                  : (up(GM::FACN) % 4 == 2 ? up(GM::FACN) : up(GM::FACN) + 2);
-    static constexpr int F1W = GM::TPW * 7 * GM::F1S;   // per warp: input features of the 7 stages of each trajectory
-    static constexpr int LSW = up(GM::TPW * 7 * GM::I); // per warp: stage adjoints lambda_s of each trajectory
-    static constexpr int PER_WARP = 32 * FACL + up(F1W) + LSW;
+    static constexpr int HBN = up(7 * UPL);             // vector read of the 7 hidden cotangents of a lane
+    static_assert(GM::NB * GM::SB + HBN <= FACL, "hbar vector read stays inside the lane slice");
+    static constexpr int F1W = GM::TPW * GM::NB * GM::F1S;   // per warp: input features of the stage times of each trajectory
+    static constexpr int LSS = up(7 * GM::I);           // per trajectory: stage adjoints lambda_s
+    static constexpr int LSW = GM::TPW * LSS;
+    static constexpr int RCW = GM::TPW * 2 * RL::RS;    // per trajectory: the two dense-forward records around t
+    static constexpr int PER_WARP = 32 * FACL + up(F1W) + LSW + RCW;
     // packed weights in LANE blocks: lane `lig` of a group reads [UPL][P::UW] at lig*LW; the pad makes the 16-byte
     // accesses of the lanes of a group hit distinct banks (upload_packed_lg builds the same image in global memory)
     static constexpr int LW = UPL * P::UW + V;
     static constexpr int WLG = GM::LPT * LW;
     static constexpr int BAROFF = up(WLG);              // mbarrier (16 bytes) behind the weights
     static constexpr int WOFF = BAROFF + V;
-    static constexpr int F1OFF = 32 * FACL, LSOFF = F1OFF + up(F1W);   // offsets inside a warp's slice
+    static constexpr int F1OFF = 32 * FACL, LSOFF = F1OFF + up(F1W), RCOFF = LSOFF + LSW;   // offsets inside a warp's slice
     static constexpr size_t bytes(int warps) { return sizeof(T) * (size_t)(WOFF + warps * PER_WARP); }
 };
+
+// error-norm ratio a/b: fp32 = one MUFU.RCP and one FMUL (b >= abstol > 0, far from the denormal range)
+__device__ __forceinline__ float kratio(float a, float b) { return a * krcp(b); }
+__device__ __forceinline__ double kratio(double a, double b) { return a / b; }
+
+// Step-end weights of a per-stage quantity x[s*stride + off]: feature blocks 0..NB-2 carry stage k, block NB-1 carries the
+// two stages that share the last stage time.  cb = (-h) b_s x_s, ct = (-h) btilde_s x_s.
+template <class T, int NB, int N>
+__device__ __forceinline__ void lg_merge(const T (&x)[N], int stride, int off, T mh, T (&cb)[NB], T (&ct)[NB]) {
+#pragma unroll
+    for (int k = 0; k < NB - 1; ++k) { const T v = x[k * stride + off]; cb[k] = (mh * Tab<T>::b(k)) * v; ct[k] = (mh * Tab<T>::bt(k)) * v; }
+    const T v5 = x[(NB - 1) * stride + off], v6 = x[NB * stride + off];
+    cb[NB - 1] = mh * (Tab<T>::b(NB - 1) * v5 + Tab<T>::b(NB) * v6);
+    ct[NB - 1] = mh * (Tab<T>::bt(NB - 1) * v5 + Tab<T>::bt(NB) * v6);
+}
 
 template <class T, class P, int NORM, int UPL, int WPB, int MINB>
 __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const __grid_constant__ P prm, const LgBwdArgs<T> a) {
@@ -102,9 +130,11 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
     using SMP = LgSmem<T, P, UPL>;
     using RL = RecLayout<T, P::I>;
     constexpr int I = P::I, G = P::G, NP = P::NP, NZ = I + NP;
-    constexpr int LPT = GM::LPT, TPW = GM::TPW, NQ1 = GM::NQ1, SB = GM::SB, F1S = GM::F1S, UW = P::UW;
-    constexpr int V = RL::V, RS = RL::RS, FACL = SMP::FACL;
-    static_assert(NQ1 % V == 0 && SB % V == 0 && UW % V == 0 && ((G + 1) * I) % V == 0, "vector widths");
+    constexpr int LPT = GM::LPT, TPW = GM::TPW, NQ1 = GM::NQ1, SB = GM::SB, F1S = GM::F1S, UW = P::UW, NB = GM::NB;
+    constexpr int V = RL::V, RS = RL::RS, FACL = SMP::FACL, NPIECE = RS / V, LSS = SMP::LSS, HBN = SMP::HBN;
+    constexpr int NW2 = (G + 1) * I;
+    static_assert(NQ1 % V == 0 && SB % V == 0 && UW % V == 0 && NW2 % V == 0, "vector widths");
+    static_assert(NPIECE <= LPT && NQ1 / V <= LPT, "one 16-byte piece of a record / feature block per lane");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* wsm = reinterpret_cast<T*>(smem_raw);
@@ -114,11 +144,12 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / LPT, lig = lane - grp * LPT, gbase = grp * LPT;
     T* wbase = wsm + SMP::WOFF + warp * SMP::PER_WARP;
-    T* fac = wbase + lane * FACL;                                   // this lane's factors: c2[7][SB] | hb[7][UPL]
+    T* fac = wbase + lane * FACL;                                   // this lane's factors: c2[NB][SB] | hb[7][UPL]
     const bool gvalid = grp < TPW;                                  // the 32 - TPW*LPT spare lanes only read
     const int gsl = gvalid ? grp : TPW - 1;
-    T* f1g = wbase + SMP::F1OFF + gsl * 7 * F1S;                     // this trajectory's input features [7][F1S]
-    T* lsg = wbase + SMP::LSOFF + gsl * 7 * I;   // its stage adjoints [7][I]
+    T* f1g = wbase + SMP::F1OFF + gsl * NB * F1S;                    // this trajectory's input features [NB][F1S]
+    T* lsg = wbase + SMP::LSOFF + gsl * LSS;                         // its stage adjoints [7][I]
+    T* rcg = wbase + SMP::RCOFF + gsl * 2 * RS;                      // its record window: record r sits in slot r & 1
     const int j0 = UPL * lig;                                       // first hidden unit of this lane
     const T* wlane = wsm + lig * SMP::LW;                           // its packed weights [UPL][UW]
 
@@ -157,24 +188,38 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
     const T abstol = a.abstol, reltol = a.reltol;
     const T* rbase = a.rec + bq * (int64_t)a.cap * RS;
     const T* dgb = a.dg + bq * (int64_t)a.nsave * I;
-    int ridx = nsteps > 0 ? nsteps - 1 : 0;                         // per-lane hint into the dense record
 
-    // ---- P1: y = sol(ts) and the input features of one stage slot, computed by ONE lane of the group ----
-    auto prep_slot = [&](int slot, double ts) {
-        double rt = rec_get_time(rbase + (int64_t)ridx * RS);
-        while (ts < rt && ridx > 0) { --ridx; rt = rec_get_time(rbase + (int64_t)ridx * RS); }
-        while (ridx + 1 < nsteps) {                                 // right-continuous at step boundaries
-            const double rn = rec_get_time(rbase + (int64_t)(ridx + 1) * RS);
-            if (!(ts >= rn)) break;
-            ++ridx; rt = rn;
-        }
+    // ---- window on the dense forward record: records ridx (holds t) and ridx-1 in shared memory ----
+    const bool haspiece = gvalid && lig < NPIECE;
+    int ridx = nsteps > 0 ? nsteps - 1 : 0;
+    double rt0 = rec_get_time(rbase + (int64_t)ridx * RS), rt1 = 0.0, pend_rt = 0.0;
+    bool prev_ok = false, pend = false;
+    T pv[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) pv[e] = T(0);
+    auto window_load = [&](int r) {                                 // blocking: this lane's piece of record r
+        if (haspiece) { T v[V]; ldv(rbase + (int64_t)r * RS + lig * V, v); stv(rcg + (r & 1) * RS + lig * V, v); }
+    };
+    window_load(ridx);
+    if (ridx > 0) { rt1 = rec_get_time(rbase + (int64_t)(ridx - 1) * RS); window_load(ridx - 1); prev_ok = true; }
+
+    // ---- P1: y = sol(ts) and the input features of one stage time, computed by ONE lane of the group ----
+    auto prep_block = [&](int blk, double ts) {
         T r[RS];
-        ldv(rbase + (int64_t)ridx * RS, r);
+        double rt;
+        if (ts >= rt0 || ridx == 0) { ldv(rcg + (ridx & 1) * RS, r); rt = rt0; }
+        else if (prev_ok && (ts >= rt1 || ridx == 1)) { ldv(rcg + ((ridx - 1) & 1) * RS, r); rt = rt1; }
+        else {                                                      // outside the window (rare): search the record in global memory
+            int k = ridx - 1;
+            double rk = rec_get_time(rbase + (int64_t)k * RS);
+            while (ts < rk && k > 0) { --k; rk = rec_get_time(rbase + (int64_t)k * RS); }
+            ldv(rbase + (int64_t)k * RS, r); rt = rk;
+        }
         const T rdt = r[RL::DT];
         T th;
         if constexpr (sizeof(T) == 4) th = (T)(ts - rt) / rdt; else th = (T)((ts - rt) / (double)rdt);
         T bw[7]; interp_weights(th, bw);
-        T fd[F1S];                                                  // f[NQ1] then df[NQ1]
+        T fd[F1S];                                                  // f[NQ1] then df[NQ1], index q*I + i
 #pragma unroll
         for (int i = 0; i < I; ++i) {
             T acc = T(0);
@@ -186,20 +231,18 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
             T rb[G], rdb[G];
             rbf_eval<true>(prm, xn, rb, rdb);
 #pragma unroll
-            for (int g = 0; g < G; ++g) { fd[i * G + g] = rb[g]; fd[NQ1 + i * G + g] = rdb[g] * dn; }   // utils.jl:18 * d(arg)/d(xn) * norm'
-            swish_both(y, fd[I * G + i], fd[NQ1 + I * G + i]);
+            for (int g = 0; g < G; ++g) { fd[g * I + i] = rb[g]; fd[NQ1 + g * I + i] = rdb[g] * dn; }   // utils.jl:18 * d(arg)/d(xn) * norm'
+            swish_both(y, fd[G * I + i], fd[NQ1 + G * I + i]);
         }
-        stv(f1g + slot * F1S, fd);
+        stv(f1g + blk * F1S, fd);
     };
 
-    // ---- P2 + S: one adjoint RHS evaluation at stage slot `slot` with stage adjoint ls (all lanes of the group) ----
-    //   dl = -(df/du)^T ls;  this lane's factors (features of its hidden units, their cotangents) -> fac, ls -> lsg
-    auto stage_eval = [&](int slot, const T (&ls)[I], T (&dl)[I]) {
+    // ---- A: lambda-independent part of an adjoint RHS evaluation at stage time `blk`:
+    //   features c2 of this lane's hidden units -> fac block `blk`;  J2[u][o] = d f_o / d h_j,  dh[u][i] = d h_j / d y_i ----
+    auto stage_a = [&](int blk, T (&J2)[UPL][I], T (&dh)[UPL][I]) {
         T fd[F1S];
-        ldv(f1g + slot * F1S, fd);
-        T pu[I], c2[SB];
-#pragma unroll
-        for (int i = 0; i < I; ++i) pu[i] = T(0);
+        ldv(f1g + blk * F1S, fd);
+        T c2[SB];
 #pragma unroll
         for (int u = 0; u < UPL; ++u) {
             const T* w = wlane + u * UW;
@@ -210,13 +253,19 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
             for (int q = 0; q + 1 < NQ1; q += 2) kfma2(h0, h1, w1[q], w1[q + 1], fd[q], fd[q + 1]);
             if constexpr (NQ1 % 2 == 1) h0 += w1[NQ1 - 1] * fd[NQ1 - 1];
             const T h = h0 + h1;
-            T dh[I];                                                // d h / d y_i
+            if constexpr (I == 2) {                                 // (dh_0, dh_1) in one packed accumulator
+                T d0 = T(0), d1 = T(0);
 #pragma unroll
-            for (int i = 0; i < I; ++i) {
-                T acc = w1[I * G + i] * fd[NQ1 + I * G + i];
+                for (int q = 0; q <= G; ++q) kfma2(d0, d1, w1[2 * q], w1[2 * q + 1], fd[NQ1 + 2 * q], fd[NQ1 + 2 * q + 1]);
+                dh[u][0] = d0; dh[u][1] = d1;
+            } else {
 #pragma unroll
-                for (int g = 0; g < G; ++g) acc += w1[i * G + g] * fd[NQ1 + i * G + g];
-                dh[i] = acc;
+                for (int i = 0; i < I; ++i) {
+                    T acc = T(0);
+#pragma unroll
+                    for (int q = 0; q <= G; ++q) acc += w1[q * I + i] * fd[NQ1 + q * I + i];
+                    dh[u][i] = acc;
+                }
             }
             const T xn = normalize<NORM>(h);
             const T dn = normalize_deriv<NORM>(xn);
@@ -226,22 +275,41 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
 #pragma unroll
             for (int g = 0; g < G; ++g) c2[u * (G + 1) + g] = rb[g];
             c2[u * (G + 1) + G] = s;
-            T w2[(G + 1) * I];
+            T w2[NW2];
             ldv(w + NQ1, w2);
+            if constexpr (I == 2) {
+                T a0 = T(0), a1 = T(0);
+#pragma unroll
+                for (int g = 0; g < G; ++g) kfma2b(a0, a1, w2[2 * g], w2[2 * g + 1], rdb[g]);
+                J2[u][0] = a0 * dn + w2[2 * G] * ds;
+                J2[u][1] = a1 * dn + w2[2 * G + 1] * ds;
+            } else {
+#pragma unroll
+                for (int o = 0; o < I; ++o) {
+                    T acc = T(0);
+#pragma unroll
+                    for (int g = 0; g < G; ++g) acc += w2[g * I + o] * rdb[g];
+                    J2[u][o] = acc * dn + w2[G * I + o] * ds;
+                }
+            }
+        }
+        stv(fac + blk * SB, c2);
+    };
+
+    // ---- B: lambda-dependent part with stage adjoint ls: hbar of this lane's units -> fac, dl = -(df/du)^T ls ----
+    auto stage_b = [&](int slot, const T (&ls)[I], const T (&J2)[UPL][I], const T (&dh)[UPL][I], T (&dl)[I]) {
+        T pu[I];
+#pragma unroll
+        for (int i = 0; i < I; ++i) pu[i] = T(0);
+#pragma unroll
+        for (int u = 0; u < UPL; ++u) {
             T hb = T(0);
 #pragma unroll
-            for (int o = 0; o < I; ++o) {                           // J2[o] = d f_o / d h_j; hb = sum_o ls[o] * J2[o]
-                T acc = T(0);
+            for (int o = 0; o < I; ++o) hb += ls[o] * J2[u][o];
+            fac[NB * SB + slot * UPL + u] = hb;
 #pragma unroll
-                for (int g = 0; g < G; ++g) acc += w2[g * I + o] * rdb[g];
-                const T j2 = acc * dn + w2[G * I + o] * ds;
-                hb += ls[o] * j2;
-            }
-            fac[7 * SB + slot * UPL + u] = hb;
-#pragma unroll
-            for (int i = 0; i < I; ++i) pu[i] += hb * dh[i];
+            for (int i = 0; i < I; ++i) pu[i] += hb * dh[u][i];
         }
-        stv(fac + slot * SB, c2);
 #pragma unroll
         for (int i = 0; i < I; ++i) {                               // all-gather over the group, summed in lane order
             T tot = T(0);
@@ -263,12 +331,25 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
 
     double t = t1;
     int sp = a.nsave - 1;                                           // next preset (save) time, descending
+    double nxt_t = 0.0;                                             // a.saveat[sp] and dL/du(t_sp), fetched one jump ahead
+    T nxt_dg[I];
+#pragma unroll
+    for (int i = 0; i < I; ++i) nxt_dg[i] = T(0);
+    auto fetch_jump = [&]() {
+        if (sp >= 0) {
+            nxt_t = a.saveat[sp];
+#pragma unroll
+            for (int i = 0; i < I; ++i) nxt_dg[i] = dgb[sp * I + i];
+        }
+    };
+    fetch_jump();
     auto apply_jumps = [&](double tt) {
         bool mod = false;
-        while (sp >= 0 && a.saveat[sp] == tt) {
+        while (sp >= 0 && nxt_t == tt) {
 #pragma unroll
-            for (int i = 0; i < I; ++i) lam[i] += dgb[sp * I + i];
+            for (int i = 0; i < I; ++i) lam[i] += nxt_dg[i];
             --sp; mod = true;
+            fetch_jump();
         }
         return mod;
     };
@@ -276,11 +357,14 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
 #pragma unroll
     for (int i = 0; i < I; ++i) lprev[i] = lam[i];
 
+    T J0[UPL][I], D0[UPL][I];                                       // part A at the current time t (block 0), carried over attempts
     double dt;                                                      // |dt|; integration runs in -t
     {   // ---- FSAL evaluation + ode_determine_initdt on the augmented state (g(T) = 0: its scale is abstol) ----
-        if (lig == 0 && gvalid) prep_slot(0, t1);
+        __syncwarp();                                               // record window visible to the group
+        if (lig == 0 && gvalid) prep_block(0, t1);
         __syncwarp();
-        stage_eval(0, lam, kl[0]);
+        stage_a(0, J0, D0);
+        stage_b(0, lam, J0, D0, kl[0]);
         __syncwarp();
         T sk[I], s0 = T(0), s1 = T(0);
 #pragma unroll
@@ -300,7 +384,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
                 for (int m = 0; m < SB; ++m) { const T x = (lam[o] * c0[m]) / abstol; ga += x * x; }
 #pragma unroll
             for (int u = 0; u < UPL; ++u) {
-                const T hb0 = fac[7 * SB + u];
+                const T hb0 = fac[NB * SB + u];
 #pragma unroll
                 for (int m = 0; m < NQ1; ++m) { const T x = (hb0 * f0[m]) / abstol; ga += x * x; }
             }
@@ -312,9 +396,11 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
         T l1[I], fv[I];
 #pragma unroll
         for (int i = 0; i < I; ++i) l1[i] = lam[i] - (T)dt0 * kl[0][i];
-        if (lig == 0 && gvalid) prep_slot(1, t1 - dt0);
+        if (lig == 0 && gvalid) prep_block(1, t1 - dt0);
         __syncwarp();
-        stage_eval(1, l1, fv);
+        T J1[UPL][I], D1[UPL][I];
+        stage_a(1, J1, D1);
+        stage_b(1, l1, J1, D1, fv);
         __syncwarp();
         nf = 3;                                                     // two evaluations + the package's repeated f0
         T s2 = T(0);
@@ -330,7 +416,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
                 for (int m = 0; m < SB; ++m) { const T x = (l1[o] * c1[m] - lam[o] * c0[m]) / abstol; gb += x * x; }
 #pragma unroll
             for (int u = 0; u < UPL; ++u) {
-                const T hb0 = fac[7 * SB + u], hb1 = fac[7 * SB + UPL + u];
+                const T hb0 = fac[NB * SB + u], hb1 = fac[NB * SB + UPL + u];
 #pragma unroll
                 for (int m = 0; m < NQ1; ++m) { const T x = (hb1 * f1[m] - hb0 * f0[m]) / abstol; gb += x * x; }
             }
@@ -354,7 +440,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
             else dt = dtpropose;
         }
         ++iter;
-        const double tstop = (sp >= 0) ? fmax(a.saveat[sp], t0) : t0;
+        const double tstop = (sp >= 0) ? fmax(nxt_t, t0) : t0;
         const double dtmin_t = fmax(eps_of(t), dtmin0);
         dt = fmin(fmax(fmin(fabs(dt), dtmax), dtmin_t), t - tstop);
         double rp_next = t0;
@@ -368,36 +454,60 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
             else if (!rp && !(dt > dtmin_t) && (t - dt > tstop || !accept) && iter > 1) { ret = RET_DTMIN; done = true; }
             else if (dt != dt) { ret = RET_UNSTABLE; done = true; }
         }
-        // ---- P1: stage states and input features of the 7 stages, one stage per lane ----
+        // ---- P1: input features at the NEW stage times 1..NB-1 (block 0 = time t is carried over), one stage time per lane ----
 #pragma unroll
-        for (int r0 = 0; r0 < 7; r0 += LPT) {
-            const int slot = r0 + lig;
-            if (slot < 7 && gvalid) prep_slot(slot, t - tab_c(slot) * dt);
+        for (int r0 = 1; r0 < NB; r0 += LPT) {
+            const int blk = r0 + lig;
+            if (blk < NB && gvalid) prep_block(blk, t - tab_c(blk) * dt);
         }
         __syncwarp();
         // ---- perform_step! on lambda; after a jump the FSAL stage is re-evaluated (stage 0 of the same loop; without a
-        // jump the recomputed stage 0 equals the FSAL value, the evaluation count follows the package) ----
+        // jump the recomputed stage 0 equals the FSAL value, the evaluation count follows the package).
+        // Software pipeline: part A of stage s+1 next to the serial chain of stage s. ----
         const T h = (T)(-dt);
         T lnew[I];
 #pragma unroll
         for (int i = 0; i < I; ++i) lnew[i] = lprev[i];
+        T Jc[UPL][I], Dc[UPL][I];
+#pragma unroll
+        for (int u = 0; u < UPL; ++u)
+#pragma unroll
+            for (int i = 0; i < I; ++i) { Jc[u][i] = J0[u][i]; Dc[u][i] = D0[u][i]; }
 #pragma unroll 1
-        for (int s = 0; s < 7; ++s) {
+        for (int s = 0; s < NB - 1; ++s) {
+            T Jn[UPL][I], Dn[UPL][I];
+            stage_a(s + 1, Jn, Dn);
             T ls[I], ks[I];
 #pragma unroll
             for (int i = 0; i < I; ++i) {
                 T acc = T(0);
 #pragma unroll
-                for (int j = 0; j < 6; ++j) acc += Tab<T>::a(s, j) * kl[j][i];
+                for (int j = 0; j < NB - 2; ++j) acc += Tab<T>::a(s, j) * kl[j][i];
                 ls[i] = lprev[i] + h * acc;
             }
-            stage_eval(s, ls, ks);
+            stage_b(s, ls, Jc, Dc, ks);
 #pragma unroll
-            for (int j = 0; j < 7; ++j)
+            for (int j = 0; j < NB - 1; ++j)
                 if (j == s) {
 #pragma unroll
                     for (int i = 0; i < I; ++i) kl[j][i] = ks[i];
                 }
+#pragma unroll
+            for (int u = 0; u < UPL; ++u)
+#pragma unroll
+                for (int i = 0; i < I; ++i) { Jc[u][i] = Jn[u][i]; Dc[u][i] = Dn[u][i]; }
+        }
+#pragma unroll
+        for (int s = NB - 1; s < 7; ++s) {                          // stages 6 and 7 share the stage time t - dt (block NB-1)
+            T ls[I];
+#pragma unroll
+            for (int i = 0; i < I; ++i) {
+                T acc = T(0);
+#pragma unroll
+                for (int j = 0; j < s; ++j) acc += Tab<T>::a(s, j) * kl[j][i];
+                ls[i] = lprev[i] + h * acc;
+            }
+            stage_b(s, ls, Jc, Dc, kl[s]);
             if (s == 6) {
 #pragma unroll
                 for (int i = 0; i < I; ++i) lnew[i] = ls[i];
@@ -421,82 +531,77 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
             bad |= (lnew[i] != lnew[i]);
         }
         // ---- step-end pass over this lane's gradient components: g_new = g + (-h) sum_s b_s kv_s, error term with btilde.
-        // kv_s is rank one: (stage adjoint or hidden cotangent of stage s) x (feature of stage s); the features are the
-        // ones the stage evaluations parked in shared memory.  g_new goes to the already consumed factor blocks. ----
+        // kv_s is rank one: (stage adjoint or hidden cotangent of stage s) x (feature of the stage time of s); the features
+        // are the ones part A parked in shared memory; stages 6 and 7 share a feature block (their weights are merged).
+        // g_new goes to the already consumed factor blocks 1..NB-2. ----
         T esl = T(0);
         const T mh = -h;
         auto fin = [&](T gold, T vb, T vt) {
             const T gn = gold + vb;
             const T sc = abstol + kmax(kabs(gold), kabs(gn)) * reltol;
-            const T r = kdiv(vt, sc);
+            const T r = kratio(vt, sc);
             esl += r * r;
             return gn;
         };
         {   // layer 2: component (o, m): kv_s = lambda_s[o] * c2_s[m]
-            T ab[7][I], at[7][I];
+            T lsv[LSS];
+            ldv(lsg, lsv);
+            T ab[I][NB], at[I][NB];
 #pragma unroll
-            for (int s = 0; s < 7; ++s)
-#pragma unroll
-                for (int o = 0; o < I; ++o) {
-                    const T l = lsg[s * I + o];
-                    ab[s][o] = (mh * Tab<T>::b(s)) * l; at[s][o] = (mh * Tab<T>::bt(s)) * l;
-                }
+            for (int o = 0; o < I; ++o) lg_merge<T, NB>(lsv, I, o, mh, ab[o], at[o]);
 #pragma unroll
             for (int m0 = 0; m0 < SB; m0 += V) {
-                T c[7][V];
+                T c[NB][V];
 #pragma unroll
-                for (int s = 0; s < 7; ++s) ldv(fac + s * SB + m0, c[s]);
+                for (int k = 0; k < NB; ++k) ldv(fac + k * SB + m0, c[k]);
                 T vb[I][V], vt[I][V];
 #pragma unroll
                 for (int o = 0; o < I; ++o)
 #pragma unroll
                     for (int e = 0; e < V; ++e) { vb[o][e] = T(0); vt[o][e] = T(0); }
 #pragma unroll
-                for (int s = 0; s < 7; ++s)
+                for (int k = 0; k < NB; ++k)
 #pragma unroll
                     for (int o = 0; o < I; ++o)
 #pragma unroll
-                        for (int e = 0; e < V; ++e) kfma2b(vb[o][e], vt[o][e], ab[s][o], at[s][o], c[s][e]);
+                        for (int e = 0; e < V; ++e) kfma2b(vb[o][e], vt[o][e], ab[o][k], at[o][k], c[k][e]);
 #pragma unroll
                 for (int o = 0; o < I; ++o) {
                     T gn[V];
 #pragma unroll
                     for (int e = 0; e < V; ++e) gn[e] = fin(g2[o][m0 + e], vb[o][e], vt[o][e]);
-                    stv(fac + o * SB + m0, gn);
+                    stv(fac + (1 + o) * SB + m0, gn);
                 }
             }
         }
         {   // layer 1: component (u, m): kv_s = hbar_s[j0+u] * f_s[m]
-            T ab[7][UPL], at[7][UPL];
+            T hbv[HBN];
+            ldv(fac + NB * SB, hbv);
+            T ab[UPL][NB], at[UPL][NB];
 #pragma unroll
-            for (int s = 0; s < 7; ++s)
-#pragma unroll
-                for (int u = 0; u < UPL; ++u) {
-                    const T hb = fac[7 * SB + s * UPL + u];
-                    ab[s][u] = (mh * Tab<T>::b(s)) * hb; at[s][u] = (mh * Tab<T>::bt(s)) * hb;
-                }
+            for (int u = 0; u < UPL; ++u) lg_merge<T, NB>(hbv, UPL, u, mh, ab[u], at[u]);
 #pragma unroll
             for (int m0 = 0; m0 < NQ1; m0 += V) {
-                T c[7][V];
+                T c[NB][V];
 #pragma unroll
-                for (int s = 0; s < 7; ++s) ldv(f1g + s * F1S + m0, c[s]);
+                for (int k = 0; k < NB; ++k) ldv(f1g + k * F1S + m0, c[k]);
                 T vb[UPL][V], vt[UPL][V];
 #pragma unroll
                 for (int u = 0; u < UPL; ++u)
 #pragma unroll
                     for (int e = 0; e < V; ++e) { vb[u][e] = T(0); vt[u][e] = T(0); }
 #pragma unroll
-                for (int s = 0; s < 7; ++s)
+                for (int k = 0; k < NB; ++k)
 #pragma unroll
                     for (int u = 0; u < UPL; ++u)
 #pragma unroll
-                        for (int e = 0; e < V; ++e) kfma2b(vb[u][e], vt[u][e], ab[s][u], at[s][u], c[s][e]);
+                        for (int e = 0; e < V; ++e) kfma2b(vb[u][e], vt[u][e], ab[u][k], at[u][k], c[k][e]);
 #pragma unroll
                 for (int u = 0; u < UPL; ++u) {
                     T gn[V];
 #pragma unroll
                     for (int e = 0; e < V; ++e) gn[e] = fin(g1[u][m0 + e], vb[u][e], vt[u][e]);
-                    stv(fac + GM::NC2 + u * NQ1 + m0, gn);
+                    stv(fac + (1 + I) * SB + u * NQ1 + m0, gn);
                 }
             }
         }
@@ -506,6 +611,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
         // ---- loopfooter!: PI controller ----
         const double q = pi_q(EEst, qold, q11);
         accept = rp ? true : (EEst <= 1.0);
+        __syncwarp();                                               // every lane of the group is past its reads of f1g
         if (!done) {
             if (accept) {
                 ++naccept;
@@ -517,11 +623,21 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
                 dtpropose = fmax(fmin(dtmax, fabs(dtnew)), fmax(eps_of(tnew), dtmin0));
                 t = tnew;
 #pragma unroll
-                for (int o = 0; o < I; ++o) ldv(fac + o * SB, g2[o]);           // commit g_new
+                for (int o = 0; o < I; ++o) ldv(fac + (1 + o) * SB, g2[o]);      // commit g_new
 #pragma unroll
-                for (int u = 0; u < UPL; ++u) ldv(fac + GM::NC2 + u * NQ1, g1[u]);
+                for (int u = 0; u < UPL; ++u) ldv(fac + (1 + I) * SB + u * NQ1, g1[u]);
 #pragma unroll
                 for (int i = 0; i < I; ++i) lam[i] = lnew[i];
+                // the last stage time of this step is the first of the next one: block NB-1 -> block 0
+                {
+                    T c5[SB];
+                    ldv(fac + (NB - 1) * SB, c5); stv(fac, c5);
+                    if (gvalid && lig < NQ1 / V) { T f5[V]; ldv(f1g + (NB - 1) * F1S + lig * V, f5); stv(f1g + lig * V, f5); }
+#pragma unroll
+                    for (int u = 0; u < UPL; ++u)
+#pragma unroll
+                        for (int i = 0; i < I; ++i) { J0[u][i] = Jc[u][i]; D0[u][i] = Dc[u][i]; }
+                }
                 modified = apply_jumps(t);
 #pragma unroll
                 for (int i = 0; i < I; ++i) lprev[i] = lam[i];
@@ -530,7 +646,28 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
                 ++nreject;
             }
         }
-        __syncwarp();                                               // factor / feature slices are rewritten by the next attempt
+        // ---- record window: land the piece fetched one attempt ago, then slide when t left the upper record ----
+        if (pend) {
+            if (haspiece) stv(rcg + ((ridx - 1) & 1) * RS + lig * V, pv);
+            rt1 = pend_rt; prev_ok = true; pend = false;
+        }
+        if (t < rt0 && ridx > 0 && !done) {
+            if (prev_ok && (t >= rt1 || ridx == 1)) { --ridx; rt0 = rt1; }
+            else {                                                  // t jumped over a whole record: search, reload (blocking)
+                int k = ridx - 1;
+                double rk = rec_get_time(rbase + (int64_t)k * RS);
+                while (t < rk && k > 0) { --k; rk = rec_get_time(rbase + (int64_t)k * RS); }
+                ridx = k; rt0 = rk;
+                window_load(ridx);
+            }
+            prev_ok = false;
+            if (ridx > 0) {                                         // the record below: in flight during the next attempt
+                if (haspiece) ldv(rbase + (int64_t)(ridx - 1) * RS + lig * V, pv);
+                pend_rt = rec_get_time(rbase + (int64_t)(ridx - 1) * RS);
+                pend = true;
+            }
+        }
+        __syncwarp();                                               // factor / feature / record slices are rewritten by the next attempt
     }
 
     // ---- results: per-warp gradient sum (fixed order over the trajectories of the warp), du0, statistics ----
@@ -557,7 +694,10 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
             T tot = T(0);
 #pragma unroll
             for (int k = 0; k < TPW; ++k) tot += shfl_t(v, lig + k * LPT);
-            if (lane < LPT) gp[P::OC1 + m * P::H + j0 + u] = tot;   // C1 then W1 are contiguous: column m of [H x NQ1]
+            if (lane < LPT) {
+                const int q = m / I, i = m % I, j = j0 + u;          // feature index m = q*I + i
+                gp[q < G ? P::OC1 + (i * G + q) * P::H + j : P::OW1 + i * P::H + j] = tot;
+            }
         }
     if (active && lig == 0) {
         if (skipped) { nf = 0; naccept = 0; nreject = 0; }
