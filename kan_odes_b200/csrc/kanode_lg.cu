@@ -14,7 +14,7 @@ namespace kanode {
 // units of lane `lig`, each in the SmallParams::UW layout
 template <class T, class P, int UPL> int upload_packed_lg(kanode_handle* h, const T** out) {
     using SMP = LgSmem<T, P, UPL>;
-    constexpr int I = P::I, G = P::G, NQ = P::NQ, LPT = LgGeom<P, UPL>::LPT;
+    constexpr int I = P::I, G = P::G, NQ = P::NQ, LPT = LgGeom<T, P, UPL>::LPT;
     T* d = nullptr;
     const int slot = sizeof(T) == 4 ? 0 : 1;
     if (slot == 0) ENSURE(h, W_WLG32, sizeof(T) * SMP::WLG, d); else ENSURE(h, W_WLG64, sizeof(T) * SMP::WLG, d);
@@ -50,11 +50,10 @@ int small_lg_loss_grad(kanode_handle* h, const T* d_u0, int64_t B, double t0, do
                        kanode_stats* d_fst, kanode_stats* d_bst, T* d_out_opt, const double* d_rp_fwd, const double* d_rp_bwd,
                        int rp_cap, bool* handled) {
     int rc = 0;
-    auto launch = [&]<class P, int NORM, int WPB, int MINB>() -> int {
+    auto launch = [&]<class P, int NORM, int UPL, int WPB, int MINB>() -> int {
         constexpr int I = P::I;
         P prm; fill_small<T>(h, prm);
-        constexpr int UPL = sizeof(T) == 4 ? 2 : 1;
-        using GM = LgGeom<P, UPL>; using SMP = LgSmem<T, P, UPL>; using RL = RecLayout<T, I>;
+        using GM = LgGeom<T, P, UPL>; using SMP = LgSmem<T, P, UPL>; using RL = RecLayout<T, I>;
         constexpr int NSLAB = KANODE_LG_NSLAB;
         const int cap = h->rec_cap;
         const int64_t nwarps = (B + GM::TPW - 1) / GM::TPW;
@@ -79,6 +78,24 @@ int small_lg_loss_grad(kanode_handle* h, const T* d_u0, int64_t B, double t0, do
         bw.abstol = (T)abstol; bw.reltol = (T)reltol; bw.maxiters = h->bwd_maxiters;
         bw.rec = rec; bw.cap = cap; bw.nsteps = nsteps; bw.retcode = retc; bw.dg = dg; bw.gpart = gpart;
         bw.du0 = d_du0; bw.stats = d_bst; bw.attempts = nullptr; bw.rp_t = d_rp_bwd; bw.rp_cap = rp_cap;
+        // launch order from the previous call's per-warp iteration counts (same batch size, dtype and launch shape)
+        const int slot = sizeof(T) == 4 ? 0 : 1;
+        const int64_t nslots = (int64_t)nblk * WPB;
+        bool ordered = false;
+        if (h->schedule && !d_rp_bwd && nwarps >= 2048 && nslots < (1ll << 30)) {
+            int *att = nullptr, *ord = nullptr;
+            ENSURE(h, W_ATT, sizeof(int) * (size_t)nslots * 2, att);
+            ENSURE(h, W_ORDER, sizeof(int) * (size_t)nslots * 2, ord);
+            att += (size_t)slot * nslots; ord += (size_t)slot * nslots;
+            if (h->order_B[slot] == B) {
+                lg_order_kernel<<<1, 1024, 0, h->stream>>>(att, (int)nslots, ord);
+                ++h->launches;
+                bw.order = ord; ordered = true;
+            }
+            bw.wattempts = att;
+            h->order_B[slot] = B;
+        }
+        (void)ordered;
         const size_t smem = SMP::bytes(WPB);
         auto kern = small_backward_lg_kernel<T, P, NORM, UPL, WPB, MINB>;
         const unsigned abit = sizeof(T) == 4 ? 1u : 2u;                  // once per handle = per device and launch shape
@@ -104,13 +121,14 @@ int small_lg_loss_grad(kanode_handle* h, const T* d_u0, int64_t B, double t0, do
         // (profiles/); KANODE_LG_SHAPE selects another one for A/B runs
         if constexpr (sizeof(T) == 4) {
             switch (h->lg_shape) {
-                case 1: return launch.template operator()<P, NORM, 4, 2>();
-                case 2: return launch.template operator()<P, NORM, 5, 2>();
-                case 3: return launch.template operator()<P, NORM, 3, 3>();
-                default: return launch.template operator()<P, NORM, KANODE_LG_WPB, KANODE_LG_MINB>();
+                case 1: return launch.template operator()<P, NORM, 2, 4, 3>();
+                case 4: return launch.template operator()<P, NORM, 1, 4, 4>();
+                case 5: return launch.template operator()<P, NORM, 1, 4, 3>();
+                case 6: return launch.template operator()<P, NORM, 1, 8, 2>();
+                default: return launch.template operator()<P, NORM, 2, KANODE_LG_WPB, KANODE_LG_MINB>();
             }
         } else {
-            return launch.template operator()<P, NORM, 4, 2>();
+            return launch.template operator()<P, NORM, 1, 4, 2>();
         }
     };
     *handled = small_dispatch<T>(h, run, rc);

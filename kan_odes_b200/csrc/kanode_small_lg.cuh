@@ -39,7 +39,7 @@
 #define KANODE_LG_WPB 4          // warps per block
 #endif
 #ifndef KANODE_LG_MINB
-#define KANODE_LG_MINB 3         // resident blocks per SM the kernel is compiled for (fp32)
+#define KANODE_LG_MINB 2         // resident blocks per SM the kernel is compiled for (fp32)
 #endif
 
 namespace kanode {
@@ -63,9 +63,14 @@ template <class T> struct LgBwdArgs {
     int* attempts;           // [B] or null
     const double* rp_t;      // replay: [B][rp_cap] end times of the accepted backward steps (descending), NaN-padded; or null
     int rp_cap;
+    // launch order (optional): warp slot -> logical warp (= block of TPW consecutive trajectories).  Warps predicted to need
+    // many attempts (from the previous call's counts) are started first, so their serial chain of steps does not end up as the
+    // tail of the launch.  gpart is indexed by the LOGICAL warp: the gradient sum does not depend on the order.
+    const int* order;        // [warp slots] or null (identity)
+    int* wattempts;          // [warp slots] loop iterations of each logical warp (feeds the next call's order), or null
 };
 
-template <class P, int UPL_> struct LgGeom {
+template <class T, class P, int UPL_> struct LgGeom {
     static constexpr int I = P::I, H = P::H, G = P::G, UPL = UPL_;
     static_assert(H % UPL == 0, "hidden width must split evenly over the lanes of a group");
     static constexpr int LPT = H / UPL;                 // lanes per trajectory
@@ -73,7 +78,9 @@ template <class P, int UPL_> struct LgGeom {
     static constexpr int TPW = 32 / LPT;                // trajectories per warp
     static constexpr int NB = 6;                        // distinct stage times of a Tsit5 attempt (c6 = c7 = 1)
     static constexpr int NQ1 = I * (G + 1);             // input features of one stage time, index q*I + i (q = G: SiLU)
-    static constexpr int SB = UPL * (G + 1);            // layer-2 factor block of one lane and one stage time
+    static constexpr int SBR = UPL * (G + 1);           // layer-2 factors of one lane and one stage time ...
+    static constexpr int VT = 16 / (int)sizeof(T);
+    static constexpr int SB = (SBR + VT - 1) / VT * VT; // ... padded to whole 16-byte vectors (pad entries stay zero)
     static constexpr int F1S = 2 * NQ1;                 // per stage time: features then their input derivatives
     static constexpr int NC2 = I * SB, NC1 = UPL * NQ1; // gradient components per lane: layer 2, layer 1
     static_assert((1 + I) * SB + NC1 <= (NB - 1) * SB, "g scratch must fit into the factor blocks 1..NB-2");
@@ -85,7 +92,7 @@ template <class P, int UPL_> struct LgGeom {
 
 // shared-memory plan of one block, in units of T (every region a multiple of 16 bytes)
 template <class T, class P, int UPL> struct LgSmem {
-    using GM = LgGeom<P, UPL>;
+    using GM = LgGeom<T, P, UPL>;
     using RL = RecLayout<T, P::I>;
     static constexpr int V = 16 / (int)sizeof(T);
     static constexpr int up(int x) { return (x + V - 1) / V * V; }
@@ -112,6 +119,56 @@ template <class T, class P, int UPL> struct LgSmem {
 // error-norm ratio a/b: fp32 = one MUFU.RCP and one FMUL (b >= abstol > 0, far from the denormal range)
 __device__ __forceinline__ float kratio(float a, float b) { return a * krcp(b); }
 __device__ __forceinline__ double kratio(double a, double b) { return a / b; }
+// packed fp32 add (FADD2): d0 = a0 + b0, d1 = a1 + b1
+__device__ __forceinline__ void kadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    unsigned long long ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rd));
+}
+template <class T> __device__ __forceinline__ void kadd2(T& d0, T& d1, T a0, T a1, T b0, T b1) { d0 = a0 + b0; d1 = a1 + b1; }
+
+// PI controller of the lane-group kernel.  fp64 follows pi_q (kanode_math.cuh) to the letter: its step sequence equals the
+// oracle's.  fp32 evaluates the same formulas with MUFU reciprocals / ex2 and no double-precision division: the fp32 solve
+// cannot reproduce fp64 step sequences anyway, a relative change of 1e-7 in dt is far inside that.
+//   q11 = EEst^beta1,  q = clamp((q11 / qold^beta2) / gamma, 1/qmax, 1/qmin)   [EXT OrdinaryDiffEqCore 1.9.0, FastPower 1.1.0]
+__device__ __forceinline__ float fastlog2f_rcp(float x) {
+    const uint32_t bits = __float_as_uint(x);
+    const float e = (float)((bits & 0x7F800000u) >> 23);
+    float s, fe;
+    if (bits & 0x00400000u) { s = __uint_as_float((bits & 0x007FFFFFu) | 0x3f000000u) - 1.0f; fe = e - 126.0f; }
+    else                    { s = __uint_as_float((bits & 0x007FFFFFu) | 0x3f800000u) - 1.0f; fe = e - 127.0f; }
+    return fe + s * (0.338953f * s + 2.198599f) * krcp(s + 1.523692f);
+}
+template <class T> struct LgCtrl;
+template <> struct LgCtrl<double> {
+    using Q = double;                                  // type of qold / q11
+    static __device__ __forceinline__ double eest(double es, int nz) { return sqrt(es / (double)nz); }
+    static __device__ __forceinline__ double q(double EEst, double qold, double& q11) { return pi_q(EEst, qold, q11); }
+    static __device__ __forceinline__ double grow(double dt, double q) { return dt / q; }                         // dt / q
+    static __device__ __forceinline__ double shrink(double dt, double q11) { return dt / fmin(1.0 / Ctrl::qmin, q11 / Ctrl::gamma); }
+    static __device__ __forceinline__ double qold_next(double EEst) { return fmax(EEst, Ctrl::qoldinit); }
+};
+template <> struct LgCtrl<float> {
+    using Q = float;
+    static __device__ __forceinline__ float eest(float es, int nz) {
+        float r;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(es * (1.0f / (float)nz)));
+        return r;
+    }
+    static __device__ __forceinline__ float q(float EEst, float qold, float& q11) {
+        if (EEst == 0.0f) return (float)(1.0 / Ctrl::qmax);
+        q11 = kex2(Ctrl::beta1 * fastlog2f_rcp(EEst));
+        const float qq = q11 * krcp(kex2(Ctrl::beta2 * fastlog2f_rcp(qold)));
+        return fmaxf((float)(1.0 / Ctrl::qmax), fminf((float)(1.0 / Ctrl::qmin), qq * (float)(1.0 / Ctrl::gamma)));
+    }
+    static __device__ __forceinline__ double grow(double dt, float q) { return dt * (double)krcp(q); }
+    static __device__ __forceinline__ double shrink(double dt, float q11) {
+        return dt * (double)krcp(fminf((float)(1.0 / Ctrl::qmin), q11 * (float)(1.0 / Ctrl::gamma)));
+    }
+    static __device__ __forceinline__ float qold_next(float EEst) { return fmaxf(EEst, (float)Ctrl::qoldinit); }
+};
 
 // Step-end weights of a per-stage quantity x[s*stride + off]: feature blocks 0..NB-2 carry stage k, block NB-1 carries the
 // two stages that share the last stage time.  cb = (-h) b_s x_s, ct = (-h) btilde_s x_s.
@@ -126,11 +183,11 @@ __device__ __forceinline__ void lg_merge(const T (&x)[N], int stride, int off, T
 
 template <class T, class P, int NORM, int UPL, int WPB, int MINB>
 __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const __grid_constant__ P prm, const LgBwdArgs<T> a) {
-    using GM = LgGeom<P, UPL>;
+    using GM = LgGeom<T, P, UPL>;
     using SMP = LgSmem<T, P, UPL>;
     using RL = RecLayout<T, P::I>;
     constexpr int I = P::I, G = P::G, NP = P::NP, NZ = I + NP;
-    constexpr int LPT = GM::LPT, TPW = GM::TPW, NQ1 = GM::NQ1, SB = GM::SB, F1S = GM::F1S, UW = P::UW, NB = GM::NB;
+    constexpr int LPT = GM::LPT, TPW = GM::TPW, NQ1 = GM::NQ1, SB = GM::SB, SBR = GM::SBR, F1S = GM::F1S, UW = P::UW, NB = GM::NB;
     constexpr int V = RL::V, RS = RL::RS, FACL = SMP::FACL, NPIECE = RS / V, LSS = SMP::LSS, HBN = SMP::HBN;
     constexpr int NW2 = (G + 1) * I;
     static_assert(NQ1 % V == 0 && SB % V == 0 && UW % V == 0 && NW2 % V == 0, "vector widths");
@@ -153,7 +210,8 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
     const int j0 = UPL * lig;                                       // first hidden unit of this lane
     const T* wlane = wsm + lig * SMP::LW;                           // its packed weights [UPL][UW]
 
-    const int64_t wg = (int64_t)blockIdx.x * WPB + warp;            // global warp index
+    const int64_t wslot = (int64_t)blockIdx.x * WPB + warp;         // launch position of this warp
+    const int64_t wg = a.order ? a.order[wslot] : wslot;            // logical warp: trajectories wg*TPW ..
     const int64_t b = wg * TPW + grp;
     const bool active = gvalid && b < a.B;
     const int64_t bq = active ? b : 0;                              // clamped: idle groups read trajectory 0, never write
@@ -186,6 +244,8 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
     const double t0 = a.t0, t1 = a.t1, dtmax = fabs(t1 - t0);
     const double dtmin0 = fmax(eps_of(t0), eps_of(t1));
     const T abstol = a.abstol, reltol = a.reltol;
+    const T inv_abstol = T(1) / abstol;
+    auto by_abstol = [&](T x) { if constexpr (sizeof(T) == 4) return x * inv_abstol; else return x / abstol; };
     const T* rbase = a.rec + bq * (int64_t)a.cap * RS;
     const T* dgb = a.dg + bq * (int64_t)a.nsave * I;
 
@@ -217,7 +277,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
         }
         const T rdt = r[RL::DT];
         T th;
-        if constexpr (sizeof(T) == 4) th = (T)(ts - rt) / rdt; else th = (T)((ts - rt) / (double)rdt);
+        if constexpr (sizeof(T) == 4) th = kratio((T)(ts - rt), rdt); else th = (T)((ts - rt) / (double)rdt);
         T bw[7]; interp_weights(th, bw);
         T fd[F1S];                                                  // f[NQ1] then df[NQ1], index q*I + i
 #pragma unroll
@@ -243,6 +303,8 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
         T fd[F1S];
         ldv(f1g + blk * F1S, fd);
         T c2[SB];
+#pragma unroll
+        for (int m = SBR; m < SB; ++m) c2[m] = T(0);
 #pragma unroll
         for (int u = 0; u < UPL; ++u) {
             const T* w = wlane + u * UW;
@@ -331,13 +393,14 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
 
     double t = t1;
     int sp = a.nsave - 1;                                           // next preset (save) time, descending
-    double nxt_t = 0.0;                                             // a.saveat[sp] and dL/du(t_sp), fetched one jump ahead
+    // a.saveat[sp] (needed right at the next loop header: fetched TWO jumps ahead) and dL/du(t_sp) (needed at the end of the
+    // attempt that reaches t_sp: fetched one jump ahead)
+    double nxt_t = sp >= 0 ? a.saveat[sp] : 0.0, nxt2_t = sp >= 1 ? a.saveat[sp - 1] : 0.0;
     T nxt_dg[I];
 #pragma unroll
     for (int i = 0; i < I; ++i) nxt_dg[i] = T(0);
     auto fetch_jump = [&]() {
         if (sp >= 0) {
-            nxt_t = a.saveat[sp];
 #pragma unroll
             for (int i = 0; i < I; ++i) nxt_dg[i] = dgb[sp * I + i];
         }
@@ -349,6 +412,8 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
 #pragma unroll
             for (int i = 0; i < I; ++i) lam[i] += nxt_dg[i];
             --sp; mod = true;
+            nxt_t = nxt2_t;
+            if (sp >= 1) nxt2_t = a.saveat[sp - 1];
             fetch_jump();
         }
         return mod;
@@ -381,12 +446,12 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
 #pragma unroll
             for (int o = 0; o < I; ++o)
 #pragma unroll
-                for (int m = 0; m < SB; ++m) { const T x = (lam[o] * c0[m]) / abstol; ga += x * x; }
+                for (int m = 0; m < SB; ++m) { const T x = by_abstol(lam[o] * c0[m]); ga += x * x; }
 #pragma unroll
             for (int u = 0; u < UPL; ++u) {
                 const T hb0 = fac[NB * SB + u];
 #pragma unroll
-                for (int m = 0; m < NQ1; ++m) { const T x = (hb0 * f0[m]) / abstol; ga += x * x; }
+                for (int m = 0; m < NQ1; ++m) { const T x = by_abstol(hb0 * f0[m]); ga += x * x; }
             }
         }
         s1 += group_sum(ga);
@@ -413,12 +478,12 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
 #pragma unroll
             for (int o = 0; o < I; ++o)
 #pragma unroll
-                for (int m = 0; m < SB; ++m) { const T x = (l1[o] * c1[m] - lam[o] * c0[m]) / abstol; gb += x * x; }
+                for (int m = 0; m < SB; ++m) { const T x = by_abstol(l1[o] * c1[m] - lam[o] * c0[m]); gb += x * x; }
 #pragma unroll
             for (int u = 0; u < UPL; ++u) {
                 const T hb0 = fac[NB * SB + u], hb1 = fac[NB * SB + UPL + u];
 #pragma unroll
-                for (int m = 0; m < NQ1; ++m) { const T x = (hb1 * f1[m] - hb0 * f0[m]) / abstol; gb += x * x; }
+                for (int m = 0; m < NQ1; ++m) { const T x = by_abstol(hb1 * f1[m] - hb0 * f0[m]); gb += x * x; }
             }
         }
         s2 += group_sum(gb);
@@ -427,7 +492,9 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
         const double dt1 = (mx <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / 5.0);
         dt = fmax(dtmin0, fmin(fmin(100.0 * dt0, dt1), dtmax));
     }
-    double qold = Ctrl::qoldinit, q11 = 1.0, dtpropose = dt;
+    using LC = LgCtrl<T>;
+    typename LC::Q qold = (typename LC::Q)Ctrl::qoldinit, q11 = (typename LC::Q)1;
+    double dtpropose = dt;
     bool accept = false, modified = false;
     int iter = 0;
     if (!(t > t0)) done = true;
@@ -436,7 +503,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
     while (__any_sync(0xffffffffu, !done)) {
         // ---- loopheader! ----
         if (iter > 0) {
-            if (!accept) dt = dt / fmin(1.0 / Ctrl::qmin, q11 / Ctrl::gamma);
+            if (!accept) dt = LC::shrink(dt, q11);
             else dt = dtpropose;
         }
         ++iter;
@@ -526,7 +593,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
             for (int j = 0; j < 7; ++j) ut += Tab<T>::bt(j) * kl[j][i];
             ut *= h;
             const T sc = abstol + kmax(kabs(lprev[i]), kabs(lnew[i])) * reltol;
-            const T r = ut / sc;
+            const T r = kratio(ut, sc);
             es += r * r;
             bad |= (lnew[i] != lnew[i]);
         }
@@ -536,12 +603,14 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
         // g_new goes to the already consumed factor blocks 1..NB-2. ----
         T esl = T(0);
         const T mh = -h;
-        auto fin = [&](T gold, T vb, T vt) {
-            const T gn = gold + vb;
-            const T sc = abstol + kmax(kabs(gold), kabs(gn)) * reltol;
-            const T r = kratio(vt, sc);
-            esl += r * r;
-            return gn;
+        T esl2 = T(0);
+        auto fin2 = [&](T go0, T go1, T vb0, T vb1, T vt0, T vt1, T& gn0, T& gn1) {   // two components per packed instruction
+            kadd2(gn0, gn1, go0, go1, vb0, vb1);
+            T sc0 = abstol, sc1 = abstol;
+            kfma2b(sc0, sc1, kmax(kabs(go0), kabs(gn0)), kmax(kabs(go1), kabs(gn1)), reltol);
+            T r0, r1;
+            if constexpr (sizeof(T) == 4) kmul2(r0, r1, vt0, vt1, krcp(sc0), krcp(sc1)); else { r0 = vt0 / sc0; r1 = vt1 / sc1; }
+            kfma2(esl, esl2, r0, r1, r0, r1);
         };
         {   // layer 2: component (o, m): kv_s = lambda_s[o] * c2_s[m]
             T lsv[LSS];
@@ -569,7 +638,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
                 for (int o = 0; o < I; ++o) {
                     T gn[V];
 #pragma unroll
-                    for (int e = 0; e < V; ++e) gn[e] = fin(g2[o][m0 + e], vb[o][e], vt[o][e]);
+                    for (int e = 0; e < V; e += 2) fin2(g2[o][m0 + e], g2[o][m0 + e + 1], vb[o][e], vb[o][e + 1], vt[o][e], vt[o][e + 1], gn[e], gn[e + 1]);
                     stv(fac + (1 + o) * SB + m0, gn);
                 }
             }
@@ -600,23 +669,27 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
                 for (int u = 0; u < UPL; ++u) {
                     T gn[V];
 #pragma unroll
-                    for (int e = 0; e < V; ++e) gn[e] = fin(g1[u][m0 + e], vb[u][e], vt[u][e]);
+                    for (int e = 0; e < V; e += 2) fin2(g1[u][m0 + e], g1[u][m0 + e + 1], vb[u][e], vb[u][e + 1], vt[u][e], vt[u][e + 1], gn[e], gn[e + 1]);
                     stv(fac + (1 + I) * SB + u * NQ1 + m0, gn);
                 }
             }
         }
-        es += group_sum(esl);
-        const double EEst = (double)ksqrt(es / T(NZ));
+        es += group_sum(esl + esl2);
+        const typename LC::Q EEst = LC::eest(es, NZ);
         if (!done && (EEst != EEst || bad)) { ret = RET_UNSTABLE; done = true; }
         // ---- loopfooter!: PI controller ----
-        const double q = pi_q(EEst, qold, q11);
-        accept = rp ? true : (EEst <= 1.0);
+        const typename LC::Q q = LC::q(EEst, qold, q11);
+        accept = rp ? true : (EEst <= (typename LC::Q)1);
         __syncwarp();                                               // every lane of the group is past its reads of f1g
+        if (pend) {                                                 // record window: land the piece fetched one attempt ago
+            if (haspiece) stv(rcg + ((ridx - 1) & 1) * RS + lig * V, pv);
+            rt1 = pend_rt; prev_ok = true; pend = false;
+        }
         if (!done) {
             if (accept) {
                 ++naccept;
-                qold = fmax(EEst, Ctrl::qoldinit);
-                const double dtnew = dt / q;
+                qold = LC::qold_next(EEst);
+                const double dtnew = LC::grow(dt, q);
                 double tnew = t - dt;
                 if (rp) tnew = rp_next;
                 else if (fabs(tnew - tstop) < 100.0 * eps_of(fmax(fabs(t), fabs(tstop)))) tnew = tstop;
@@ -646,11 +719,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
                 ++nreject;
             }
         }
-        // ---- record window: land the piece fetched one attempt ago, then slide when t left the upper record ----
-        if (pend) {
-            if (haspiece) stv(rcg + ((ridx - 1) & 1) * RS + lig * V, pv);
-            rt1 = pend_rt; prev_ok = true; pend = false;
-        }
+        // ---- record window: slide when t left the upper record ----
         if (t < rt0 && ridx > 0 && !done) {
             if (prev_ok && (t >= rt1 || ridx == 1)) { --ridx; rt0 = rt1; }
             else {                                                  // t jumped over a whole record: search, reload (blocking)
@@ -676,7 +745,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
 #pragma unroll
     for (int o = 0; o < I; ++o)
 #pragma unroll
-        for (int m = 0; m < SB; ++m) {
+        for (int m = 0; m < SBR; ++m) {
             const T v = ok ? g2[o][m] : T(0);
             T tot = T(0);
 #pragma unroll
@@ -699,6 +768,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
                 gp[q < G ? P::OC1 + (i * G + q) * P::H + j : P::OW1 + i * P::H + j] = tot;
             }
         }
+    if (lane == 0 && a.wattempts) a.wattempts[wg] = iter;
     if (active && lig == 0) {
         if (skipped) { nf = 0; naccept = 0; nreject = 0; }
         if (a.du0)
@@ -706,6 +776,43 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
             for (int i = 0; i < I; ++i) a.du0[b * I + i] = skipped ? T(0) : lam[i];
         if (a.stats) a.stats[b] = kanode_stats{naccept, nreject, nf, ret};
         if (a.attempts) a.attempts[b] = naccept + nreject;
+    }
+}
+
+// Launch order from the previous call's per-warp iteration counts: logical warps with more than 5/4 of the mean count first
+// (any order among them), the others behind them in their natural order.  One block; n is a few thousand.
+__global__ void __launch_bounds__(1024) lg_order_kernel(const int* __restrict__ att, int n, int* __restrict__ order) {
+    __shared__ unsigned long long ssum;
+    __shared__ int snlong, sbase[2], swarp[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) { ssum = 0ull; snlong = 0; }
+    __syncthreads();
+    unsigned long long loc = 0;
+    for (int i = tid; i < n; i += blockDim.x) loc += (unsigned long long)att[i];
+    for (int d = 16; d > 0; d >>= 1) loc += __shfl_down_sync(0xffffffffu, loc, d);
+    if (lane == 0) atomicAdd(&ssum, loc);
+    __syncthreads();
+    const int thr = (int)((ssum * 5ull) / (4ull * (unsigned long long)(n > 0 ? n : 1)));
+    int cnt = 0;
+    for (int i = tid; i < n; i += blockDim.x) cnt += att[i] > thr;
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, d);
+    if (lane == 0) atomicAdd(&snlong, cnt);
+    __syncthreads();
+    if (tid == 0) { sbase[0] = snlong; sbase[1] = 0; }               // [0]: next position of a short warp, [1]: of a long one
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += blockDim.x) {
+        const int i = c0 + tid;
+        const bool in = i < n, lg = in && att[i] > thr;
+        const unsigned ml = __ballot_sync(0xffffffffu, lg), ms = __ballot_sync(0xffffffffu, in && !lg);
+        if (lane == 0) { swarp[1][w] = __popc(ml); swarp[0][w] = __popc(ms); }
+        __syncthreads();
+        int offl = 0, offs = 0;
+        for (int k = 0; k < w; ++k) { offl += swarp[1][k]; offs += swarp[0][k]; }
+        const unsigned below = (1u << lane) - 1u;
+        if (in) order[lg ? sbase[1] + offl + __popc(ml & below) : sbase[0] + offs + __popc(ms & below)] = i;
+        __syncthreads();
+        if (tid == 0) { int tl = 0, ts_ = 0; for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { tl += swarp[1][k]; ts_ += swarp[0][k]; } sbase[1] += tl; sbase[0] += ts_; }
+        __syncthreads();
     }
 }
 

@@ -33,6 +33,9 @@
 // run) and T=float (mirrors the device path's arithmetic type).
 // Time is always double.
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -671,6 +674,17 @@ template <class T> struct Api {
 extern "C" {
 
 size_t kanode_oracle_param_count(const kanode_desc* d) { return param_count(d); }
+
+// OpenMP thread count of the batched entry points (a launcher such as torchrun exports OMP_NUM_THREADS=1; the bench sets
+// the count it reports explicitly).  n <= 0 leaves it unchanged.  Returns the count in effect.
+int kanode_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n; return 1;
+#endif
+}
 
 #define ORACLE_DEFINE(SUF, T)                                                                                        \
     int kanode_oracle_rhs_##SUF(const kanode_desc* d, const T* p, const T* u, T* du, int64_t batch) {                \

@@ -44,6 +44,11 @@ class Oracle:
             raise ValueError("invalid descriptor")
         self.n = int(desc.n_state)
 
+    def set_threads(self, n: int) -> int:
+        """OpenMP threads of the batched entry points; returns the count in effect (n <= 0: query only)."""
+        self.lib.kanode_oracle_set_threads.restype = C.c_int
+        return int(self.lib.kanode_oracle_set_threads(C.c_int(n)))
+
     def _fn(self, name):
         f = getattr(self.lib, f"kanode_oracle_{name}_{self.suf}")
         f.restype = C.c_int

@@ -11,15 +11,18 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def test_reference_arm_prints_one_json_line():
-    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    import os
+    env = dict(os.environ, OMP_NUM_THREADS="1")          # what torchrun exports: the arm must set its thread count itself
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--batch", "2048", "--lean"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "kan_ode_fwd_adjoint_trajectory_train_steps_per_s"
     assert d["unit"] == "trajectories/s" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    assert d["cpu_baseline"]["value"] == d["value"] and d["config"]["batch_per_gpu"] == 2048
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] == "lotka_volterra_kan_ode_2_10_2_g5_ensemble"
 
