@@ -63,7 +63,9 @@ typedef enum {
     KANODE_ERR_NO_DEVICE = -2,    /* no usable CUDA device (no CPU fallback)   */
     KANODE_ERR_CUDA = -3,         /* CUDA runtime error, see kanode_last_error */
     KANODE_ERR_NOMEM = -4,
-    KANODE_ERR_UNSUPPORTED = -5   /* valid request outside the built kernels   */
+    KANODE_ERR_UNSUPPORTED = -5,  /* valid request outside the built kernels   */
+    KANODE_ERR_SOLVER = -6        /* kanode_loss_grad*: some trajectory's solve did not return Success; outputs are written,
+                                     the failed trajectories are left out of loss / grad (retcodes in the stats arrays) */
 } kanode_status;
 
 /* normalizer: LV/src/kdense.jl:25,41-47,57-61 (NNlib.fast_act maps tanh->tanh_fast) */
@@ -83,7 +85,11 @@ typedef enum {
 /* rhs_kind */
 typedef enum {
     KANODE_RHS_CHAIN = 0,         /* du = chain(u)                NeuralODE dudt       */
-    KANODE_RHS_SOURCE_LAPLACIAN = 1 /* du = lap_coef*lap(u) + chain_1to1.(u)  AC_Source:90-93 */
+    KANODE_RHS_SOURCE_LAPLACIAN = 1, /* du = lap_coef*lap(u) + chain_1to1.(u)  AC_Source:90-93 */
+    KANODE_RHS_MAP = 2            /* not an ODE: the chain as a map x[I_first] -> y[O_last], i.e. the direct layer call
+                                     (l::KDense)(x, p, st) -> (y, st) of kdense.jl:109-130 (Activation_getter.jl:39,
+                                     Allen-Cahn_Source.jl:91).  n_state = I_first.  kanode_rhs evaluates it (output
+                                     [batch][O_last]), kanode_vjp pulls back; the solve entry points refuse it. */
 } kanode_rhs_kind;
 
 typedef struct {
@@ -221,6 +227,44 @@ int kanode_loss_grad_replay_f64(kanode_handle* h, const double* u0, int64_t batc
                                 const double* fwd_t, const double* bwd_t, int32_t max_steps,
                                 double* loss, double* grad, double* du0, double* out,
                                 kanode_stats* fwd_stats, kanode_stats* bwd_stats);
+
+/* ---- pullback of the solve for an ARBITRARY loss (the reference's gradient call, LV_driver_KANODE.jl:197-203,284 with the
+ * optional reg term; Burgers_Surrogate.jl:105-107,191 with a transposed target) -------------------------------------
+ * Zygote.gradient(loss, p) runs the forward solve, differentiates loss(pred) itself and hands dL/dpred to the adjoint of
+ * the solve [EXT SciMLSensitivity 7.69.0 InterpolatingAdjoint].  This entry point is that adjoint: the forward problem is
+ * re-solved densely, the backward problem on z = [lambda; g] is integrated t1 -> t0 with the jumps lambda += dL_dout[b][s]
+ * at the save times.  grad = sum_b (d pred_b/d p)^T dL_dout[b] (no 1/batch: the cotangent carries every scale),
+ * du0[b] = (d pred_b/d u0_b)^T dL_dout[b].  out (optional) receives the predictions of the dense forward solve.
+ * Returns KANODE_ERR_SOLVER like kanode_loss_grad when a solve fails.  The Julia rrule on the NeuralODE call binds this. */
+int kanode_solve_adjoint(kanode_handle* h, const float* u0, int64_t batch, double t0, double t1,
+                         const double* saveat, int32_t nsave, float abstol, float reltol,
+                         const float* dL_dout /* [batch][nsave][n] */, float* out /* or NULL */,
+                         float* grad /* [np] */, float* du0 /* [batch][n] or NULL */,
+                         kanode_stats* fwd_stats /* or NULL */, kanode_stats* bwd_stats /* or NULL */);
+int kanode_solve_adjoint_f64(kanode_handle* h, const double* u0, int64_t batch, double t0, double t1,
+                             const double* saveat, int32_t nsave, double abstol, double reltol,
+                             const double* dL_dout, double* out, double* grad, double* du0,
+                             kanode_stats* fwd_stats, kanode_stats* bwd_stats);
+/* device-pointer variant (no host synchronisation; d_grad receives the same sum, d_out optional) */
+int kanode_solve_adjoint_dev(kanode_handle* h, const float* d_u0, int64_t batch, double t0, double t1,
+                             const double* saveat, int32_t nsave, float abstol, float reltol,
+                             const float* d_dL_dout, float* d_out, float* d_grad, float* d_du0,
+                             kanode_stats* d_fwd_stats, kanode_stats* d_bwd_stats);
+
+/* ---- per-edge activations (LV/Activation_getter.jl:3-63; feeds prune, LV_driver_KANODE.jl:52-108, and the plotters) ----
+ * act[k][i][o] = sum_g C_l[o,(i,g)] * basis_g(normalizer(x[k][i])) + W_l[o,i] * swish(x[k][i]) for layer `layer` of the chain
+ * at its inputs x[K][I_l]: the fused basis kernel without the sum over the inputs; sum_i act[k][i][o] is the layer output
+ * (the identity commented at Activation_getter.jl:33-36). */
+int kanode_edge_activations(kanode_handle* h, int32_t layer, const float* x /* [K][I_l] */, float* act /* [K][I_l][O_l] */, int64_t K);
+int kanode_edge_activations_f64(kanode_handle* h, int32_t layer, const double* x, double* act, int64_t K);
+
+/* ---- sparsity regulariser (reg_loss, LV_driver_KANODE.jl:187-194; added to the loss when sparse_on == 1, :199-201) ----
+ * reg(p) = act_reg * sum|p| + entropy_reg * (-sum e log e), e = |p| / sum|p|.  Once set (non-zero), kanode_loss_grad* add
+ * reg(p) to the loss and d reg/d p to the gradient (the *_dev variants add batch*nsave*n*reg and batch*dreg to their
+ * un-normalised sums, so the caller's normalisation gives the same).  (0, 0) switches it off (the default). */
+int kanode_set_regularizer(kanode_handle* h, double act_reg, double entropy_reg);
+/* reg(p) and d reg/d p of the current parameters on their own (host pointers; grad may be NULL) */
+int kanode_reg_loss(kanode_handle* h, double act_reg, double entropy_reg, double* loss, float* grad /* [np] or NULL */);
 
 /* Flux.Adam(eta, (beta1, beta2), eps) + update!(opt, p, grad)  (LV_driver_KANODE.jl:219,287; [EXT Flux 0.14.22]):
  *   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g^2;  p -= eta * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps),  g = grad_scale*d_grad.

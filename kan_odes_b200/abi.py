@@ -17,12 +17,13 @@ NORM_TANH, NORM_SOFTSIGN, NORM_SIGMOID = 0, 1, 2
 # kanode_basis (utils.jl:8-62)
 BASIS_RBF, BASIS_RSWAF, BASIS_IQF = 0, 1, 2
 # kanode_rhs_kind
-RHS_CHAIN, RHS_SOURCE_LAPLACIAN = 0, 1
+RHS_CHAIN, RHS_SOURCE_LAPLACIAN, RHS_MAP = 0, 1, 2
 # kanode_retcode
 RET_SUCCESS, RET_MAXITERS, RET_DT_LESS_THAN_MIN, RET_UNSTABLE, RET_RECORD_OVERFLOW = range(5)
 RETCODE_NAMES = ("Success", "MaxIters", "DtLessThanMin", "Unstable", "RecordOverflow")
 
-ERR_NAMES = {0: "OK", -1: "INVALID", -2: "NO_DEVICE", -3: "CUDA", -4: "NOMEM", -5: "UNSUPPORTED"}
+ERR_NAMES = {0: "OK", -1: "INVALID", -2: "NO_DEVICE", -3: "CUDA", -4: "NOMEM", -5: "UNSUPPORTED", -6: "SOLVER"}
+ERR_SOLVER = -6
 
 
 class LayerDesc(C.Structure):
@@ -61,6 +62,8 @@ EXPORTED_SYMBOLS = (
     "kanode_set_params_f64", "kanode_rhs_f64", "kanode_vjp_f64", "kanode_solve_f64", "kanode_loss_grad_f64",
     "kanode_loss_grad_dev_f64", "kanode_last_timing", "kanode_adam_step_dev", "kanode_last_gpass_timing",
     "kanode_loss_grad_replay", "kanode_loss_grad_replay_f64",
+    "kanode_solve_adjoint", "kanode_solve_adjoint_f64", "kanode_solve_adjoint_dev",
+    "kanode_edge_activations", "kanode_edge_activations_f64", "kanode_set_regularizer", "kanode_reg_loss",
 )
 
 _lib = None

@@ -14,7 +14,6 @@
 
 #include "kanode_host.h"
 #include "kanode_small_host.h"
-#include "kanode_small_ls.cuh"
 #include "kanode_generic.cuh"
 #include "kanode_wide_api.h"
 
@@ -61,6 +60,9 @@ template <class T> int put_saveat(kanode_handle* h, const double* saveat, int ns
     return 0;
 }
 
+// The lockstep engines index with 32-bit offsets and put the batch on grid.y: larger batches take the block-per-trajectory kernels
+inline bool wide_batch_ok(const kanode_handle* h, int64_t B) { return B <= 65535 && (int64_t)B * h->n * 8 < (1ll << 31); }
+
 template <class T> int rhs_dev(kanode_handle* h, const T* d_u, T* d_du, int64_t B) {
     if (!h->have_params) return fail(h, KANODE_ERR_INVALID, "parameters not set");
     if (B <= 0) return 0;
@@ -74,7 +76,7 @@ template <class T> int rhs_dev(kanode_handle* h, const T* d_u, T* d_du, int64_t 
     };
     if (small_dispatch<T>(h, run, rc)) return rc;
     WideKey wk;
-    if (h->wide && wide_match(h->desc, wk) && (int64_t)B * h->n * 8 < (1ll << 31)) return wide_rhs(h, wk, generic_params<T>(h), d_u, d_du, B);
+    if (h->wide && wide_match(h->desc, wk) && wide_batch_ok(h, B)) return wide_rhs(h, wk, generic_params<T>(h), d_u, d_du, B);
     return generic_rhs<T>(h, d_u, d_du, B);
 }
 
@@ -101,6 +103,7 @@ template <class T>
 int solve_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double t1, const double* saveat, int nsave,
               double abstol, double reltol, T* d_out, kanode_stats* d_stats) {
     if (!h->have_params) return fail(h, KANODE_ERR_INVALID, "parameters not set");
+    if (h->desc.rhs_kind == KANODE_RHS_MAP) return fail(h, KANODE_ERR_UNSUPPORTED, "a KANODE_RHS_MAP handle is a map, not an ODE right-hand side");
     if (int rc = check_saveat(h, t0, t1, saveat, nsave)) return rc;
     if (B <= 0) return 0;
     const double* d_saveat = nullptr;
@@ -119,20 +122,23 @@ int solve_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double t1, 
     };
     if (small_dispatch<T>(h, run, rc)) return rc;
     WideKey wk;
-    if (h->wide && wide_match(h->desc, wk) && (int64_t)B * h->n * 8 < (1ll << 31))
+    if (h->wide && wide_match(h->desc, wk) && wide_batch_ok(h, B))
         return wide_solve(h, wk, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);
     int sg = 0;
-    if (h->wide && wsrc_match(h->desc, sg) && (int64_t)B * h->n * 8 < (1ll << 31))
+    if (h->wide && wsrc_match(h->desc, sg) && wide_batch_ok(h, B))
         return wsrc_solve(h, sg, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);
     return generic_solve<T>(h, d_u0, B, t0, t1, d_saveat, nsave, abstol, reltol, d_out, d_stats);
 }
+
+template <class T> int reg_apply(kanode_handle* h, double* d_loss, double loss_scale, T* d_grad, double grad_scale);
 
 template <class T>
 int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double t1, const double* saveat, int nsave,
                   const T* d_target, double abstol, double reltol, double* d_loss_sum, T* d_grad_sum, T* d_du0,
                   kanode_stats* d_fst, kanode_stats* d_bst, T* d_out_opt, const double* d_rp_fwd = nullptr,
-                  const double* d_rp_bwd = nullptr, int rp_cap = 0) {
+                  const double* d_rp_bwd = nullptr, int rp_cap = 0, const T* d_cot = nullptr) {
     if (!h->have_params) return fail(h, KANODE_ERR_INVALID, "parameters not set");
+    if (h->desc.rhs_kind == KANODE_RHS_MAP) return fail(h, KANODE_ERR_UNSUPPORTED, "a KANODE_RHS_MAP handle is a map, not an ODE right-hand side");
     if (int rc = check_saveat(h, t0, t1, saveat, nsave)) return rc;
     if (nsave < 1) return fail(h, KANODE_ERR_INVALID, "loss needs at least one save time");
     h->wide_gp_used = 0;
@@ -140,117 +146,67 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
     if (B <= 0) { CK(h, cudaMemsetAsync(d_grad_sum, 0, sizeof(T) * h->np, h->stream)); return 0; }
     const double* d_saveat = nullptr;
     if (int rc = put_saveat<T>(h, saveat, nsave, &d_saveat)) return rc;
-    if (h->bwd_lg || d_rp_fwd || d_rp_bwd) {
-        bool handled = false;
-        const int rcl = small_lg_loss_grad<T>(h, d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum, d_grad_sum,
-                                              d_du0, d_fst, d_bst, d_out_opt, d_rp_fwd, d_rp_bwd, rp_cap, &handled);
-        if (handled) return rcl;
-        if (d_rp_fwd || d_rp_bwd) return fail(h, KANODE_ERR_UNSUPPORTED, "dt-replay is implemented by the small-model ensemble kernels only");
-    }
-    int rc = 0;
-    auto run = [&]<class P, int NORM>() -> int {
-        constexpr int I = P::I;
-        P prm; fill_small<T>(h, prm);
-        if (d_rp_fwd || d_rp_bwd) return fail(h, KANODE_ERR_UNSUPPORTED, "dt-replay needs the lane-group kernels (KANODE_BWD=1)");
-        const int cap = h->rec_cap;
-        double* rec_t = nullptr; T *rec = nullptr, *dg = nullptr, *fac = nullptr, *g = nullptr;
-        int *nsteps = nullptr, *retc = nullptr;
-        ENSURE(h, W_REC_T, sizeof(double) * (size_t)cap * B, rec_t);
-        ENSURE(h, W_REC, sizeof(T) * (size_t)cap * (1 + 8 * I) * B, rec);
-        ENSURE(h, W_NSTEPS, sizeof(int) * (size_t)B, nsteps);
-        ENSURE(h, W_RET, sizeof(int) * (size_t)B, retc);
-        ENSURE(h, W_DG, sizeof(T) * (size_t)nsave * I * B, dg);
-        ENSURE(h, W_G, sizeof(T) * (size_t)2 * P::NP * B, g);
-        SmallFwdArgs<T> a{};
-        if (int rcw = upload_packed<T, P>(h, &a.wpk)) return rcw;
-        a.u0 = d_u0; a.B = B; a.t0 = t0; a.t1 = t1; a.saveat = d_saveat; a.nsave = nsave;
-        a.abstol = (T)abstol; a.reltol = (T)reltol; a.maxiters = 100000; a.out = d_out_opt; a.stats = d_fst;
-        a.rec_t = rec_t; a.rec = rec; a.cap = cap; a.nsteps = nsteps; a.retcode = retc;
-        a.target = d_target; a.dg = dg; a.loss_sum = d_loss_sum;
-        cudaEventRecord(h->ev[0], h->stream);
-        small_forward_kernel<T, P, NORM, true><<<blocks_for(B, 64), 64, 0, h->stream>>>(prm, a);
-        cudaEventRecord(h->ev[1], h->stream);
-        SmallBwdArgs<T> bw{};
-        bw.wpk = a.wpk; bw.B = B; bw.t0 = t0; bw.t1 = t1; bw.saveat = d_saveat; bw.nsave = nsave;
-        bw.abstol = (T)abstol; bw.reltol = (T)reltol; bw.maxiters = 100000;
-        bw.rec_t = rec_t; bw.rec = rec; bw.cap = cap; bw.nsteps = nsteps; bw.retcode = retc; bw.dg = dg;
-        bw.fac = nullptr; bw.g = g; bw.du0 = d_du0; bw.stats = d_bst;
-        bw.maxiters = h->bwd_maxiters;
-        {
-            // Scheduling from the previous call's per-trajectory step counts (same batch size, same dtype): the
-            // trajectories predicted to need the most steps get a warp each (small_backward_warp_kernel: the step-end
-            // gradient pass is spread over the lanes), launched ahead of the bulk, which follows on a second stream.
-            // Their serial chain of steps then finishes well inside the bulk's run time instead of bounding the launch.
-            constexpr int BT = KANODE_BWD_BT;                              // threads (= trajectories) per block
-            const int kLongSlots = h->long_slots;
-            const size_t smem = sizeof(T) * (7 * StageRec<P>::N * BT + P::WPK) + 16;   // stage records + packed weights + mbarrier
-            CK(h, cudaFuncSetAttribute(small_backward_kernel<T, P, NORM, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int slot = sizeof(T) == 4 ? 0 : 1;
-            bool have_long = false;
-            if (h->schedule && B >= 4096 && kLongSlots > 0) {
-                // W_ATT: [2 dtypes][ attempts[B] ], W_ORDER: [2 dtypes][ sched (4 x u64) | long_list[cap] | flag[B] ]
-                int* att = nullptr; char* ob = nullptr;
-                const size_t per = 64 + sizeof(int) * (size_t)kLongSlots + (size_t)B;
-                ENSURE(h, W_ATT, sizeof(int) * (size_t)B * 2, att);
-                ENSURE(h, W_ORDER, 2 * ((per + 63) / 64 * 64), ob);
-                att += (size_t)slot * B; ob += (size_t)slot * ((per + 63) / 64 * 64);
-                unsigned long long* sched = reinterpret_cast<unsigned long long*>(ob);     // [0] prev sum, [1] running sum
-                int* long_count = reinterpret_cast<int*>(sched + 2);
-                int* long_list = reinterpret_cast<int*>(ob + 64);
-                unsigned char* long_flag = reinterpret_cast<unsigned char*>(long_list + kLongSlots);
-                if (h->order_B[slot] == B) {
-                    CK(h, cudaMemcpyAsync(&sched[0], &sched[1], sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
-                    CK(h, cudaMemsetAsync(&sched[1], 0, sizeof(unsigned long long) + sizeof(int), h->stream));   // running sum, long_count
-                    mark_long_kernel<<<blocks_for(B, 256), 256, 0, h->stream>>>(att, B, &sched[0], long_count, kLongSlots, long_list, long_flag);
-                    clamp_count_kernel<<<1, 1, 0, h->stream>>>(long_count, kLongSlots);
-                    h->launches += 2;
-                    have_long = true;
-                    CK(h, cudaEventRecord(h->aux_ev[0], h->stream));
-                    SmallBwdArgs<T> lg = bw;
-                    lg.long_list = long_list; lg.long_count = long_count; lg.gidn = kLongSlots;
-                    lg.attempts = att; lg.attempts_sum = &sched[1];
-                    // one warp per predicted-long trajectory, kLongWarps of them per block; each block asks for enough shared
-                    // memory to own its SM, so the long solves run undisturbed on a few SMs while the bulk gets the rest
-                    constexpr int kLongWarps = 12;
-                    constexpr size_t kExclusiveSmem = 200 * 1024;
-                    static_assert(sizeof(T) * (P::WPK + kLongWarps * (7 * StageRec<P>::N + 2)) + 32 <= kExclusiveSmem, "smem");
-                    CK(h, cudaFuncSetAttribute(small_backward_warp_kernel<T, P, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExclusiveSmem));
-                    small_backward_warp_kernel<T, P, NORM><<<blocks_for(kLongSlots, kLongWarps), kLongWarps * 32, kExclusiveSmem, h->stream>>>(prm, lg);
-                    ++h->launches;
-                    bw.long_flag = long_flag;
-                } else {
-                    CK(h, cudaMemsetAsync(ob, 0, 64, h->stream));
-                }
-                bw.attempts = att; bw.attempts_sum = &sched[1];
-                h->order_B[slot] = B;
-            }
-            bw.gidn = B;
-            {
-                cudaStream_t bulk = have_long ? h->aux_stream : h->stream;
-                if (have_long) CK(h, cudaStreamWaitEvent(bulk, h->aux_ev[0], 0));
-                small_backward_kernel<T, P, NORM, 0><<<blocks_for(B, BT), BT, smem, bulk>>>(prm, bw);
-                if (have_long) { CK(h, cudaEventRecord(h->aux_ev[1], bulk)); CK(h, cudaStreamWaitEvent(h->stream, h->aux_ev[1], 0)); }
-            }
-            cudaEventRecord(h->ev[2], h->stream);
-            reduce_rows_kernel<T, T><<<P::NP, 256, 0, h->stream>>>(g, B, d_grad_sum, 1.0);
-            cudaEventRecord(h->ev[3], h->stream);
-            h->launches += 3;
+    if (d_cot) {
+        // pullback with caller-supplied cotangents: every engine keeps dL/du(t_s) in W_DG as [B][nsave][n] and, given a null
+        // target, leaves it alone (it only zeroes the entries of failed trajectories): pre-fill it and drop the target
+        T* dg = nullptr;
+        ENSURE(h, W_DG, sizeof(T) * (size_t)nsave * h->n * B, dg);
+        CK(h, cudaMemcpyAsync(dg, d_cot, sizeof(T) * (size_t)nsave * h->n * B, cudaMemcpyDeviceToDevice, h->stream));
+        d_target = nullptr;
+    } else if (!d_target) return fail(h, KANODE_ERR_INVALID, "null target");
+    auto engine = [&]() -> int {
+        {   // small-model registry: lane-group adjoint engine (kanode_lg.cu)
+            bool handled = false;
+            const int rcl = small_lg_loss_grad<T>(h, d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum, d_grad_sum,
+                                                  d_du0, d_fst, d_bst, d_out_opt, d_rp_fwd, d_rp_bwd, rp_cap, &handled);
+            if (handled) return rcl;
+            if (d_rp_fwd || d_rp_bwd) return fail(h, KANODE_ERR_UNSUPPORTED, "dt-replay is implemented by the small-model ensemble kernels only");
         }
-        h->ev_valid = true;
-        CK(h, cudaGetLastError());
-        return 0;
+        WideKey wk;
+        if (h->wide && wide_match(h->desc, wk) && wide_batch_ok(h, B))
+            return wide_loss_grad(h, wk, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum,
+                                  d_grad_sum, d_du0, d_fst, d_bst, d_out_opt);
+        int sg = 0;
+        if (h->wide && wsrc_match(h->desc, sg) && wide_batch_ok(h, B))
+            return wsrc_loss_grad(h, sg, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum,
+                                  d_grad_sum, d_du0, d_fst, d_bst, d_out_opt);
+        return generic_loss_grad<T>(h, d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum, d_grad_sum,
+                                    d_du0, d_fst, d_bst, d_out_opt);
     };
-    if (small_dispatch<T>(h, run, rc)) return rc;
-    WideKey wk;
-    if (h->wide && wide_match(h->desc, wk) && (int64_t)B * h->n * 8 < (1ll << 31))
-        return wide_loss_grad(h, wk, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum,
-                              d_grad_sum, d_du0, d_fst, d_bst, d_out_opt);
-    int sg = 0;
-    if (h->wide && wsrc_match(h->desc, sg) && (int64_t)B * h->n * 8 < (1ll << 31))
-        return wsrc_loss_grad(h, sg, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum,
-                              d_grad_sum, d_du0, d_fst, d_bst, d_out_opt);
-    return generic_loss_grad<T>(h, d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum, d_grad_sum,
-                                d_du0, d_fst, d_bst, d_out_opt);
+    if (int rc = engine()) return rc;
+    // sparsity regulariser (reg_loss, LV_driver_KANODE.jl:187-201): the sums are un-normalised (caller divides the loss by
+    // B*nsave*n and the gradient by B), so reg enters with those factors
+    if (!d_cot && (h->reg_act != 0.0 || h->reg_entropy != 0.0))
+        return reg_apply<T>(h, d_loss_sum, (double)B * nsave * h->n, d_grad_sum, (double)B);
+    return 0;
+}
+
+template <class T> int reg_apply(kanode_handle* h, double* d_loss, double loss_scale, T* d_grad, double grad_scale) {
+    double* acc = nullptr;
+    ENSURE(h, W_REG, 2 * sizeof(double), acc);
+    CK(h, cudaMemsetAsync(acc, 0, 2 * sizeof(double), h->stream));
+    const T* p = generic_params<T>(h);
+    const unsigned nb = (unsigned)std::min<size_t>((h->np + 255) / 256, 1184);
+    reg_sums_kernel<T><<<nb, 256, 0, h->stream>>>(p, h->np, acc);
+    reg_apply_kernel<T><<<blocks_for((int64_t)h->np, 256), 256, 0, h->stream>>>(p, h->np, acc, h->reg_act, h->reg_entropy, d_loss, loss_scale,
+                                                                                 d_grad, grad_scale);
+    h->launches += 2;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+// failed[0] = forward solves that did not return Success, [1] = of those, dense-record overflows, [2] = failed adjoint solves
+__global__ void __launch_bounds__(256) stats_scan_kernel(const kanode_stats* __restrict__ f, const kanode_stats* __restrict__ b, int64_t B,
+                                                         int* __restrict__ failed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int ff = 0, fo = 0, fb = 0;
+    if (i < B) { ff = f[i].retcode != KANODE_RET_SUCCESS; fo = f[i].retcode == KANODE_RET_RECORD_OVERFLOW; fb = b[i].retcode != KANODE_RET_SUCCESS; }
+    ff = __syncthreads_count(ff); fo = __syncthreads_count(fo); fb = __syncthreads_count(fb);
+    if (threadIdx.x == 0) {
+        if (ff) atomicAdd(&failed[0], ff);
+        if (fo) atomicAdd(&failed[1], fo);
+        if (fb) atomicAdd(&failed[2], fb);
+    }
 }
 
 // ---- host-pointer wrappers -----------------------------------------------------------------------------------
@@ -267,12 +223,12 @@ template <class T> int rhs_host(kanode_handle* h, const T* u, T* du, int64_t B) 
     if (int rc = enter(h)) return rc;
     if (B < 0 || (B > 0 && (!u || !du))) return fail(h, KANODE_ERR_INVALID, "bad arguments");
     if (B == 0) return 0;
-    const size_t bytes = sizeof(T) * (size_t)B * h->n;
+    const size_t bytes = sizeof(T) * (size_t)B * h->n, obytes = sizeof(T) * (size_t)B * h->n_out;   // n_out != n only for KANODE_RHS_MAP
     T *d_u = nullptr, *d_du = nullptr;
-    ENSURE(h, W_U0, bytes, d_u); ENSURE(h, W_OUT, bytes, d_du);
+    ENSURE(h, W_U0, bytes, d_u); ENSURE(h, W_OUT, obytes, d_du);
     CK(h, cudaMemcpyAsync(d_u, u, bytes, cudaMemcpyHostToDevice, h->stream));
     if (int rc = rhs_dev<T>(h, d_u, d_du, B)) return rc;
-    CK(h, cudaMemcpyAsync(du, d_du, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(du, d_du, obytes, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -280,13 +236,13 @@ template <class T> int rhs_host(kanode_handle* h, const T* u, T* du, int64_t B) 
 template <class T> int vjp_host(kanode_handle* h, const T* u, const T* lam, T* ubar, T* pbar, int64_t B) {
     if (int rc = enter(h)) return rc;
     if (B < 0 || !pbar || (B > 0 && (!u || !lam || !ubar))) return fail(h, KANODE_ERR_INVALID, "bad arguments");
-    const size_t bytes = sizeof(T) * (size_t)(B > 0 ? B : 1) * h->n;
+    const size_t bytes = sizeof(T) * (size_t)(B > 0 ? B : 1) * h->n, lbytes = sizeof(T) * (size_t)(B > 0 ? B : 1) * h->n_out;
     T *d_u = nullptr, *d_lam = nullptr, *d_ub = nullptr, *d_pb = nullptr;
-    ENSURE(h, W_U0, bytes, d_u); ENSURE(h, W_LAM, bytes, d_lam); ENSURE(h, W_OUT, bytes, d_ub);
+    ENSURE(h, W_U0, bytes, d_u); ENSURE(h, W_LAM, lbytes, d_lam); ENSURE(h, W_OUT, bytes, d_ub);
     ENSURE(h, W_GRAD, sizeof(T) * h->np, d_pb);
     if (B > 0) {
         CK(h, cudaMemcpyAsync(d_u, u, sizeof(T) * (size_t)B * h->n, cudaMemcpyHostToDevice, h->stream));
-        CK(h, cudaMemcpyAsync(d_lam, lam, sizeof(T) * (size_t)B * h->n, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaMemcpyAsync(d_lam, lam, sizeof(T) * (size_t)B * h->n_out, cudaMemcpyHostToDevice, h->stream));   // cotangent of the output
     }
     if (int rc = vjp_dev<T>(h, d_u, d_lam, d_ub, d_pb, B)) return rc;
     if (B > 0) CK(h, cudaMemcpyAsync(ubar, d_ub, sizeof(T) * (size_t)B * h->n, cudaMemcpyDeviceToHost, h->stream));
@@ -317,9 +273,11 @@ template <class T>
 int loss_grad_host(kanode_handle* h, const T* u0, int64_t B, double t0, double t1, const double* saveat, int nsave,
                    const T* target, double abstol, double reltol, T* loss, T* grad, T* du0, kanode_stats* fst,
                    kanode_stats* bst, const double* rp_fwd = nullptr, const double* rp_bwd = nullptr, int rp_cap = 0,
-                   T* out = nullptr) {
+                   T* out = nullptr, const T* cot = nullptr) {
+    // cot != null: pullback of the solve with the caller's cotangents dL/dpred (kanode_solve_adjoint): no target, no loss,
+    // and the gradient is the plain sum over the batch
     if (int rc = enter(h)) return rc;
-    if (B <= 0 || !u0 || !target || !loss || !grad) return fail(h, KANODE_ERR_INVALID, "bad arguments");
+    if (B <= 0 || !u0 || (!target && !cot) || (!loss && !cot) || !grad) return fail(h, KANODE_ERR_INVALID, "bad arguments");
     if ((rp_fwd || rp_bwd) && (!rp_fwd || !rp_bwd || rp_cap < 1)) return fail(h, KANODE_ERR_INVALID, "replay needs both step sequences");
     const size_t nout = (size_t)B * nsave * h->n;
     for (int attempt = 0;; ++attempt) {
@@ -333,7 +291,11 @@ int loss_grad_host(kanode_handle* h, const T* u0, int64_t B, double t0, double t
         ENSURE(h, W_STATS_F, sizeof(kanode_stats) * (size_t)B, d_f);
         ENSURE(h, W_STATS_B, sizeof(kanode_stats) * (size_t)B, d_b);
         CK(h, cudaMemcpyAsync(d_u0, u0, sizeof(T) * (size_t)B * h->n, cudaMemcpyHostToDevice, h->stream));
-        CK(h, cudaMemcpyAsync(d_tg, target, sizeof(T) * nout, cudaMemcpyHostToDevice, h->stream));
+        T* d_cot = nullptr;
+        if (cot) {
+            ENSURE(h, W_COT, sizeof(T) * (nout ? nout : 1), d_cot);
+            CK(h, cudaMemcpyAsync(d_cot, cot, sizeof(T) * nout, cudaMemcpyHostToDevice, h->stream));
+        } else CK(h, cudaMemcpyAsync(d_tg, target, sizeof(T) * nout, cudaMemcpyHostToDevice, h->stream));
         double *d_rpf = nullptr, *d_rpb = nullptr; T* d_out = nullptr;
         if (rp_fwd) {
             ENSURE(h, W_RPF, sizeof(double) * (size_t)B * rp_cap, d_rpf);
@@ -343,36 +305,67 @@ int loss_grad_host(kanode_handle* h, const T* u0, int64_t B, double t0, double t
         }
         if (out) ENSURE(h, W_OUT, sizeof(T) * (nout ? nout : 1), d_out);
         if (int rc = loss_grad_dev<T>(h, d_u0, B, t0, t1, saveat, nsave, d_tg, abstol, reltol, d_loss, d_grad, d_du0,
-                                      d_f, d_b, d_out, d_rpf, d_rpb, rp_cap)) return rc;
+                                      d_f, d_b, d_out, d_rpf, d_rpb, rp_cap, d_cot)) return rc;
         if (out) CK(h, cudaMemcpyAsync(out, d_out, sizeof(T) * nout, cudaMemcpyDeviceToHost, h->stream));
-        // every result goes to ONE pinned staging block with async copies and a single synchronisation
+        // every result goes to ONE pinned staging block with async copies and a single synchronisation; the per-trajectory
+        // statistics travel only when the caller asked for them (a 3-counter scan tells whether any solve failed)
+        int* d_cnt = nullptr;
+        ENSURE(h, W_FAILCNT, 3 * sizeof(int), d_cnt);
+        CK(h, cudaMemsetAsync(d_cnt, 0, 3 * sizeof(int), h->stream));
+        stats_scan_kernel<<<blocks_for(B, 256), 256, 0, h->stream>>>(d_f, d_b, B, d_cnt);
+        ++h->launches;
         const size_t o_f = 0, o_b = o_f + sizeof(kanode_stats) * (size_t)B, o_du = o_b + sizeof(kanode_stats) * (size_t)B,
-                     o_g = o_du + sizeof(T) * (size_t)B * h->n, o_l = (o_g + sizeof(T) * h->np + 7) / 8 * 8, total = o_l + 8;
+                     o_g = o_du + sizeof(T) * (size_t)B * h->n, o_l = (o_g + sizeof(T) * h->np + 7) / 8 * 8, o_c = o_l + 8, total = o_c + 16;
         if (h->stage_bytes < total) {
             if (h->stage) { CK(h, cudaStreamSynchronize(h->stream)); cudaFreeHost(h->stage); h->stage = nullptr; h->stage_bytes = 0; }
             CK(h, cudaMallocHost(&h->stage, total + total / 8));
             h->stage_bytes = total + total / 8;
         }
         char* st = static_cast<char*>(h->stage);
-        CK(h, cudaMemcpyAsync(st + o_f, d_f, sizeof(kanode_stats) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+        if (fst) CK(h, cudaMemcpyAsync(st + o_f, d_f, sizeof(kanode_stats) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
         if (bst) CK(h, cudaMemcpyAsync(st + o_b, d_b, sizeof(kanode_stats) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
         if (du0) CK(h, cudaMemcpyAsync(st + o_du, d_du0, sizeof(T) * (size_t)B * h->n, cudaMemcpyDeviceToHost, h->stream));
         CK(h, cudaMemcpyAsync(st + o_g, d_grad, sizeof(T) * h->np, cudaMemcpyDeviceToHost, h->stream));
         CK(h, cudaMemcpyAsync(st + o_l, d_loss, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(st + o_c, d_cnt, 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(h, cudaStreamSynchronize(h->stream));
-        const kanode_stats* f = reinterpret_cast<const kanode_stats*>(st + o_f);
-        bool overflow = false;
-        for (int64_t b = 0; b < B; ++b) overflow |= (f[b].retcode == KANODE_RET_RECORD_OVERFLOW);
-        if (overflow && attempt < 6) { h->rec_cap *= 4; continue; }   // grow the dense record and redo the step
+        int cnt[3]; std::memcpy(cnt, st + o_c, sizeof cnt);
+        if (cnt[1] > 0 && attempt < 6) { h->rec_cap *= 4; continue; }   // grow the dense record and redo the step
         if (fst) std::memcpy(fst, st + o_f, sizeof(kanode_stats) * (size_t)B);
         if (bst) std::memcpy(bst, st + o_b, sizeof(kanode_stats) * (size_t)B);
         if (du0) std::memcpy(du0, st + o_du, sizeof(T) * (size_t)B * h->n);
         const T* gs = reinterpret_cast<const T*>(st + o_g);
         double lsum = 0; std::memcpy(&lsum, st + o_l, sizeof(double));
-        *loss = (T)(lsum / ((double)B * nsave * h->n));
-        for (size_t i = 0; i < h->np; ++i) grad[i] = (T)((double)gs[i] / (double)B);
+        if (loss) *loss = (T)(lsum / ((double)B * nsave * h->n));
+        const double gdiv = cot ? 1.0 : (double)B;
+        for (size_t i = 0; i < h->np; ++i) grad[i] = (T)((double)gs[i] / gdiv);
+        h->last_failed[0] = cnt[0]; h->last_failed[1] = cnt[2];
+        // In the reference a failed solve gives a short solution and loss() throws (LV_driver_KANODE.jl:197-203); here the
+        // failed trajectories are left out of the sums, every output is still written, and the call reports it.
+        if (cnt[0] + cnt[2] > 0)
+            return fail(h, KANODE_ERR_SOLVER, "%d forward and %d adjoint solves of %lld did not return Success (see the per-trajectory retcodes); "
+                        "loss and gradient leave them out", cnt[0], cnt[2], (long long)B);
         return 0;
     }
+}
+
+template <class T> int edge_activations_host(kanode_handle* h, int layer, const T* x, T* act, int64_t K) {
+    if (int rc = enter(h)) return rc;
+    if (!h->have_params) return fail(h, KANODE_ERR_INVALID, "parameters not set");
+    if (layer < 0 || layer >= h->desc.n_layers || K < 0 || (K > 0 && (!x || !act))) return fail(h, KANODE_ERR_INVALID, "bad arguments");
+    if (K == 0) return 0;
+    if (int rc = generic_supported(h)) return rc;
+    const kanode_layer_desc& L = h->desc.layers[layer];
+    const size_t nin = (size_t)K * L.in_dims, nact = nin * L.out_dims;
+    T *d_x = nullptr, *d_a = nullptr;
+    ENSURE(h, W_U0, sizeof(T) * nin, d_x); ENSURE(h, W_ACT, sizeof(T) * nact, d_a);
+    CK(h, cudaMemcpyAsync(d_x, x, sizeof(T) * nin, cudaMemcpyHostToDevice, h->stream));
+    edge_activation_kernel<T><<<blocks_for((int64_t)nin, 128), 128, 0, h->stream>>>(h->gm, layer, generic_params<T>(h), d_x, d_a, K);
+    ++h->launches;
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(act, d_a, sizeof(T) * nact, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 }  // namespace
@@ -406,11 +399,10 @@ int kanode_create(const kanode_desc* desc, int device, void* stream, kanode_hand
     kanode_handle* h = new (std::nothrow) kanode_handle();
     if (!h) return fail(nullptr, KANODE_ERR_NOMEM, "out of host memory");
     h->desc = *desc; h->device = device; h->np = np; h->n = desc->n_state;
+    h->n_out = desc->rhs_kind == KANODE_RHS_MAP ? desc->layers[desc->n_layers - 1].out_dims : desc->n_state;
     h->params.assign(np, 0.0);
-    if (const char* e = std::getenv("KANODE_BWD")) h->bwd_lg = std::atoi(e);                 // 0: round-1 thread-per-trajectory adjoint (A/B)
     if (const char* e = std::getenv("KANODE_LG_SHAPE")) h->lg_shape = std::atoi(e);
     if (const char* e = std::getenv("KANODE_BWD_MAXIT")) h->bwd_maxiters = std::atoi(e);     // timing experiments only
-    if (const char* e = std::getenv("KANODE_LONG_SLOTS")) h->long_slots = std::atoi(e);
     if (const char* e = std::getenv("KANODE_SCHEDULE")) h->schedule = std::atoi(e);
     if (const char* e = std::getenv("KANODE_WIDE")) h->wide = std::atoi(e);
     if (const char* e = std::getenv("KANODE_WIDE_TC")) h->wide_tc = std::atoi(e);
@@ -561,6 +553,58 @@ int kanode_loss_grad_replay_f64(kanode_handle* h, const double* u0, int64_t batc
     if (!fwd_t || !bwd_t) return fail(h, KANODE_ERR_INVALID, "replay needs both step sequences");
     return loss_grad_host<double>(h, u0, batch, t0, t1, saveat, nsave, target, abstol, reltol, loss, grad, du0,
                                   fwd_stats, bwd_stats, fwd_t, bwd_t, max_steps, out);
+}
+int kanode_solve_adjoint(kanode_handle* h, const float* u0, int64_t batch, double t0, double t1, const double* saveat, int32_t nsave,
+                         float abstol, float reltol, const float* dL_dout, float* out, float* grad, float* du0,
+                         kanode_stats* fwd_stats, kanode_stats* bwd_stats) {
+    if (!dL_dout) return fail(h, KANODE_ERR_INVALID, "null cotangent");
+    return loss_grad_host<float>(h, u0, batch, t0, t1, saveat, nsave, nullptr, abstol, reltol, nullptr, grad, du0, fwd_stats, bwd_stats,
+                                 nullptr, nullptr, 0, out, dL_dout);
+}
+int kanode_solve_adjoint_f64(kanode_handle* h, const double* u0, int64_t batch, double t0, double t1, const double* saveat,
+                             int32_t nsave, double abstol, double reltol, const double* dL_dout, double* out, double* grad,
+                             double* du0, kanode_stats* fwd_stats, kanode_stats* bwd_stats) {
+    if (!dL_dout) return fail(h, KANODE_ERR_INVALID, "null cotangent");
+    return loss_grad_host<double>(h, u0, batch, t0, t1, saveat, nsave, nullptr, abstol, reltol, nullptr, grad, du0, fwd_stats, bwd_stats,
+                                  nullptr, nullptr, 0, out, dL_dout);
+}
+int kanode_solve_adjoint_dev(kanode_handle* h, const float* d_u0, int64_t batch, double t0, double t1, const double* saveat,
+                             int32_t nsave, float abstol, float reltol, const float* d_dL_dout, float* d_out, float* d_grad,
+                             float* d_du0, kanode_stats* d_fwd_stats, kanode_stats* d_bwd_stats) {
+    if (int rc = enter(h)) return rc;
+    if (batch < 0 || !d_dL_dout || !d_grad) return fail(h, KANODE_ERR_INVALID, "bad arguments");
+    double* d_loss = nullptr;
+    ENSURE(h, W_LOSS, sizeof(double), d_loss);
+    return loss_grad_dev<float>(h, d_u0, batch, t0, t1, saveat, nsave, nullptr, abstol, reltol, d_loss, d_grad, d_du0, d_fwd_stats,
+                                d_bwd_stats, d_out, nullptr, nullptr, 0, d_dL_dout);
+}
+int kanode_edge_activations(kanode_handle* h, int32_t layer, const float* x, float* act, int64_t K) {
+    return edge_activations_host<float>(h, layer, x, act, K);
+}
+int kanode_edge_activations_f64(kanode_handle* h, int32_t layer, const double* x, double* act, int64_t K) {
+    return edge_activations_host<double>(h, layer, x, act, K);
+}
+int kanode_set_regularizer(kanode_handle* h, double act_reg, double entropy_reg) {
+    if (!h || !(act_reg >= 0.0) || !(entropy_reg >= 0.0)) return fail(h, KANODE_ERR_INVALID, "bad regulariser weights");
+    h->reg_act = act_reg; h->reg_entropy = entropy_reg;
+    return 0;
+}
+int kanode_reg_loss(kanode_handle* h, double act_reg, double entropy_reg, double* loss, float* grad) {
+    if (int rc = enter(h)) return rc;
+    if (!h->have_params || !loss) return fail(h, KANODE_ERR_INVALID, "bad arguments");
+    double* d_l = nullptr; float* d_g = nullptr;
+    ENSURE(h, W_LOSS, sizeof(double), d_l); ENSURE(h, W_GRAD, sizeof(float) * h->np, d_g);
+    CK(h, cudaMemsetAsync(d_l, 0, sizeof(double), h->stream));
+    CK(h, cudaMemsetAsync(d_g, 0, sizeof(float) * h->np, h->stream));
+    const double a0 = h->reg_act, e0 = h->reg_entropy;
+    h->reg_act = act_reg; h->reg_entropy = entropy_reg;
+    const int rc = reg_apply<float>(h, d_l, 1.0, grad ? d_g : nullptr, 1.0);
+    h->reg_act = a0; h->reg_entropy = e0;
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(loss, d_l, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (grad) CK(h, cudaMemcpyAsync(grad, d_g, sizeof(float) * h->np, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
 }
 int kanode_loss_grad_dev(kanode_handle* h, const float* d_u0, int64_t batch, double t0, double t1, const double* saveat,
                          int32_t nsave, const float* d_target, float abstol, float reltol, double* d_loss_sum,

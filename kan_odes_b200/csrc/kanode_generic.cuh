@@ -292,7 +292,7 @@ template <class T, class Fn> __device__ T pw_reverse(const GenericModel& m, cons
 // du = f(u) for either rhs kind (block-wide)
 template <class T>
 __device__ void g_rhs(const GenericModel& m, const T* p, const T* u, T* du, GSmem<T>& sm) {
-    if (m.rhs_kind == KANODE_RHS_CHAIN) { g_chain_forward<T>(m, p, u, du, sm, nullptr); return; }
+    if (m.rhs_kind != KANODE_RHS_SOURCE_LAPLACIAN) { g_chain_forward<T>(m, p, u, du, sm, nullptr); return; }
     const int n = m.n;
     const T ls = (T)m.lap_scale;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
@@ -305,7 +305,7 @@ __device__ void g_rhs(const GenericModel& m, const T* p, const T* u, T* du, GSme
 // ubar = (df/du)^T lam and the parameter part: chain -> stage record; source -> kg[np] (block-reduced, small np)
 template <class T>
 __device__ void g_vjp(const GenericModel& m, const T* p, const T* y, const T* lam, T* ubar, GSmem<T>& sm, T* rec) {
-    if (m.rhs_kind == KANODE_RHS_CHAIN) { g_chain_vjp<T>(m, p, y, lam, ubar, sm, rec); return; }
+    if (m.rhs_kind != KANODE_RHS_SOURCE_LAPLACIAN) { g_chain_vjp<T>(m, p, y, lam, ubar, sm, rec); return; }
     // source model: rec holds kg[np] = sum_j lam_j dkan(y_j)/dp ; np <= GEN_FEAT
     const int n = m.n, np = (int)m.np;
     const T ls = (T)m.lap_scale;
@@ -347,6 +347,52 @@ __device__ void g_vjp(const GenericModel& m, const T* p, const T* y, const T* la
     __syncthreads();
 }
 
+// per-edge activations of layer l (LV/Activation_getter.jl:22-31,44-54): thread per (sample k, input i);
+// act[k][i][o] = sum_g C[o,(i,g)] basis_g(norm(x_i)) + W[o,i] swish(x_i) — the fused basis expansion without the sum over i
+template <class T>
+__global__ void __launch_bounds__(128) edge_activation_kernel(const __grid_constant__ GenericModel m, int l, const T* __restrict__ p,
+                                                              const T* __restrict__ x, T* __restrict__ act, int64_t K) {
+    const GenericLayer& L = m.L[l];
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K * L.I) return;
+    const int i = (int)(idx % L.I);
+    T c[GEN_MAX_G + 1];
+    g_features(L, m.grid + L.goff, x[idx], c);
+    T* a = act + idx * L.O;
+    for (int o = 0; o < L.O; ++o) {
+        T v = T(0);
+        for (int g = 0; g < L.G; ++g) v += p[L.offC + ((long long)i * L.G + g) * L.O + o] * c[g];
+        if (L.use_base) v += p[L.offW + (long long)i * L.O + o] * c[L.G];
+        a[o] = v;
+    }
+}
+
+// reg_loss(p) = act_reg * sum|p| + entropy_reg * (-sum e log e), e = |p| / sum|p|  (LV_driver_KANODE.jl:187-194), three passes:
+// acc[0] = S = sum|p|;  acc[1] = sum |p| log|p| (so that -sum e log e = log S - acc[1]/S);  then the gradient
+//   d reg / d p_j = sign(p_j) * (act_reg - entropy_reg * (log e_j + E) / S)
+template <class T> __global__ void __launch_bounds__(256) reg_sums_kernel(const T* __restrict__ p, size_t n, double* __restrict__ acc) {
+    double s = 0.0, sl = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double a = fabs((double)p[i]);
+        s += a; if (a > 0.0) sl += a * log(a);
+    }
+    for (int d = 16; d > 0; d >>= 1) { s += __shfl_down_sync(0xffffffffu, s, d); sl += __shfl_down_sync(0xffffffffu, sl, d); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], s); atomicAdd(&acc[1], sl); }
+}
+// loss_out (optional): += loss_scale * reg;  grad (optional): += grad_scale * d reg/d p
+template <class T>
+__global__ void __launch_bounds__(256) reg_apply_kernel(const T* __restrict__ p, size_t n, const double* __restrict__ acc, double act_reg,
+                                                        double ent_reg, double* loss_out, double loss_scale, T* __restrict__ grad, double grad_scale) {
+    const double S = acc[0], E = S > 0.0 ? log(S) - acc[1] / S : 0.0;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && loss_out) *loss_out += loss_scale * (S * act_reg + E * ent_reg);
+    if (i >= n || !grad) return;
+    const double v = (double)p[i], a = fabs(v);
+    if (a == 0.0) return;
+    const double dE = -(log(a / S) + E) / S;
+    grad[i] += (T)(grad_scale * (v > 0.0 ? 1.0 : -1.0) * (act_reg + ent_reg * dE));
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // argument blocks (device pointers); per-trajectory workspace slices are carved inside the kernels
 // ---------------------------------------------------------------------------------------------------------
@@ -373,7 +419,7 @@ template <class T> struct GenBwdArgs {
 
 template <class T> __global__ void __launch_bounds__(GEN_BT) generic_rhs_kernel(const __grid_constant__ GenericModel m, const T* p, const T* u, T* du) {
     __shared__ GSmem<T> sm;
-    g_rhs<T>(m, p, u + (int64_t)blockIdx.x * m.n, du + (int64_t)blockIdx.x * m.n, sm);
+    g_rhs<T>(m, p, u + (int64_t)blockIdx.x * m.n, du + (int64_t)blockIdx.x * m.n_out, sm);
 }
 
 // ubar per sample; pbar accumulated over the batch with atomics (utility entry point, not the training path)
@@ -383,8 +429,8 @@ __global__ void __launch_bounds__(GEN_BT) generic_vjp_kernel(const __grid_consta
     __shared__ GSmem<T> sm;
     const int64_t b = blockIdx.x;
     T* rec = recs + b * m.rec_len;
-    g_vjp<T>(m, p, u + b * m.n, lam + b * m.n, ubar + b * m.n, sm, rec);
-    if (m.rhs_kind != KANODE_RHS_CHAIN) {
+    g_vjp<T>(m, p, u + b * m.n, lam + b * m.n_out, ubar + b * m.n, sm, rec);
+    if (m.rhs_kind == KANODE_RHS_SOURCE_LAPLACIAN) {
         for (int j = threadIdx.x; j < (int)m.np; j += blockDim.x) atomicAdd(&pbar[j], rec[j]);
         return;
     }
@@ -514,7 +560,7 @@ __global__ void __launch_bounds__(GEN_BT) generic_forward_kernel(const __grid_co
                     const T v = uprev[i] + h * acc;
                     const int64_t o = (b * a.nsave + sidx) * n + i;
                     if (a.out) a.out[o] = v;
-                    if (DENSE) {
+                    if (DENSE && a.target) {                        // target == null: a.dg holds the caller's cotangents
                         const T e = v - a.target[o];
                         lsum += (double)e * (double)e;
                         a.dg[o] = (T(2) / (T)((double)n * a.nsave)) * e;
@@ -859,6 +905,7 @@ inline int generic_init(kanode_handle* h) {
     const kanode_desc& d = h->desc;
     m = GenericModel{};
     m.n_layers = d.n_layers; m.rhs_kind = d.rhs_kind; m.n = d.n_state; m.np = (long long)h->np;
+    m.n_out = d.rhs_kind == KANODE_RHS_MAP ? d.layers[d.n_layers - 1].out_dims : d.n_state;
     m.lap_scale = d.rhs_kind == KANODE_RHS_SOURCE_LAPLACIAN ? d.lap_coef / (d.dx * d.dx) : 0.0;
     long long off = 0, roff = 0;
     int goff = 0;
@@ -875,7 +922,7 @@ inline int generic_init(kanode_handle* h) {
         L.rx = roff; roff += L.I;
         L.ry = roff; roff += L.O;
     }
-    m.rec_len = d.rhs_kind == KANODE_RHS_CHAIN ? roff : (long long)h->np;
+    m.rec_len = d.rhs_kind != KANODE_RHS_SOURCE_LAPLACIAN ? roff : (long long)h->np;
     return 0;
 }
 
@@ -884,7 +931,7 @@ inline int generic_supported(kanode_handle* h) {
     const kanode_desc& d = h->desc;
     for (int l = 0; l < d.n_layers; ++l) {
         if (d.layers[l].grid_len > GEN_MAX_G) return fail(h, KANODE_ERR_UNSUPPORTED, "grid_len > %d", GEN_MAX_G);
-        if (d.rhs_kind == KANODE_RHS_CHAIN && l > 0 && d.layers[l].in_dims > GEN_ACT)
+        if (d.rhs_kind != KANODE_RHS_SOURCE_LAPLACIAN && l > 0 && d.layers[l].in_dims > GEN_ACT)
             return fail(h, KANODE_ERR_UNSUPPORTED, "hidden width %d > %d", d.layers[l].in_dims, GEN_ACT);
         if (d.rhs_kind == KANODE_RHS_SOURCE_LAPLACIAN && (d.layers[l].in_dims > GEN_PW || d.layers[l].out_dims > GEN_PW))
             return fail(h, KANODE_ERR_UNSUPPORTED, "pointwise chain wider than %d", GEN_PW);

@@ -20,7 +20,7 @@ struct GenericLayer {
     long long rx, ry;          // offsets of x_l (layer input) and ybar_l (output cotangent) in a backward stage record
 };
 struct GenericModel {
-    int n_layers, rhs_kind, n;
+    int n_layers, rhs_kind, n, n_out;   // n_out: output length of one sample (= n except for KANODE_RHS_MAP)
     long long np;
     double lap_scale;          // lap_coef / dx^2
     long long rec_len;         // length of one backward stage record
@@ -48,13 +48,14 @@ struct kanode_handle {
     uint64_t params_version = 0;     // bumped by set_params; derived device copies are refreshed lazily
     uint64_t wpk_version[2] = {~0ull, ~0ull};
     uint64_t wlg_version[2] = {~0ull, ~0ull};   // lane-block weight image of the lane-group adjoint kernel
-    int bwd_lg = 1;                  // small path: 1 = lane-group adjoint kernel, 0 = round-1 thread-per-trajectory kernel (KANODE_BWD)
     int bwd_maxiters = 100000;       // KANODE_BWD_MAXIT (timing experiments)
-    int long_slots = 256;            // KANODE_LONG_SLOTS (round-1 kernel)
+    double reg_act = 0.0, reg_entropy = 0.0;   // kanode_set_regularizer
+    int n_out = 0;                   // output length of one sample of kanode_rhs (= n except for KANODE_RHS_MAP)
+    int last_failed[2] = {0, 0};     // failed forward / adjoint solves of the last host-pointer loss_grad call
     unsigned attr_done = 0;          // per-handle (= per-device) one-time cudaFuncSetAttribute bits
     int rec_cap = 32;
     int64_t order_B[2] = {0, 0};     // batch size the cached launch order (per dtype) was built for; 0 = none
-    int schedule = 1;                // 1: reuse last call's step counts to launch long backward solves first
+    int schedule = 1;                // 1: launch order of the adjoint warps from the last call's iteration counts (KANODE_SCHEDULE)
     int lg_shape = 0;                // launch shape of the lane-group adjoint kernel (KANODE_LG_SHAPE; 0 = default)
     int64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fwd start / bwd start / reduce start / end
@@ -65,7 +66,7 @@ struct kanode_handle {
     void* stage = nullptr; size_t stage_bytes = 0;   // pinned host staging block for the results of the host entry points
     // grow-only device workspace, keyed by purpose
     enum { W_U0, W_OUT, W_TARGET, W_STATS_F, W_STATS_B, W_SAVEAT, W_REC_T, W_REC, W_NSTEPS, W_RET, W_DG, W_FAC, W_G,
-           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_WPK32, W_WPK64, W_LAM, W_GEN, W_GEN2, W_LS, W_ATT, W_ORDER, W_WIDE_F, W_WIDE_B, W_W1T32, W_W1T64, W_W2IMG, W_W2TIMG, W_W1IMG, W_WIDE_R, W_WLG32, W_WLG64, W_GPART, W_SLAB, W_RPF, W_RPB, W_COT, W_COUNT };
+           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_WPK32, W_WPK64, W_LAM, W_GEN, W_GEN2, W_LS, W_ATT, W_ORDER, W_WIDE_F, W_WIDE_B, W_W1T32, W_W1T64, W_W2IMG, W_W2TIMG, W_W1IMG, W_WIDE_R, W_WLG32, W_WLG64, W_GPART, W_SLAB, W_RPF, W_RPB, W_COT, W_FAILCNT, W_REG, W_ACT, W_COUNT };
     DevBuf ws[W_COUNT];
     kanode::GenericModel gm{};               // layer table for the generic kernels
     // wide (batched lockstep) engine: attempts the last forward-only / dense-forward / backward call needed, counter state
@@ -117,6 +118,8 @@ inline size_t count_params(const kanode_desc* d) {
         if (d->layers[0].in_dims != d->n_state || d->layers[d->n_layers - 1].out_dims != d->n_state) return 0;
     } else if (d->rhs_kind == KANODE_RHS_SOURCE_LAPLACIAN) {
         if (d->layers[0].in_dims != 1 || d->layers[d->n_layers - 1].out_dims != 1 || d->n_state < 3 || !(d->dx > 0)) return 0;
+    } else if (d->rhs_kind == KANODE_RHS_MAP) {
+        if (d->layers[0].in_dims != d->n_state) return 0;
     } else return 0;
     return np;
 }

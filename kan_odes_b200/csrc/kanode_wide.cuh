@@ -1335,7 +1335,7 @@ __global__ void __launch_bounds__(W_ET) wide_fwd_accept_kernel(const WideCtl c, 
                 const T v = up + h * accv;
                 const int64_t o = ((int64_t)b * a.nsave + s) * n + i;
                 if (a.out) a.out[o] = v;
-                if (a.rec) {
+                if (a.rec && a.target) {                            // target == null: a.dg holds the caller's cotangents
                     const T d = v - a.target[o];
                     lsum += (double)d * (double)d;
                     a.dg[o] = (T(2) / (T)((double)n * a.nsave)) * d;
@@ -1650,11 +1650,18 @@ inline int wide_attempt_graph(kanode_handle* h, int slot, const std::vector<char
         CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         const int64_t n0 = body();
         cudaGraph_t graph = nullptr;
-        CK(h, cudaStreamEndCapture(h->stream, &graph));
+        // always end the capture: an error inside the body must not leave the caller's stream in capture mode
+        const cudaError_t ec = cudaStreamEndCapture(h->stream, &graph);
         const int64_t extra = h->launches - l0;          // launches the helpers counted on the handle directly
         h->launches = l0;
-        CK(h, cudaGraphInstantiate(&g.exec, graph, 0));
+        if (n0 < 0 || ec != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            (void)cudaGetLastError();
+            return fail(h, KANODE_ERR_CUDA, "capturing a step attempt failed: %s", ec != cudaSuccess ? cudaGetErrorString(ec) : "a kernel of the attempt could not be enqueued");
+        }
+        const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
         cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) { g.exec = nullptr; return fail(h, KANODE_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ei)); }
         g.sig = sig; g.nodes = (int)(n0 + extra);
     }
     *out = g.exec;
@@ -1746,8 +1753,8 @@ int wide_l2_reverse(kanode_handle* h, const WideModel& m, const T* p, const T* h
             constexpr size_t smem = 2 * (size_t)KC * TC_M * 16 + 2 * (size_t)KC * TC_N * 16 + (size_t)TC_N * NWP * 4 + 64;
             const float* img = nullptr;
             if (int rc = wide_w2t_image<H, G>(h, m, p, &img)) return rc;
-            static bool attr_set = false;
-            if (!attr_set) { CK(h, cudaFuncSetAttribute(wide_l2_vjp_tc_kernel<H, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+            constexpr unsigned abit = 4u << (G == 5 ? 0 : 1);           // once per handle (= per device) and instantiation
+            if (!(h->attr_done & abit)) { CK(h, cudaFuncSetAttribute(wide_l2_vjp_tc_kernel<H, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); h->attr_done |= abit; }
             const int nblk = m.n / TC_KB;
             wide_l2_vjp_tc_kernel<H, G><<<dim3(nblk, (unsigned)((B + TC_N - 1) / TC_N)), 128, smem, h->stream>>>(m, img, hidden, in, B, part);
             wide_sum_partials_kernel<float, H><<<(unsigned)((B * H + 3) / 4), 128, 0, h->stream>>>(part, nblk, B, hbar, in.mask);
@@ -1768,8 +1775,8 @@ int wide_l2_forward(kanode_handle* h, const WideModel& m, const T* p, const T* h
             constexpr size_t smem = 2 * (size_t)KC * TC_M * 16 + 2 * (size_t)KC * TC_N * 16 + 64;
             const float* img = nullptr;
             if (int rc = wide_w2_image<H, G>(h, m, p, &img)) return rc;
-            static bool attr_set = false;
-            if (!attr_set) { CK(h, cudaFuncSetAttribute(wide_l2_fwd_tc_kernel<H, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+            constexpr unsigned abit = 16u << (G == 5 ? 0 : 1);
+            if (!(h->attr_done & abit)) { CK(h, cudaFuncSetAttribute(wide_l2_fwd_tc_kernel<H, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); h->attr_done |= abit; }
             const dim3 g((m.n + TC_M - 1) / TC_M, (unsigned)((B + TC_N - 1) / TC_N));
             wide_l2_fwd_tc_kernel<H, G><<<g, 128, smem, h->stream>>>(m, img, hidden, out, mask, B);
             return 0;
@@ -1975,8 +1982,8 @@ int wide_loss_grad_t(kanode_handle* h, const T* p, const T* d_u0, int64_t B, dou
             constexpr int KU = (G + 1 + 3) / 4 * 4, KC = TC1_UC * KU / 4;
             constexpr size_t smem1 = 2 * (2 * (size_t)KC * TC_M * 16 + 2 * (size_t)KC * TC1_N * 16) + 64;
             if (int rc = wide_w1_image<H, G>(h, m, p, &w1img)) return rc;
-            static bool attr_set = false;
-            if (!attr_set) { CK(h, cudaFuncSetAttribute(wide_l1_fwd_tc_kernel<H, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1)); attr_set = true; }
+            constexpr unsigned abit = 64u << (G == 5 ? 0 : 1);
+            if (!(h->attr_done & abit)) { CK(h, cudaFuncSetAttribute(wide_l1_fwd_tc_kernel<H, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1)); h->attr_done |= abit; }
             l1_tc = true;
         }
     }

@@ -105,6 +105,24 @@ class KDense:
     def statelength(self) -> int:                                                  # kdense.jl:94-96
         return self.grid_len
 
+    def __call__(self, x, p, st=None, *, device: int = 0, dtype=None):
+        """(l::KDense)(x, p, st) -> (y, st)  (kdense.jl:109-130; direct calls at Activation_getter.jl:39,
+        Allen-Cahn_Source.jl:91).  x: [in_dims] or [K, in_dims] (one sample per row; Julia's columns), p: {"C": [O, G*I],
+        "W": [O, I]} or the layer's flat [vec(C); vec(W)].  Evaluated by the CUDA library through a KANODE_RHS_MAP handle
+        (cached on the layer per device / dtype)."""
+        from .node import KanOde
+        x = np.asarray(x)
+        dt = np.dtype(dtype if dtype is not None else (np.float64 if x.dtype == np.float64 else np.float32))
+        key = (device, dt.str)
+        cache = self.__dict__.setdefault("_map_handles", {})
+        if key not in cache:
+            cache[key] = KanOde(Chain(self), rhs_kind=abi.RHS_MAP, device=device, dtype=dt)
+        ode = cache[key]
+        flat = flatten_params({"layer_1": p}) if isinstance(p, dict) else np.asarray(p)
+        ode.set_params(flat.astype(dt))
+        y = ode.rhs(x.reshape(-1, self.in_dims))
+        return (y[0] if x.ndim == 1 else y), st
+
     def _fill(self, d: abi.LayerDesc) -> None:
         d.in_dims, d.out_dims, d.grid_len = self.in_dims, self.out_dims, self.grid_len
         d.normalizer, d.basis = self.normalizer.code, self.basis_func.code
@@ -139,6 +157,63 @@ class Chain:
         d.n_state = self.layers[0].in_dims if n_state is None else int(n_state)
         d.lap_coef, d.dx = float(lap_coef), float(dx)
         return d
+
+
+def activation_getter(chain: Chain, p, X, *, device: int = 0, dtype=np.float64):
+    """LV/Activation_getter.jl:3-63 for any chain: the per-edge activations of every layer at the inputs the samples X [K, I_1]
+    drive through the chain.  Returns (acts, layer_inputs): acts[l][k, i, o] (kanode_edge_activations), layer_inputs[l] [K, I_l].
+    For the reference's two-layer LV model: activations_x = acts[0][:, 0, :], activations_y = acts[0][:, 1, :] ([K, O]), and
+    its activations_second[2*(i-1)+o, k] = acts[1][k, i, o]."""
+    from .node import KanOde
+    dt = np.dtype(dtype)
+    ode = KanOde(chain, rhs_kind=abi.RHS_MAP, device=device, dtype=dt)
+    ode.set_params(np.asarray(p, dtype=dt))
+    x = np.asarray(X, dtype=dt).reshape(-1, chain.layers[0].in_dims)
+    acts, inputs = [], []
+    for l in range(len(chain.layers)):
+        inputs.append(x)
+        a = ode.edge_activations(l, x)
+        acts.append(a)
+        x = a.sum(axis=1)                                             # the layer output (Activation_getter.jl:33-36,39)
+    ode.close()
+    return acts, inputs
+
+
+def prune(chain: Chain, p, X, theta: float = 1e-2, *, device: int = 0):
+    """prune (LV_driver_KANODE.jl:52-108) for a two-layer chain [I, H, O]: a hidden node is kept when both its largest incoming
+    and its largest outgoing activation magnitude over the samples X exceed theta (gamma_pr = 1e-2 in the manuscript).
+    Returns (new_chain, new_flat_params, nodes_to_keep).  (The reference fills the pruned layer-2 W from layer_2.C columns
+    (:103) — an indexing slip; here W2 keeps its own columns.)"""
+    if len(chain.layers) != 2:
+        raise ValueError("prune handles the reference's two-layer KAN")
+    l1, l2 = chain.layers
+    acts, _ = activation_getter(chain, p, X, device=device)
+    keep = []
+    for j in range(l1.out_dims):
+        input_score = np.abs(acts[0][:, :, j]).max()                  # over samples and inputs (:78)
+        output_score = np.abs(acts[1][:, j, :]).max()                 # over samples and outputs (:79)
+        if min(input_score, output_score) > theta:
+            keep.append(j)
+    if not keep:
+        raise ValueError("every hidden node would be pruned")
+    ps = unflatten_params(chain, np.asarray(p))
+    G = l1.grid_len
+    c2cols = np.concatenate([np.arange(j * G, (j + 1) * G) for j in keep])
+    new = {"layer_1": {"C": ps["layer_1"]["C"][keep, :]}, "layer_2": {"C": ps["layer_2"]["C"][:, c2cols]}}
+    if l1.use_base_act:
+        new["layer_1"]["W"] = ps["layer_1"]["W"][keep, :]
+    if l2.use_base_act:
+        new["layer_2"]["W"] = ps["layer_2"]["W"][:, keep]
+    import dataclasses
+    nc = Chain(dataclasses.replace(l1, out_dims=len(keep)), dataclasses.replace(l2, in_dims=len(keep)))
+    flat = np.concatenate([np.asarray(new[n][k]).reshape(-1, order="F") for n in ("layer_1", "layer_2") for k in ("C", "W") if k in new[n]])
+    return nc, flat.astype(np.asarray(p).dtype), keep
+
+
+def reg_loss(p, act_reg: float = 1.0, entropy_reg: float = 1.0) -> float:
+    """reg_loss (LV_driver_KANODE.jl:187-194) on the host — a reference for KanOde.reg_loss / set_regularizer."""
+    a = np.abs(np.asarray(p, dtype=np.float64)); S = a.sum(); e = a[a > 0] / S
+    return float(S * act_reg - (e * np.log(e)).sum() * entropy_reg)
 
 
 def setup(rng: np.random.Generator, chain: Chain):

@@ -72,6 +72,7 @@ class KanOde:
         self.chain = chain
         self.desc = chain.desc(rhs_kind, n_state, lap_coef, dx)
         self.n = int(self.desc.n_state)
+        self.n_out = chain.layers[-1].out_dims if rhs_kind == abi.RHS_MAP else self.n
         self.np_ = int(self.lib.kanode_param_count(C.byref(self.desc)))
         if self.np_ == 0:
             raise abi.KanodeError("invalid model descriptor")
@@ -115,14 +116,14 @@ class KanOde:
     # ---- RHS / VJP -----------------------------------------------------------------------------------
     def rhs(self, u):
         u = self._arr(u).reshape(-1, self.n)
-        du = np.empty_like(u)
+        du = np.empty((u.shape[0], self.n_out), self.dtype)            # n_out != n only for a map handle (abi.RHS_MAP)
         rc = self._fn("kanode_rhs")(self.h, _ptr(u), _ptr(du), C.c_int64(u.shape[0]))
         abi.check(self.lib, self.h, rc, "kanode_rhs")
         return du
 
     def vjp(self, u, lam):
         u = self._arr(u).reshape(-1, self.n)
-        lam = self._arr(lam).reshape(-1, self.n)
+        lam = self._arr(lam).reshape(-1, self.n_out)
         ubar = np.empty_like(u); pbar = np.empty(self.np_, self.dtype)
         rc = self._fn("kanode_vjp")(self.h, _ptr(u), _ptr(lam), _ptr(ubar), _ptr(pbar), C.c_int64(u.shape[0]))
         abi.check(self.lib, self.h, rc, "kanode_vjp")
@@ -143,10 +144,13 @@ class KanOde:
         abi.check(self.lib, self.h, rc, "kanode_solve")
         return ODESolution(sa, out, Stats.from_raw(stats))
 
-    def loss_grad(self, u0, tspan, saveat, target, abstol=1e-6, reltol=1e-3, want_du0=True, want_stats=True):
+    def loss_grad(self, u0, tspan, saveat, target, abstol=1e-6, reltol=1e-3, want_du0=True, want_stats=True,
+                  allow_failed=False):
         """loss = mean(abs2, target - predict) and d loss / d p (what `Zygote.gradient(loss, p)[1]` returns in the reference,
         LV_driver_KANODE.jl:197-203,284).  `want_du0` / `want_stats` add d loss / d u0 and the per-trajectory solver
-        statistics to the result (two more device-to-host copies of batch-sized arrays)."""
+        statistics to the result (two more device-to-host copies of batch-sized arrays).  A trajectory whose forward or
+        adjoint solve does not return Success raises KanodeError (the reference's `loss` throws on a short solution);
+        `allow_failed=True` returns the result anyway (the failed trajectories are left out of loss / grad)."""
         u0 = self._arr(u0).reshape(-1, self.n)
         B = u0.shape[0]
         sa = np.ascontiguousarray(saveat, dtype=np.float64).reshape(-1)
@@ -161,8 +165,9 @@ class KanOde:
                       self._real, self._real, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         rc = f(self.h, _ptr(u0), B, float(tspan[0]), float(tspan[1]), _ptr(sa), sa.size, _ptr(target), abstol, reltol,
                C.byref(loss), _ptr(grad), _ptr(du0), fst, bst)
-        abi.check(self.lib, self.h, rc, "kanode_loss_grad")
-        out = dict(loss=float(loss.value), grad=grad)
+        if not (rc == abi.ERR_SOLVER and allow_failed):
+            abi.check(self.lib, self.h, rc, "kanode_loss_grad")
+        out = dict(loss=float(loss.value), grad=grad, solver_failed=(rc == abi.ERR_SOLVER))
         if want_du0:
             out["du0"] = du0
         if want_stats:
@@ -193,6 +198,50 @@ class KanOde:
         return dict(loss=float(loss.value), grad=grad, du0=du0, out=out, fwd_stats=Stats.from_raw(fst),
                     bwd_stats=Stats.from_raw(bst))
 
+    def solve_adjoint(self, u0, tspan, saveat, dL_dout, abstol=1e-6, reltol=1e-3, allow_failed=False):
+        """Pullback of the solve for an arbitrary loss: given dL/dpred [batch, nsave, n] returns the predictions of the dense
+        forward solve, grad = sum_b (d pred_b/d p)^T dL_dout[b] and du0 (kanode_solve_adjoint; what Zygote.gradient(loss, p)
+        runs for the reference's loss, LV_driver_KANODE.jl:197-203,284 / Burgers_Surrogate.jl:105-107,191)."""
+        u0 = self._arr(u0).reshape(-1, self.n)
+        B = u0.shape[0]
+        sa = np.ascontiguousarray(saveat, dtype=np.float64).reshape(-1)
+        cot = self._arr(dL_dout).reshape(B, sa.size, self.n)
+        out = np.empty_like(cot); grad = np.empty(self.np_, self.dtype); du0 = np.empty_like(u0)
+        fst = (abi.Stats * B)(); bst = (abi.Stats * B)()
+        f = self._fn("kanode_solve_adjoint")
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_int32, self._real, self._real,
+                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = f(self.h, _ptr(u0), B, float(tspan[0]), float(tspan[1]), _ptr(sa), sa.size, abstol, reltol, _ptr(cot), _ptr(out),
+               _ptr(grad), _ptr(du0), fst, bst)
+        if not (rc == abi.ERR_SOLVER and allow_failed):
+            abi.check(self.lib, self.h, rc, "kanode_solve_adjoint")
+        return dict(out=out, grad=grad, du0=du0, fwd_stats=Stats.from_raw(fst), bwd_stats=Stats.from_raw(bst))
+
+    def edge_activations(self, layer: int, x):
+        """act[k, i, o] = C[o,(i,g)]·basis_g(norm(x[k,i])) + W[o,i]·swish(x[k,i]) of layer `layer` (0-based) at its inputs
+        x [K, I] (LV/Activation_getter.jl); act.sum(axis=1) is the layer output."""
+        L = self.chain.layers[layer]
+        x = self._arr(x).reshape(-1, L.in_dims)
+        act = np.empty((x.shape[0], L.in_dims, L.out_dims), self.dtype)
+        rc = self._fn("kanode_edge_activations")(self.h, C.c_int32(layer), _ptr(x), _ptr(act), C.c_int64(x.shape[0]))
+        abi.check(self.lib, self.h, rc, "kanode_edge_activations")
+        return act
+
+    def set_regularizer(self, act_reg: float = 0.0, entropy_reg: float = 0.0) -> None:
+        """reg_loss(p, act_reg, entropy_reg) is added to every loss_grad from now on (LV_driver_KANODE.jl:187-201:
+        `sparse_on == 1` uses (5e-4, 0)); (0, 0) switches it off."""
+        self.lib.kanode_set_regularizer.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        rc = self.lib.kanode_set_regularizer(self.h, float(act_reg), float(entropy_reg))
+        abi.check(self.lib, self.h, rc, "kanode_set_regularizer")
+
+    def reg_loss(self, act_reg: float = 1.0, entropy_reg: float = 1.0):
+        """reg_loss of the current parameters and its gradient (float32)."""
+        loss = C.c_double(0); grad = np.empty(self.np_, np.float32)
+        self.lib.kanode_reg_loss.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        rc = self.lib.kanode_reg_loss(self.h, float(act_reg), float(entropy_reg), C.byref(loss), _ptr(grad))
+        abi.check(self.lib, self.h, rc, "kanode_reg_loss")
+        return float(loss.value), grad
+
     def launch_count(self) -> int:
         return int(self.lib.kanode_launch_count(self.h))
 
@@ -221,6 +270,25 @@ class NeuralODE:
         self.ode.set_params(p)
         r = self.ode.loss_grad(u0, self.tspan, self.saveat, target, self.abstol, self.reltol)
         return r["loss"], r["grad"], r
+
+    def pullback(self, u0, p):
+        """`pred, back = Zygote.pullback(p -> Array(node(u0, p, st)[1]), p)`: back(dL_dpred) -> (dL/dp, dL/du0)."""
+        self.ode.set_params(p)
+        sol = self.ode.solve(u0, self.tspan, self.saveat, self.abstol, self.reltol)
+
+        def back(dL_dpred):
+            self.ode.set_params(p)
+            r = self.ode.solve_adjoint(u0, self.tspan, self.saveat, dL_dpred, self.abstol, self.reltol)
+            return r["grad"], r["du0"]
+        return sol.array, back
+
+    def gradient(self, loss_and_cotangent, u0, p):
+        """`Zygote.gradient(loss, p)[1]` for the reference's unchanged `loss(p)`: `loss_and_cotangent(pred)` returns
+        (loss value, dloss/dpred) for pred [batch, nsave, n] — any loss of the predictions (mean(abs2, X - pred), a transposed
+        target, extra terms), differentiated by the caller; the solve's pullback comes from kanode_solve_adjoint."""
+        pred, back = self.pullback(u0, p)
+        value, cot = loss_and_cotangent(pred)
+        return value, back(cot)[0]
 
 
 class SourceODE(NeuralODE):

@@ -171,6 +171,8 @@ template <class T> bool build_model(const kanode_desc* d, Model<T>& m) {
     } else if (m.rhs_kind == KANODE_RHS_SOURCE_LAPLACIAN) {
         if (m.L.front().I != 1 || m.L.back().O != 1 || m.n < 3) return false;
         m.lap_scale = (T)(d->lap_coef / (d->dx * d->dx));
+    } else if (m.rhs_kind == KANODE_RHS_MAP) {                      // a chain used as a map: only chain_forward / activations apply
+        if (m.L.front().I != m.n) return false;
     } else return false;
     return true;
 }
@@ -558,7 +560,8 @@ template <class T>
 int loss_grad_one(const Model<T>& m, const T* p, const T* u0, double t0, double t1, const double* saveat, int nsave,
                   const T* target, const SolveOpts& o, double& loss_sum, T* grad /* [np], overwritten */,
                   T* du0 /* [n] or null */, kanode_stats& fst, kanode_stats& bst, T* out_opt,
-                  double* fwd_t = nullptr, double* bwd_t = nullptr, int step_cap = 0) {
+                  double* fwd_t = nullptr, double* bwd_t = nullptr, int step_cap = 0,
+                  const T* cot = nullptr /* caller-supplied dL/dpred [nsave][n]: replaces the MSE cotangent (target unused) */) {
     const int n = m.n; const size_t np = m.np; const int N = n + (int)np;
     Dense<T> dense;
     std::vector<T> out((size_t)nsave * n);
@@ -571,7 +574,8 @@ int loss_grad_one(const Model<T>& m, const T* p, const T* u0, double t0, double 
     std::vector<T> dg((size_t)nsave * n);
     double ls = 0;
     const T scale = T(2) / (T)((double)n * nsave);
-    for (size_t i = 0; i < out.size(); ++i) { const T e = out[i] - target[i]; ls += (double)e * (double)e; dg[i] = scale * e; }
+    if (cot) std::copy(cot, cot + out.size(), dg.begin());      // any loss(pred): Zygote hands its cotangent to the adjoint
+    else for (size_t i = 0; i < out.size(); ++i) { const T e = out[i] - target[i]; ls += (double)e * (double)e; dg[i] = scale * e; }
     loss_sum = ls;
     std::fill(grad, grad + np, T(0));
     if (fst.retcode != KANODE_RET_SUCCESS) { bst = kanode_stats{0, 0, 0, fst.retcode}; if (du0) std::fill(du0, du0 + n, T(0)); return 0; }
@@ -667,6 +671,77 @@ template <class T> struct Api {
         for (size_t i = 0; i < m.np; ++i) grad[i] = (T)(gsum[i] / (double)batch);
         return 0;
     }
+    // pullback of the solve: grad = sum_b (d pred_b / d p)^T cot_b, du0[b] = (d pred_b / d u0_b)^T cot_b  (no 1/batch: the
+    // cotangent carries every scale), what Zygote.gradient(loss, p) does for an arbitrary loss(pred)
+    // (LV_driver_KANODE.jl:197-203 with the optional reg term, Burgers_Surrogate.jl:105-107 with a transposed target)
+    static int adjoint(const kanode_desc* d, const T* p, const T* u0, int64_t batch, double t0, double t1,
+                       const double* saveat, int nsave, const T* cot, double abstol, double reltol,
+                       T* grad, T* du0, kanode_stats* fst, kanode_stats* bst, T* out_opt) {
+        Model<T> m; if (!build_model(d, m)) return KANODE_ERR_INVALID;
+        SolveOpts o; o.abstol = abstol; o.reltol = reltol;
+        std::vector<double> gsum(m.np, 0.0);
+#pragma omp parallel
+        {
+            std::vector<T> g(m.np); std::vector<double> gl(m.np, 0.0);
+#pragma omp for schedule(dynamic, 16)
+            for (int64_t b = 0; b < batch; ++b) {
+                kanode_stats f, bk; double ls = 0;
+                loss_grad_one(m, p, u0 + b * m.n, t0, t1, saveat, nsave, (const T*)nullptr, o, ls, g.data(),
+                              du0 ? du0 + b * m.n : nullptr, f, bk, out_opt ? out_opt + (size_t)b * nsave * m.n : nullptr,
+                              nullptr, nullptr, 0, cot + (size_t)b * nsave * m.n);
+                for (size_t i = 0; i < m.np; ++i) gl[i] += (double)g[i];
+                if (fst) fst[b] = f;
+                if (bst) bst[b] = bk;
+            }
+#pragma omp critical
+            { for (size_t i = 0; i < m.np; ++i) gsum[i] += gl[i]; }
+        }
+        for (size_t i = 0; i < m.np; ++i) grad[i] = (T)gsum[i];
+        return 0;
+    }
+    // a chain evaluated as a map x[I_0] -> y[O_last] (direct layer call, kdense.jl:109-130)
+    static int map(const kanode_desc* d, const T* p, const T* x, T* y, int64_t batch) {
+        Model<T> m; if (!build_model(d, m)) return KANODE_ERR_INVALID;
+        Tape<T> tp; tp.init(m);
+        const int I = m.L.front().I, O = m.L.back().O;
+        for (int64_t b = 0; b < batch; ++b) chain_forward(m, p, x + b * I, y + b * O, tp);
+        return 0;
+    }
+    // per-edge activations of layer l at its inputs x[K][I]: act[k][i][o] = sum_g C[o,(i,g)] basis_g(norm(x_i)) + W[o,i] swish(x_i)
+    // (Activation_getter.jl:22-31,44-54; their sum over i is the layer output, :33-36)
+    static int edge_activations(const kanode_desc* d, int l, const T* p, const T* x, T* act, int64_t K) {
+        Model<T> m; if (!build_model(d, m)) return KANODE_ERR_INVALID;
+        if (l < 0 || l >= (int)m.L.size()) return KANODE_ERR_INVALID;
+        const auto& L = m.L[l];
+        const T* C = p + L.offC; const T* W = p + L.offW;
+        for (int64_t k = 0; k < K; ++k)
+            for (int i = 0; i < L.I; ++i) {
+                const T xi = x[k * L.I + i];
+                const T xn = normalize(L.norm, xi);
+                T* a = act + ((size_t)k * L.I + i) * L.O;
+                std::fill(a, a + L.O, T(0));
+                for (int g = 0; g < L.G; ++g) {
+                    T y, dy; basis_eval(L.basis, (xn - L.grid[g]) * L.inv_h, y, dy);
+                    const T* col = C + ((size_t)i * L.G + g) * L.O;
+                    for (int o = 0; o < L.O; ++o) a[o] += col[o] * y;
+                }
+                if (L.use_base) { const T s = xi * sigmoid(xi); const T* col = W + (size_t)i * L.O; for (int o = 0; o < L.O; ++o) a[o] += col[o] * s; }
+            }
+        return 0;
+    }
+    // reg_loss(p, act_reg, entropy_reg) (LV_driver_KANODE.jl:187-194) and its gradient (what Zygote differentiates at :199-201)
+    static int reg_loss(const T* p, size_t np, double act_reg, double entropy_reg, double* loss, T* grad) {
+        double S = 0; for (size_t i = 0; i < np; ++i) S += std::fabs((double)p[i]);
+        double E = 0;
+        for (size_t i = 0; i < np; ++i) { const double e = std::fabs((double)p[i]) / S; if (e > 0) E -= e * std::log(e); }
+        *loss = S * act_reg + E * entropy_reg;
+        if (grad) for (size_t i = 0; i < np; ++i) {
+            const double a = std::fabs((double)p[i]), sg = p[i] > 0 ? 1.0 : (p[i] < 0 ? -1.0 : 0.0);
+            const double dE = a > 0 ? -(std::log(a / S) + E) / S : 0.0;          // d(-sum e log e)/d|p_i|
+            grad[i] = (T)(sg * (act_reg + entropy_reg * dE));
+        }
+        return 0;
+    }
 };
 
 }  // namespace
@@ -718,6 +793,24 @@ int kanode_oracle_set_threads(int n) {
 
 ORACLE_DEFINE(f64, double)
 ORACLE_DEFINE(f32, float)
+
+#define ORACLE_DEFINE2(SUF, T)                                                                                       \
+    int kanode_oracle_adjoint_##SUF(const kanode_desc* d, const T* p, const T* u0, int64_t batch, double t0, double t1, \
+                                    const double* saveat, int nsave, const T* cot, double abstol, double reltol,     \
+                                    T* grad, T* du0, kanode_stats* fst, kanode_stats* bst, T* out_opt) {            \
+        return Api<T>::adjoint(d, p, u0, batch, t0, t1, saveat, nsave, cot, abstol, reltol, grad, du0, fst, bst, out_opt); \
+    }                                                                                                                \
+    int kanode_oracle_map_##SUF(const kanode_desc* d, const T* p, const T* x, T* y, int64_t batch) {                 \
+        return Api<T>::map(d, p, x, y, batch);                                                                       \
+    }                                                                                                                \
+    int kanode_oracle_edge_activations_##SUF(const kanode_desc* d, int l, const T* p, const T* x, T* act, int64_t K) { \
+        return Api<T>::edge_activations(d, l, p, x, act, K);                                                         \
+    }                                                                                                                \
+    int kanode_oracle_reg_loss_##SUF(const T* p, size_t np, double act_reg, double entropy_reg, double* loss, T* grad) { \
+        return Api<T>::reg_loss(p, np, act_reg, entropy_reg, loss, grad);                                            \
+    }
+ORACLE_DEFINE2(f64, double)
+ORACLE_DEFINE2(f32, float)
 
 // exposed for the controller / tableau tests
 float kanode_oracle_fastpower(double x, double y) { return fastpower(x, y); }

@@ -117,6 +117,47 @@ class Oracle:
             res["fwd_t"] = fwd_t; res["bwd_t"] = bwd_t
         return res
 
+    def adjoint(self, p, u0, tspan, saveat, cot, abstol=1e-6, reltol=1e-3):
+        """Pullback of the solve with caller-supplied cotangents dL/dpred [B, nsave, n] (kanode_solve_adjoint's counterpart):
+        grad = sum_b (d pred_b/d p)^T cot_b (no 1/B), du0, predictions, statistics."""
+        u0 = self._a(u0).reshape(-1, self.n); p = self._a(p)
+        B = u0.shape[0]
+        sa = np.ascontiguousarray(saveat, dtype=np.float64)
+        cot = self._a(cot).reshape(B, sa.size, self.n)
+        grad = np.empty(self.np_, self.dtype); du0 = np.empty_like(u0); out = np.empty_like(cot)
+        fst = (abi.Stats * B)(); bst = (abi.Stats * B)()
+        rc = self._fn("adjoint")(C.byref(self.desc), _ptr(p), _ptr(u0), C.c_int64(B), C.c_double(tspan[0]), C.c_double(tspan[1]),
+                                 _ptr(sa), C.c_int(sa.size), _ptr(cot), C.c_double(abstol), C.c_double(reltol), _ptr(grad),
+                                 _ptr(du0), fst, bst, _ptr(out))
+        assert rc == 0, rc
+        return dict(grad=grad, du0=du0, out=out, fwd_stats=np.frombuffer(fst, dtype=np.int32).reshape(B, 4).copy(),
+                    bwd_stats=np.frombuffer(bst, dtype=np.int32).reshape(B, 4).copy())
+
+    def map(self, p, x):
+        """The chain as a map x [K, I_first] -> y [K, O_last] (direct layer call, kdense.jl:109-130); desc.rhs_kind = RHS_MAP."""
+        I = int(self.desc.layers[0].in_dims); O = int(self.desc.layers[self.desc.n_layers - 1].out_dims)
+        x = self._a(x).reshape(-1, I); p = self._a(p)
+        y = np.empty((x.shape[0], O), self.dtype)
+        rc = self._fn("map")(C.byref(self.desc), _ptr(p), _ptr(x), _ptr(y), C.c_int64(x.shape[0]))
+        assert rc == 0, rc
+        return y
+
+    def edge_activations(self, p, layer, x):
+        """act[k, i, o] of layer `layer` at its inputs x [K, I_l] (LV/Activation_getter.jl)."""
+        L = self.desc.layers[layer]
+        x = self._a(x).reshape(-1, int(L.in_dims)); p = self._a(p)
+        act = np.empty((x.shape[0], int(L.in_dims), int(L.out_dims)), self.dtype)
+        rc = self._fn("edge_activations")(C.byref(self.desc), C.c_int(layer), _ptr(p), _ptr(x), _ptr(act), C.c_int64(x.shape[0]))
+        assert rc == 0, rc
+        return act
+
+    def reg_loss(self, p, act_reg=1.0, entropy_reg=1.0):
+        """reg_loss (LV_driver_KANODE.jl:187-194) and its gradient."""
+        p = self._a(p); loss = C.c_double(0); grad = np.empty_like(p)
+        rc = self._fn("reg_loss")(_ptr(p), C.c_size_t(p.size), C.c_double(act_reg), C.c_double(entropy_reg), C.byref(loss), _ptr(grad))
+        assert rc == 0, rc
+        return float(loss.value), grad
+
     # small helpers for the unit tests
     def fastpower(self, x, y):
         self.lib.kanode_oracle_fastpower.restype = C.c_float
