@@ -266,6 +266,27 @@ int kanode_set_regularizer(kanode_handle* h, double act_reg, double entropy_reg)
 /* reg(p) and d reg/d p of the current parameters on their own (host pointers; grad may be NULL) */
 int kanode_reg_loss(kanode_handle* h, double act_reg, double entropy_reg, double* loss, float* grad /* [np] or NULL */);
 
+/* ---- device-resident training iteration (LV_driver_KANODE.jl:280-291: grad = Zgrad(loss, p)[1]; update!(opt, p, grad);
+ * loss_train(p); loss_test(p)) --------------------------------------------------------------------------------------
+ * kanode_train_begin copies the handle's current parameters into a device-resident fp32 master copy and zeroes the Adam
+ * moments (Flux.Adam(eta, (beta1, beta2), eps), :219).  kanode_train_step_dev then runs ONE reference iteration without
+ * any host synchronisation on the small-model ensemble path (the lockstep PDE engines poll a device flag while they
+ * enqueue step attempts): loss + gradient at p_k (regulariser included when set), Adam update p_k -> p_{k+1}, refresh of
+ * every derived device image of the parameters by kernels, then the two forward-only loss solves of the reference at
+ * p_{k+1}.  d_losses (device, 3 doubles) receives loss(p_k), loss_train(p_{k+1}) = mean(abs2, target - predict) and
+ * loss_test(p_{k+1}) (the test solve is skipped when d_target_test is NULL; its slot is left untouched).
+ * All data pointers are device pointers of this handle's GPU; saveat arrays are host pointers.  fp32 handles only.
+ * kanode_train_apply_dev is the second half on its own (Adam + refresh) for callers that all-reduce d_grad_sum across
+ * processes first (g = grad_scale * d_grad_sum).  kanode_train_params copies the master parameters to the host (blocks). */
+int kanode_train_begin(kanode_handle* h, float eta, float beta1, float beta2, float eps);
+int kanode_train_step_dev(kanode_handle* h, const float* d_u0, int64_t batch, double t0, double t1,
+                          const double* saveat, int32_t nsave, const float* d_target, float abstol, float reltol,
+                          const float* d_u0_test /* or NULL */, int64_t batch_test, double t1_test,
+                          const double* saveat_test, int32_t nsave_test, const float* d_target_test /* or NULL */,
+                          double* d_losses /* device [3] */);
+int kanode_train_apply_dev(kanode_handle* h, const float* d_grad_sum, float grad_scale);
+int kanode_train_params(kanode_handle* h, float* p /* [np] host */);
+
 /* Flux.Adam(eta, (beta1, beta2), eps) + update!(opt, p, grad)  (LV_driver_KANODE.jl:219,287; [EXT Flux 0.14.22]):
  *   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g^2;  p -= eta * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps),  g = grad_scale*d_grad.
  * All pointers are device pointers of np floats; t is the 1-based iteration count.  grad_scale lets a data-parallel

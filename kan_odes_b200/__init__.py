@@ -6,7 +6,7 @@ with an underscore so that it is importable; the project name is kan-odes_b200.)
 from .abi import KanodeError, load_library  # noqa: F401
 from .layers import (Chain, KDense, activation_getter, flatten_params, glorot_uniform, iqf, prune, rbf, reg_loss, rswaf, setup,  # noqa: F401
                      sigmoid, sigmoid_fast, softsign, swish, tanh, tanh_fast, unflatten_params)
-from .optim import Adam  # noqa: F401
+from .optim import Adam, DeviceTrainer  # noqa: F401
 from .node import KanOde, NeuralODE, ODESolution, SourceODE, Stats, Tsit5  # noqa: F401
 
 __version__ = "0.1.0"

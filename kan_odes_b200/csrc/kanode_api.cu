@@ -68,6 +68,7 @@ template <class T> int rhs_dev(kanode_handle* h, const T* d_u, T* d_du, int64_t 
     if (B <= 0) return 0;
     int rc = 0;
     auto run = [&]<class P, int NORM>() -> int {
+        if (int rcr = host_params_refresh(h)) return rcr;              // the weights travel in the kernel parameter block
         P prm; fill_small<T>(h, prm);
         small_rhs_kernel<T, P, NORM><<<blocks_for(B, 128), 128, 0, h->stream>>>(prm, d_u, d_du, B);
         ++h->launches;
@@ -85,6 +86,7 @@ template <class T> int vjp_dev(kanode_handle* h, const T* d_u, const T* d_lam, T
     if (B <= 0) { CK(h, cudaMemsetAsync(d_pbar, 0, sizeof(T) * h->np, h->stream)); return 0; }
     int rc = 0;
     auto run = [&]<class P, int NORM>() -> int {
+        if (int rcr = host_params_refresh(h)) return rcr;
         P prm; fill_small<T>(h, prm);
         T *fac = nullptr, *rows = nullptr;
         ENSURE(h, W_FAC, sizeof(T) * (size_t)P::NF * B, fac);
@@ -214,7 +216,7 @@ template <class T> int set_params_host(kanode_handle* h, const T* p, size_t np) 
     if (int rc = enter(h)) return rc;
     if (!p || np != h->np) return fail(h, KANODE_ERR_INVALID, "expected %zu parameters, got %zu", h->np, np);
     for (size_t i = 0; i < np; ++i) h->params[i] = (double)p[i];
-    h->have_params = true;
+    h->have_params = true; h->params_host_stale = false;
     ++h->params_version;
     return generic_upload_params(h);
 }
@@ -347,6 +349,67 @@ int loss_grad_host(kanode_handle* h, const T* u0, int64_t B, double t0, double t
                         "loss and gradient leave them out", cnt[0], cnt[2], (long long)B);
         return 0;
     }
+}
+
+// ---- device-resident training ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) f32_to_f64_kernel(const float* __restrict__ a, double* __restrict__ b, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = (double)a[i];
+}
+// acc += sum (a - b)^2
+__global__ void __launch_bounds__(256) sq_err_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, double* __restrict__ acc) {
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double d = (double)a[i] - (double)b[i];
+        s += d * d;
+    }
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(acc, s);
+}
+__global__ void train_losses_kernel(const double* __restrict__ raw, double s0, double s1, double s2, int have_test, double* __restrict__ out) {
+    out[0] = raw[0] * s0; out[1] = raw[1] * s1;
+    if (have_test) out[2] = raw[2] * s2;
+}
+
+// every device copy of the parameters follows the fp32 master d_p, by kernels on the handle's stream (no host round trip)
+int params_follow_dev(kanode_handle* h, const float* d_p) {
+    float* pf = nullptr; double* pd = nullptr;
+    ENSURE(h, W_PARAMS, sizeof(float) * h->np, pf);
+    ENSURE(h, W_PARAMS64, sizeof(double) * h->np, pd);
+    if (pf != d_p) CK(h, cudaMemcpyAsync(pf, d_p, sizeof(float) * h->np, cudaMemcpyDeviceToDevice, h->stream));
+    f32_to_f64_kernel<<<blocks_for((int64_t)h->np, 256), 256, 0, h->stream>>>(d_p, pd, h->np);
+    ++h->launches;
+    ++h->params_version;                                               // the wide engines rebuild their images from pf / pd lazily
+    h->have_params = true; h->params_host_stale = true;
+    bool handled = false;
+    if (int rc = small_pack_dev(h, d_p, &handled)) return rc;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int train_apply(kanode_handle* h, const float* d_grad, float grad_scale) {
+    float *p = (float*)h->ws[kanode_handle::W_TR_P].p, *m = (float*)h->ws[kanode_handle::W_TR_M].p, *v = (float*)h->ws[kanode_handle::W_TR_V].p;
+    ++h->tr_t;
+    const float c1 = (float)(1.0 / (1.0 - std::pow((double)h->tr_b1, (double)h->tr_t)));
+    const float c2 = (float)(1.0 / (1.0 - std::pow((double)h->tr_b2, (double)h->tr_t)));
+    adam_update_kernel<<<blocks_for((int64_t)h->np, 256), 256, 0, h->stream>>>(p, d_grad, m, v, h->np, h->tr_eta, h->tr_b1, h->tr_b2, h->tr_eps,
+                                                                                c1, c2, grad_scale);
+    ++h->launches;
+    return params_follow_dev(h, p);
+}
+
+// loss = mean(abs2, target - predict) of a forward-only solve, accumulated un-normalised into *d_acc
+int forward_loss_dev(kanode_handle* h, const float* d_u0, int64_t B, double t0, double t1, const double* saveat, int nsave,
+                     const float* d_target, double abstol, double reltol, double* d_acc) {
+    const size_t nout = (size_t)B * nsave * h->n;
+    float* d_out = nullptr;
+    ENSURE(h, W_TR_OUT, sizeof(float) * (nout ? nout : 1), d_out);
+    if (int rc = solve_dev<float>(h, d_u0, B, t0, t1, saveat, nsave, abstol, reltol, d_out, nullptr)) return rc;
+    const unsigned nb = (unsigned)std::min<size_t>((nout + 255) / 256, 2368);
+    sq_err_kernel<<<nb, 256, 0, h->stream>>>(d_out, d_target, nout, d_acc);
+    ++h->launches;
+    CK(h, cudaGetLastError());
+    return 0;
 }
 
 template <class T> int edge_activations_host(kanode_handle* h, int layer, const T* x, T* act, int64_t K) {
@@ -492,10 +555,11 @@ int kanode_set_params_f64(kanode_handle* h, const double* p, size_t np) { return
 int kanode_set_params_dev(kanode_handle* h, const float* d_p, size_t np) {
     if (int rc = enter(h)) return rc;
     if (!d_p || np != h->np) return fail(h, KANODE_ERR_INVALID, "expected %zu parameters, got %zu", h->np, np);
-    std::vector<float> tmp(np);
-    CK(h, cudaMemcpyAsync(tmp.data(), d_p, sizeof(float) * np, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));
-    return set_params_host<float>(h, tmp.data(), np);
+    // device copies follow by kernels; the host copy is fetched lazily by the few entry points that read it
+    float* master = nullptr;
+    ENSURE(h, W_TR_P, sizeof(float) * np, master);
+    if (master != d_p) CK(h, cudaMemcpyAsync(master, d_p, sizeof(float) * np, cudaMemcpyDeviceToDevice, h->stream));
+    return params_follow_dev(h, master);
 }
 
 int kanode_rhs(kanode_handle* h, const float* u, float* du, int64_t batch) { return rhs_host<float>(h, u, du, batch); }
@@ -604,6 +668,61 @@ int kanode_reg_loss(kanode_handle* h, double act_reg, double entropy_reg, double
     CK(h, cudaMemcpyAsync(loss, d_l, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (grad) CK(h, cudaMemcpyAsync(grad, d_g, sizeof(float) * h->np, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int kanode_train_begin(kanode_handle* h, float eta, float beta1, float beta2, float eps) {
+    if (int rc = enter(h)) return rc;
+    if (!h->have_params) return fail(h, KANODE_ERR_INVALID, "parameters not set");
+    if (!(eta > 0.f)) return fail(h, KANODE_ERR_INVALID, "bad learning rate");
+    if (int rc = host_params_refresh(h)) return rc;
+    float *p = nullptr, *m = nullptr, *v = nullptr, *g = nullptr; double* raw = nullptr;
+    ENSURE(h, W_TR_P, sizeof(float) * h->np, p); ENSURE(h, W_TR_M, sizeof(float) * h->np, m);
+    ENSURE(h, W_TR_V, sizeof(float) * h->np, v); ENSURE(h, W_TR_GRAD, sizeof(float) * h->np, g);
+    ENSURE(h, W_TR_RAW, 4 * sizeof(double), raw);
+    std::vector<float> tmp(h->np);
+    for (size_t i = 0; i < h->np; ++i) tmp[i] = (float)h->params[i];
+    CK(h, cudaMemcpyAsync(p, tmp.data(), sizeof(float) * h->np, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemsetAsync(m, 0, sizeof(float) * h->np, h->stream));
+    CK(h, cudaMemsetAsync(v, 0, sizeof(float) * h->np, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->tr_eta = eta; h->tr_b1 = beta1; h->tr_b2 = beta2; h->tr_eps = eps; h->tr_t = 0; h->train_on = true;
+    return 0;
+}
+int kanode_train_apply_dev(kanode_handle* h, const float* d_grad_sum, float grad_scale) {
+    if (int rc = enter(h)) return rc;
+    if (!h->train_on || !d_grad_sum) return fail(h, KANODE_ERR_INVALID, "kanode_train_begin first");
+    return train_apply(h, d_grad_sum, grad_scale);
+}
+int kanode_train_step_dev(kanode_handle* h, const float* d_u0, int64_t batch, double t0, double t1, const double* saveat,
+                          int32_t nsave, const float* d_target, float abstol, float reltol, const float* d_u0_test,
+                          int64_t batch_test, double t1_test, const double* saveat_test, int32_t nsave_test,
+                          const float* d_target_test, double* d_losses) {
+    if (int rc = enter(h)) return rc;
+    if (!h->train_on) return fail(h, KANODE_ERR_INVALID, "kanode_train_begin first");
+    if (batch <= 0 || !d_u0 || !d_target || !d_losses) return fail(h, KANODE_ERR_INVALID, "bad arguments");
+    const bool test = d_target_test && d_u0_test && batch_test > 0 && nsave_test > 0;
+    double* raw = (double*)h->ws[kanode_handle::W_TR_RAW].p;
+    float* g = (float*)h->ws[kanode_handle::W_TR_GRAD].p;
+    CK(h, cudaMemsetAsync(raw, 0, 4 * sizeof(double), h->stream));
+    if (int rc = loss_grad_dev<float>(h, d_u0, batch, t0, t1, saveat, nsave, d_target, abstol, reltol, &raw[0], g, nullptr, nullptr, nullptr,
+                                      (float*)nullptr)) return rc;
+    if (int rc = train_apply(h, g, 1.0f / (float)batch)) return rc;
+    if (int rc = forward_loss_dev(h, d_u0, batch, t0, t1, saveat, nsave, d_target, abstol, reltol, &raw[1])) return rc;
+    if (test)
+        if (int rc = forward_loss_dev(h, d_u0_test, batch_test, t0, t1_test, saveat_test, nsave_test, d_target_test, abstol, reltol, &raw[2])) return rc;
+    const double s = 1.0 / ((double)batch * nsave * h->n), st = test ? 1.0 / ((double)batch_test * nsave_test * h->n) : 0.0;
+    train_losses_kernel<<<1, 1, 0, h->stream>>>(raw, s, s, st, test ? 1 : 0, d_losses);
+    ++h->launches;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+int kanode_train_params(kanode_handle* h, float* p) {
+    if (int rc = enter(h)) return rc;
+    if (!h->train_on || !p) return fail(h, KANODE_ERR_INVALID, "kanode_train_begin first");
+    CK(h, cudaMemcpyAsync(p, h->ws[kanode_handle::W_TR_P].p, sizeof(float) * h->np, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < h->np; ++i) h->params[i] = (double)p[i];
+    h->params_host_stale = false;
     return 0;
 }
 int kanode_loss_grad_dev(kanode_handle* h, const float* d_u0, int64_t batch, double t0, double t1, const double* saveat,

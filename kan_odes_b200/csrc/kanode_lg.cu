@@ -19,6 +19,7 @@ template <class T, class P, int UPL> int upload_packed_lg(kanode_handle* h, cons
     const int slot = sizeof(T) == 4 ? 0 : 1;
     if (slot == 0) ENSURE(h, W_WLG32, sizeof(T) * SMP::WLG, d); else ENSURE(h, W_WLG64, sizeof(T) * SMP::WLG, d);
     if (h->wlg_version[slot] != h->params_version) {
+        if (int rc = host_params_refresh(h)) return rc;
         std::vector<T> pk((size_t)SMP::WLG, T(0));
         for (int l = 0; l < LPT; ++l)
             for (int u = 0; u < UPL; ++u) {
@@ -38,6 +39,45 @@ template <class T, class P, int UPL> int upload_packed_lg(kanode_handle* h, cons
     }
     *out = d;
     return 0;
+}
+
+// one thread per hidden unit: the same two images upload_packed / upload_packed_lg build on the host
+template <class P, int UPL>
+__global__ void __launch_bounds__(64) small_pack_kernel(const float* __restrict__ p, float* __restrict__ wpk, float* __restrict__ wlg) {
+    using SMP = LgSmem<float, P, UPL>;
+    constexpr int I = P::I, G = P::G, NQ = P::NQ;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P::H) return;
+    float* a = wpk + (size_t)j * P::UW;                                          // [C1 (i*G+g) | W1 (i) | C2 (g*I+o) | W2 (o)]
+    float* b = wlg + (size_t)(j / UPL) * SMP::LW + (size_t)(j % UPL) * P::UW;    // w1 index q*I + i, then the same w2 block
+    for (int i = 0; i < I; ++i) {
+        for (int g = 0; g < G; ++g) { const float v = p[P::OC1 + (i * G + g) * P::H + j]; a[i * G + g] = v; b[g * I + i] = v; }
+        const float v = p[P::OW1 + i * P::H + j]; a[I * G + i] = v; b[G * I + i] = v;
+    }
+    for (int g = 0; g < G; ++g)
+        for (int o = 0; o < I; ++o) { const float v = p[P::OC2 + (j * G + g) * I + o]; a[NQ + g * I + o] = v; b[NQ + g * I + o] = v; }
+    for (int o = 0; o < I; ++o) { const float v = p[P::OW2 + j * I + o]; a[NQ + G * I + o] = v; b[NQ + G * I + o] = v; }
+}
+
+int small_pack_dev(kanode_handle* h, const float* d_p, bool* handled) {
+    int rc = 0;
+    auto run = [&]<class P, int NORM>() -> int {
+        constexpr int UPL = 2;
+        using SMP = LgSmem<float, P, UPL>;
+        float *wpk = nullptr, *wlg = nullptr;
+        const bool fresh_pk = h->ws[kanode_handle::W_WPK32].bytes < sizeof(float) * P::WPK, fresh_lg = h->ws[kanode_handle::W_WLG32].bytes < sizeof(float) * SMP::WLG;
+        ENSURE(h, W_WPK32, sizeof(float) * P::WPK, wpk);
+        ENSURE(h, W_WLG32, sizeof(float) * SMP::WLG, wlg);
+        if (fresh_pk) CK(h, cudaMemsetAsync(wpk, 0, sizeof(float) * P::WPK, h->stream));        // pad entries stay zero
+        if (fresh_lg) CK(h, cudaMemsetAsync(wlg, 0, sizeof(float) * SMP::WLG, h->stream));
+        small_pack_kernel<P, UPL><<<(P::H + 63) / 64, 64, 0, h->stream>>>(d_p, wpk, wlg);
+        ++h->launches;
+        CK(h, cudaGetLastError());
+        h->wpk_version[0] = h->params_version; h->wlg_version[0] = h->params_version;
+        return 0;
+    };
+    *handled = small_dispatch<float>(h, run, rc);
+    return rc;
 }
 
 #ifndef KANODE_LG_NSLAB
@@ -82,7 +122,7 @@ int small_lg_loss_grad(kanode_handle* h, const T* d_u0, int64_t B, double t0, do
         const int slot = sizeof(T) == 4 ? 0 : 1;
         const int64_t nslots = (int64_t)nblk * WPB;
         bool ordered = false;
-        if (h->schedule && !d_rp_bwd && nwarps >= 2048 && nslots < (1ll << 30)) {
+        if (h->schedule && !d_rp_bwd && nwarps >= 512 && nslots < (1ll << 30)) {
             int *att = nullptr, *ord = nullptr;
             ENSURE(h, W_ATT, sizeof(int) * (size_t)nslots * 2, att);
             ENSURE(h, W_ORDER, sizeof(int) * (size_t)nslots * 2, ord);

@@ -34,26 +34,40 @@ template <class T, class P> void fill_small(const kanode_handle* h, P& p) {
     p.dk = (T)(-2.0 * inv_h / sc);
 }
 
-// packed per-hidden-unit weights for the shared-memory kernels (layout: SmallParams::UW), uploaded on demand
+// Device-resident training leaves the host copy of the parameters behind (kanode_train_*): bring it back before anything
+// that reads h->params (blocks on the stream).
+inline int host_params_refresh(kanode_handle* h) {
+    if (!h->params_host_stale) return 0;
+    std::vector<float> tmp(h->np);
+    CK(h, cudaMemcpyAsync(tmp.data(), h->ws[kanode_handle::W_TR_P].p, sizeof(float) * h->np, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < h->np; ++i) h->params[i] = (double)tmp[i];
+    h->params_host_stale = false;
+    return 0;
+}
+
+// packed per-hidden-unit weights for the shared-memory kernels (layout: SmallParams::UW), uploaded when the parameters changed
 template <class T, class P> int upload_packed(kanode_handle* h, const T** out) {
-    std::vector<T> pk((size_t)P::WPK, T(0));
-    constexpr int I = P::I, H = P::H, G = P::G, NQ = P::NQ;
-    for (int j = 0; j < H; ++j) {
-        T* w = pk.data() + (size_t)j * P::UW;
-        for (int i = 0; i < I; ++i) {
-            for (int g = 0; g < G; ++g) w[i * G + g] = (T)h->params[P::OC1 + (i * G + g) * H + j];
-            w[I * G + i] = (T)h->params[P::OW1 + i * H + j];
-        }
-        for (int g = 0; g < G; ++g)
-            for (int o = 0; o < I; ++o) w[NQ + g * I + o] = (T)h->params[P::OC2 + (j * G + g) * I + o];
-        for (int o = 0; o < I; ++o) w[NQ + G * I + o] = (T)h->params[P::OW2 + j * I + o];
-    }
     T* d = nullptr;
-    if (sizeof(T) == 4) ENSURE(h, W_WPK32, sizeof(T) * pk.size(), d); else ENSURE(h, W_WPK64, sizeof(T) * pk.size(), d);
-    if (h->wpk_version[sizeof(T) == 4 ? 0 : 1] != h->params_version) {
+    const int slot = sizeof(T) == 4 ? 0 : 1;
+    if (slot == 0) ENSURE(h, W_WPK32, sizeof(T) * P::WPK, d); else ENSURE(h, W_WPK64, sizeof(T) * P::WPK, d);
+    if (h->wpk_version[slot] != h->params_version) {
+        if (int rc = host_params_refresh(h)) return rc;
+        std::vector<T> pk((size_t)P::WPK, T(0));
+        constexpr int I = P::I, H = P::H, G = P::G, NQ = P::NQ;
+        for (int j = 0; j < H; ++j) {
+            T* w = pk.data() + (size_t)j * P::UW;
+            for (int i = 0; i < I; ++i) {
+                for (int g = 0; g < G; ++g) w[i * G + g] = (T)h->params[P::OC1 + (i * G + g) * H + j];
+                w[I * G + i] = (T)h->params[P::OW1 + i * H + j];
+            }
+            for (int g = 0; g < G; ++g)
+                for (int o = 0; o < I; ++o) w[NQ + g * I + o] = (T)h->params[P::OC2 + (j * G + g) * I + o];
+            for (int o = 0; o < I; ++o) w[NQ + G * I + o] = (T)h->params[P::OW2 + j * I + o];
+        }
         CK(h, cudaMemcpyAsync(d, pk.data(), sizeof(T) * pk.size(), cudaMemcpyHostToDevice, h->stream));
         CK(h, cudaStreamSynchronize(h->stream));                       // pk is a stack-lifetime staging buffer
-        h->wpk_version[sizeof(T) == 4 ? 0 : 1] = h->params_version;
+        h->wpk_version[slot] = h->params_version;
     }
     *out = d;
     return 0;
@@ -83,5 +97,9 @@ int small_lg_loss_grad(kanode_handle* h, const T* d_u0, int64_t B, double t0, do
                        const T* d_target, double abstol, double reltol, double* d_loss_sum, T* d_grad_sum, T* d_du0,
                        kanode_stats* d_fst, kanode_stats* d_bst, T* d_out_opt, const double* d_rp_fwd, const double* d_rp_bwd,
                        int rp_cap, bool* handled);
+
+// Device-side refresh of the small-model weight images (forward kernels' packed per-unit weights, lane-block image of the
+// adjoint kernel) from fp32 device parameters: no host copy, no synchronisation.  *handled = false outside the registry.
+int small_pack_dev(kanode_handle* h, const float* d_p, bool* handled);
 
 }  // namespace kanode

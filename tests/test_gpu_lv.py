@@ -216,9 +216,9 @@ def test_training_loop_reduces_loss_and_adam_kernel_matches_host():
 
 
 def test_scheduled_backward_with_long_trajectory_warps_matches_plain(lv_saveat):
-    """Second call with the same batch: the step counts of the first call predict the long backward solves, which then
-    run in the warp-per-trajectory kernel ahead of the bulk (kanode_small_ls.cuh).  Same arithmetic: identical step
-    counts, gradients equal to 1e-11 (fp64), and the long ones still match the oracle."""
+    """Second call with the same batch: the warp iteration counts of the first call decide the launch order of the adjoint
+    warps (long ones first, kanode_lg.cu).  The per-warp gradient partials are indexed by the logical warp, so the result does
+    not depend on the order: identical step counts and gradients, and the long solves still match the oracle."""
     chain = lv_chain()
     p = glorot_params(chain, seed=0)
     B = 8192
@@ -227,7 +227,7 @@ def test_scheduled_backward_with_long_trajectory_warps_matches_plain(lv_saveat):
     tg = rng.uniform(0.0, 3.0, (B, 35, 2))
     ode = K.KanOde(chain, dtype=np.float64); ode.set_params(p)
     r1 = ode.loss_grad(u0, TSPAN, lv_saveat, tg)          # no history: plain launch
-    r2 = ode.loss_grad(u0, TSPAN, lv_saveat, tg)          # scheduled launch (long list + bulk on two streams)
+    r2 = ode.loss_grad(u0, TSPAN, lv_saveat, tg)          # ordered launch
     r3 = ode.loss_grad(u0, TSPAN, lv_saveat, tg)
     att = r1["bwd_stats"].naccept + r1["bwd_stats"].nreject
     assert (att > att.mean() + 4).sum() > 0, "workload has no long trajectories; the test would not exercise the warp kernel"
@@ -264,4 +264,47 @@ def test_lean_loss_grad_call_matches_full(lv_saveat):
     full = ode.loss_grad(u0, TSPAN, lv_saveat, tg)
     lean = ode.loss_grad(u0, TSPAN, lv_saveat, tg, want_du0=False, want_stats=False)
     ode.close()
-    assert set(lean) == {"loss", "grad"} and lean["loss"] == full["loss"] and np.array_equal(lean["grad"], full["grad"])
+    assert set(lean) == {"loss", "grad", "solver_failed"} and lean["loss"] == full["loss"] and np.array_equal(lean["grad"], full["grad"])
+
+
+def test_device_resident_training_matches_the_host_loop():
+    """kanode_train_step_dev (grad -> Adam -> loss_train -> loss_test on the device, LV_driver_KANODE.jl:280-291) against the same
+    iteration driven from the host with a round trip per call (host-pointer loss_grad, the Adam kernel on the copied gradient,
+    parameters read back and set again, two host-pointer forward solves): 100-iteration loss curves equal to 1e-6."""
+    import torch
+    from examples.train_lv import lv_data
+    t, X = lv_data()
+    chain = lv_chain()
+    p0 = (glorot_params(chain, 0).astype(np.float64) / 1e5).astype(np.float32)
+    u0 = np.array([[1.0, 1.0]], np.float32)
+    Xtr = X[:, :35].T[None].astype(np.float32); Xte = X.T[None].astype(np.float32)
+    eta, iters = 5e-4, 100                                       # Flux.Adam(5e-4), LV_driver_KANODE.jl:219
+    # host-driven loop
+    ode = K.KanOde(chain, dtype=np.float32)
+    opt = K.Adam(eta)
+    d_p = torch.tensor(p0, device="cuda"); d_m = torch.zeros_like(d_p); d_v = torch.zeros_like(d_p)
+    p = p0.copy()
+    host = np.zeros((iters, 3))
+    for k in range(iters):
+        ode.set_params(p)
+        r = ode.loss_grad(u0, TSPAN, t[:35], Xtr, want_du0=False, want_stats=False)
+        d_g = torch.tensor(r["grad"], device="cuda")
+        opt.update_dev(ode, d_p.data_ptr(), d_g.data_ptr(), d_m.data_ptr(), d_v.data_ptr(), grad_scale=1.0)
+        ode.lib.kanode_sync(ode.h)
+        p = d_p.cpu().numpy()
+        ode.set_params(p)
+        ptr = ode.solve(u0, TSPAN, t[:35]).array; pte = ode.solve(u0, (0.0, 14.0), t).array
+        host[k] = [r["loss"], np.mean((ptr.astype(np.float64) - Xtr) ** 2), np.mean((pte.astype(np.float64) - Xte) ** 2)]
+    # device-resident loop
+    ode2 = K.KanOde(chain, dtype=np.float32); ode2.set_params(p0)
+    tr = K.DeviceTrainer(ode2, u0, Xtr, TSPAN, t[:35], target_test=Xte, tspan_test=(0.0, 14.0), saveat_test=t, eta=eta)
+    for _ in range(iters):
+        tr.step()
+    dev = tr.losses()
+    assert dev.shape == (iters, 3) and np.isfinite(dev).all()
+    assert np.abs(dev / host - 1).max() < 1e-6, np.abs(dev / host - 1).max(axis=0)
+    assert np.abs(tr.params() - p).max() < 1e-6 * np.abs(p).max()
+    assert dev[-1, 1] < dev[0, 1]                                # it trains
+    # the handle serves the host-pointer entry points with the trained parameters afterwards (host copy refreshed lazily)
+    assert np.abs(ode2.rhs(u0) - ode.rhs(u0)).max() < 1e-6
+    ode.close(); ode2.close()
