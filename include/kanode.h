@@ -266,6 +266,19 @@ int kanode_set_regularizer(kanode_handle* h, double act_reg, double entropy_reg)
 /* reg(p) and d reg/d p of the current parameters on their own (host pointers; grad may be NULL) */
 int kanode_reg_loss(kanode_handle* h, double act_reg, double entropy_reg, double* loss, float* grad /* [np] or NULL */);
 
+/* ---- several GPUs behind ONE handle (the Julia surface stays single-process) ---------------------------
+ * kanode_create_multi builds one child handle per listed device (own stream, own workspace) inside the returned handle.  The
+ * host-pointer entry points kanode_set_params*, kanode_solve*, kanode_loss_grad*, kanode_solve_adjoint*,
+ * kanode_set_regularizer and kanode_set_record_capacity accept it: the batch is split into contiguous shards, one host thread
+ * per device drives its shard (trajectories are independent: no data-path exchange), and the only cross-device step is the sum
+ * of the per-device gradient / loss sums, done by ONE kernel on the first device that loads the other devices' partial sums
+ * straight from their memory over NVLink peer access (staged with cudaMemcpyPeer when peer access is unavailable); the sum
+ * order is fixed, so the result does not depend on timing.  kanode_rhs* / kanode_vjp* / kanode_edge_activations* run on the
+ * first device; the *_dev, *_replay and kanode_train_* entry points take device pointers of one GPU and return
+ * KANODE_ERR_UNSUPPORTED on a multi-device handle (data-parallel processes use one plain handle each + kanode_train_apply_dev). */
+int kanode_create_multi(const kanode_desc* desc, const int32_t* devices, int32_t n_devices, kanode_handle** out);
+int32_t kanode_device_count(const kanode_handle* h);   /* 1 for a plain handle */
+
 /* ---- device-resident training iteration (LV_driver_KANODE.jl:280-291: grad = Zgrad(loss, p)[1]; update!(opt, p, grad);
  * loss_train(p); loss_test(p)) --------------------------------------------------------------------------------------
  * kanode_train_begin copies the handle's current parameters into a device-resident fp32 master copy and zeroes the Adam

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -23,7 +24,7 @@ namespace {
 
 int enter(kanode_handle* h) {
     if (!h) return fail(nullptr, KANODE_ERR_INVALID, "null handle");
-    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaSetDevice(h->children.empty() ? h->device : h->children[0]->device));
     return 0;
 }
 
@@ -275,11 +276,12 @@ template <class T>
 int loss_grad_host(kanode_handle* h, const T* u0, int64_t B, double t0, double t1, const double* saveat, int nsave,
                    const T* target, double abstol, double reltol, T* loss, T* grad, T* du0, kanode_stats* fst,
                    kanode_stats* bst, const double* rp_fwd = nullptr, const double* rp_bwd = nullptr, int rp_cap = 0,
-                   T* out = nullptr, const T* cot = nullptr) {
+                   T* out = nullptr, const T* cot = nullptr, bool keep_on_device = false) {
     // cot != null: pullback of the solve with the caller's cotangents dL/dpred (kanode_solve_adjoint): no target, no loss,
-    // and the gradient is the plain sum over the batch
+    // and the gradient is the plain sum over the batch.  keep_on_device: the un-normalised gradient / loss sums stay in
+    // W_GRAD / W_LOSS for the multi-device combine (loss and grad are not written).
     if (int rc = enter(h)) return rc;
-    if (B <= 0 || !u0 || (!target && !cot) || (!loss && !cot) || !grad) return fail(h, KANODE_ERR_INVALID, "bad arguments");
+    if (B <= 0 || !u0 || (!target && !cot) || (!keep_on_device && ((!loss && !cot) || !grad))) return fail(h, KANODE_ERR_INVALID, "bad arguments");
     if ((rp_fwd || rp_bwd) && (!rp_fwd || !rp_bwd || rp_cap < 1)) return fail(h, KANODE_ERR_INVALID, "replay needs both step sequences");
     const size_t nout = (size_t)B * nsave * h->n;
     for (int attempt = 0;; ++attempt) {
@@ -327,8 +329,10 @@ int loss_grad_host(kanode_handle* h, const T* u0, int64_t B, double t0, double t
         if (fst) CK(h, cudaMemcpyAsync(st + o_f, d_f, sizeof(kanode_stats) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
         if (bst) CK(h, cudaMemcpyAsync(st + o_b, d_b, sizeof(kanode_stats) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
         if (du0) CK(h, cudaMemcpyAsync(st + o_du, d_du0, sizeof(T) * (size_t)B * h->n, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaMemcpyAsync(st + o_g, d_grad, sizeof(T) * h->np, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaMemcpyAsync(st + o_l, d_loss, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (!keep_on_device) {
+            CK(h, cudaMemcpyAsync(st + o_g, d_grad, sizeof(T) * h->np, cudaMemcpyDeviceToHost, h->stream));
+            CK(h, cudaMemcpyAsync(st + o_l, d_loss, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        }
         CK(h, cudaMemcpyAsync(st + o_c, d_cnt, 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(h, cudaStreamSynchronize(h->stream));
         int cnt[3]; std::memcpy(cnt, st + o_c, sizeof cnt);
@@ -336,11 +340,13 @@ int loss_grad_host(kanode_handle* h, const T* u0, int64_t B, double t0, double t
         if (fst) std::memcpy(fst, st + o_f, sizeof(kanode_stats) * (size_t)B);
         if (bst) std::memcpy(bst, st + o_b, sizeof(kanode_stats) * (size_t)B);
         if (du0) std::memcpy(du0, st + o_du, sizeof(T) * (size_t)B * h->n);
-        const T* gs = reinterpret_cast<const T*>(st + o_g);
-        double lsum = 0; std::memcpy(&lsum, st + o_l, sizeof(double));
-        if (loss) *loss = (T)(lsum / ((double)B * nsave * h->n));
-        const double gdiv = cot ? 1.0 : (double)B;
-        for (size_t i = 0; i < h->np; ++i) grad[i] = (T)((double)gs[i] / gdiv);
+        if (!keep_on_device) {
+            const T* gs = reinterpret_cast<const T*>(st + o_g);
+            double lsum = 0; std::memcpy(&lsum, st + o_l, sizeof(double));
+            if (loss) *loss = (T)(lsum / ((double)B * nsave * h->n));
+            const double gdiv = cot ? 1.0 : (double)B;
+            for (size_t i = 0; i < h->np; ++i) grad[i] = (T)((double)gs[i] / gdiv);
+        }
         h->last_failed[0] = cnt[0]; h->last_failed[1] = cnt[2];
         // In the reference a failed solve gives a short solution and loss() throws (LV_driver_KANODE.jl:197-203); here the
         // failed trajectories are left out of the sums, every output is still written, and the call reports it.
@@ -412,6 +418,106 @@ int forward_loss_dev(kanode_handle* h, const float* d_u0, int64_t B, double t0, 
     return 0;
 }
 
+// ---- several devices behind one handle (kanode_create_multi) ---------------------------------------------------------
+constexpr int KANODE_MAX_DEVICES = 16;
+template <class T> struct PeerPtrs { const T* g[KANODE_MAX_DEVICES]; const double* l[KANODE_MAX_DEVICES]; int n; };
+// out_g[i] = scale * sum_k g_k[i], out_l = sum_k l_k: the partial sums are loaded from the peers' memory, in device order
+template <class T>
+__global__ void __launch_bounds__(256) peer_sum_kernel(const PeerPtrs<T> pp, size_t np, T* __restrict__ out_g, double* __restrict__ out_l, double scale) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { double l = 0.0; for (int k = 0; k < pp.n; ++k) l += *pp.l[k]; *out_l = l; }
+    if (i >= np) return;
+    double a = 0.0;
+    for (int k = 0; k < pp.n; ++k) a += (double)pp.g[k][i];
+    out_g[i] = (T)(a * scale);
+}
+
+struct Shard { int k; int64_t b0, bk; };
+inline std::vector<Shard> make_shards(const kanode_handle* h, int64_t B) {
+    const int nd = (int)h->children.size();
+    const int64_t per = (B + nd - 1) / nd;
+    std::vector<Shard> s;
+    for (int k = 0; k < nd; ++k) {
+        const int64_t b0 = std::min<int64_t>(B, (int64_t)k * per), bk = std::min<int64_t>(B, b0 + per) - b0;
+        if (bk > 0) s.push_back(Shard{k, b0, bk});
+    }
+    return s;
+}
+// one host thread per device runs f(child, shard); a failed solve (KANODE_ERR_SOLVER) does not stop the others
+template <class F> int multi_fanout(kanode_handle* h, const std::vector<Shard>& shards, F&& f) {
+    std::vector<int> rcs(shards.size(), 0);
+    std::vector<std::thread> th;
+    for (size_t j = 0; j < shards.size(); ++j) th.emplace_back([&, j] { rcs[j] = f(h->children[shards[j].k], shards[j]); });
+    for (auto& t : th) t.join();
+    int soft = 0;
+    for (size_t j = 0; j < shards.size(); ++j) {
+        if (rcs[j] == KANODE_ERR_SOLVER) { soft = KANODE_ERR_SOLVER; h->err = h->children[shards[j].k]->err; continue; }
+        if (rcs[j] != 0) return fail(h, rcs[j], "device %d: %s", h->children[shards[j].k]->device, h->children[shards[j].k]->err.c_str());
+    }
+    return soft;
+}
+
+template <class T>
+int multi_solve(kanode_handle* h, const T* u0, int64_t B, double t0, double t1, const double* saveat, int nsave, double abstol,
+                double reltol, T* out, kanode_stats* stats) {
+    if (B <= 0) return 0;
+    const size_t n = h->n;
+    return multi_fanout(h, make_shards(h, B), [&](kanode_handle* c, const Shard& s) {
+        return solve_host<T>(c, u0 + s.b0 * n, s.bk, t0, t1, saveat, nsave, abstol, reltol, out ? out + (size_t)s.b0 * nsave * n : nullptr,
+                             stats ? stats + s.b0 : nullptr);
+    });
+}
+
+template <class T>
+int multi_loss_grad(kanode_handle* h, const T* u0, int64_t B, double t0, double t1, const double* saveat, int nsave, const T* target,
+                    double abstol, double reltol, T* loss, T* grad, T* du0, kanode_stats* fst, kanode_stats* bst, T* out, const T* cot) {
+    if (B <= 0 || !u0 || (!target && !cot) || (!loss && !cot) || !grad) return fail(h, KANODE_ERR_INVALID, "bad arguments");
+    const size_t n = h->n, per_traj = (size_t)nsave * n;
+    const std::vector<Shard> shards = make_shards(h, B);
+    const int soft = multi_fanout(h, shards, [&](kanode_handle* c, const Shard& s) {
+        return loss_grad_host<T>(c, u0 + s.b0 * n, s.bk, t0, t1, saveat, nsave, target ? target + s.b0 * per_traj : nullptr, abstol, reltol,
+                                 nullptr, nullptr, du0 ? du0 + s.b0 * n : nullptr, fst ? fst + s.b0 : nullptr, bst ? bst + s.b0 : nullptr,
+                                 nullptr, nullptr, 0, out ? out + s.b0 * per_traj : nullptr, cot ? cot + s.b0 * per_traj : nullptr, true);
+    });
+    if (soft != 0 && soft != KANODE_ERR_SOLVER) return soft;
+    // the only cross-device step: sum of the per-device gradient / loss sums on the first device
+    kanode_handle* c0 = h->children[shards[0].k];
+    if (int rc = enter(c0)) return rc;
+    T* d_g = nullptr; double* d_l = nullptr;
+    ENSURE(c0, W_MULTI_G, sizeof(T) * h->np, d_g); ENSURE(c0, W_MULTI_L, sizeof(double), d_l);
+    PeerPtrs<T> pp{}; pp.n = (int)shards.size();
+    T* stage = nullptr;
+    if (!h->peer_ok && shards.size() > 1) ENSURE(c0, W_MULTI_STAGE, (sizeof(T) * h->np + 8) * shards.size(), stage);
+    for (size_t j = 0; j < shards.size(); ++j) {
+        kanode_handle* c = h->children[shards[j].k];
+        const T* g = (const T*)c->ws[kanode_handle::W_GRAD].p; const double* l = (const double*)c->ws[kanode_handle::W_LOSS].p;
+        if (c != c0 && !h->peer_ok) {                                  // no peer loads: stage the partial sums on the first device
+            char* base = reinterpret_cast<char*>(stage) + j * (sizeof(T) * h->np + 8);
+            CK(c0, cudaMemcpyPeerAsync(base + 8, c0->device, g, c->device, sizeof(T) * h->np, c0->stream));
+            CK(c0, cudaMemcpyPeerAsync(base, c0->device, l, c->device, sizeof(double), c0->stream));
+            g = reinterpret_cast<const T*>(base + 8); l = reinterpret_cast<const double*>(base);
+        }
+        pp.g[j] = g; pp.l[j] = l;
+    }
+    peer_sum_kernel<T><<<blocks_for((int64_t)h->np, 256), 256, 0, c0->stream>>>(pp, h->np, d_g, d_l, cot ? 1.0 : 1.0 / (double)B);
+    ++c0->launches;
+    CK(c0, cudaGetLastError());
+    double lsum = 0.0;
+    CK(c0, cudaMemcpyAsync(grad, d_g, sizeof(T) * h->np, cudaMemcpyDeviceToHost, c0->stream));
+    CK(c0, cudaMemcpyAsync(&lsum, d_l, sizeof(double), cudaMemcpyDeviceToHost, c0->stream));
+    CK(c0, cudaStreamSynchronize(c0->stream));
+    if (loss) *loss = (T)(lsum / ((double)B * nsave * n));
+    return soft;
+}
+
+template <class T> int set_params_any(kanode_handle* h, const T* p, size_t np) {
+    if (h && !h->children.empty()) {
+        for (kanode_handle* c : h->children) if (int rc = set_params_host<T>(c, p, np)) return fail(h, rc, "%s", c->err.c_str());
+        h->have_params = true;
+        return 0;
+    }
+    return set_params_host<T>(h, p, np);
+}
 template <class T> int edge_activations_host(kanode_handle* h, int layer, const T* x, T* act, int64_t K) {
     if (int rc = enter(h)) return rc;
     if (!h->have_params) return fail(h, KANODE_ERR_INVALID, "parameters not set");
@@ -489,8 +595,48 @@ int kanode_create(const kanode_desc* desc, int device, void* stream, kanode_hand
     return 0;
 }
 
+int kanode_create_multi(const kanode_desc* desc, const int32_t* devices, int32_t n_devices, kanode_handle** out) {
+    if (!out) return fail(nullptr, KANODE_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    if (!devices || n_devices < 1 || n_devices > KANODE_MAX_DEVICES) return fail(nullptr, KANODE_ERR_INVALID, "1..%d devices", KANODE_MAX_DEVICES);
+    for (int a = 0; a < n_devices; ++a)
+        for (int b = a + 1; b < n_devices; ++b)
+            if (devices[a] == devices[b]) return fail(nullptr, KANODE_ERR_INVALID, "device %d listed twice", devices[a]);
+    const size_t np = count_params(desc);
+    if (np == 0) return fail(nullptr, KANODE_ERR_INVALID, "invalid descriptor");
+    kanode_handle* h = new (std::nothrow) kanode_handle();
+    if (!h) return fail(nullptr, KANODE_ERR_NOMEM, "out of host memory");
+    h->desc = *desc; h->np = np; h->n = desc->n_state;
+    h->n_out = desc->rhs_kind == KANODE_RHS_MAP ? desc->layers[desc->n_layers - 1].out_dims : desc->n_state;
+    for (int k = 0; k < n_devices; ++k) {
+        kanode_handle* c = nullptr;
+        if (int rc = kanode_create(desc, devices[k], nullptr, &c)) { kanode_destroy(h); return rc; }   // the error text is already set
+        h->children.push_back(c);
+    }
+    h->device = h->children[0]->device;
+    // peer access from the first device to the others: the gradient combine loads their partial sums in place
+    h->peer_ok = true;
+    if (cudaSetDevice(h->device) != cudaSuccess) { kanode_destroy(h); return fail(nullptr, KANODE_ERR_CUDA, "cudaSetDevice failed"); }
+    for (int k = 1; k < n_devices; ++k) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, h->device, devices[k]) != cudaSuccess || !can) { h->peer_ok = false; continue; }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(devices[k], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) h->peer_ok = false;
+        (void)cudaGetLastError();
+    }
+    *out = h;
+    return 0;
+}
+
+int32_t kanode_device_count(const kanode_handle* h) { return h ? (h->children.empty() ? 1 : (int32_t)h->children.size()) : 0; }
+
 int kanode_destroy(kanode_handle* h) {
     if (!h) return 0;
+    if (!h->children.empty()) {
+        for (kanode_handle* c : h->children) kanode_destroy(c);
+        delete h;
+        return 0;
+    }
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (auto& b : h->ws) if (b.p) cudaFree(b.p);
@@ -505,7 +651,11 @@ int kanode_destroy(kanode_handle* h) {
     return 0;
 }
 
+#define KANODE_SINGLE_ONLY(h, what)                                                                                   \
+    if ((h) && !(h)->children.empty()) return fail(h, KANODE_ERR_UNSUPPORTED, what " takes device pointers of one GPU: not available on a multi-device handle")
+
 int kanode_sync(kanode_handle* h) {
+    if (h && !h->children.empty()) { for (kanode_handle* c : h->children) if (int rc = kanode_sync(c)) return fail(h, rc, "%s", c->err.c_str()); return 0; }
     if (int rc = enter(h)) return rc;
     CK(h, cudaStreamSynchronize(h->stream));
     return 0;
@@ -513,14 +663,21 @@ int kanode_sync(kanode_handle* h) {
 
 int kanode_set_record_capacity(kanode_handle* h, int32_t max_steps) {
     if (!h || max_steps < 1) return fail(h, KANODE_ERR_INVALID, "bad capacity");
+    for (kanode_handle* c : h->children) c->rec_cap = max_steps;
     h->rec_cap = max_steps;
     return 0;
 }
 
-int64_t kanode_launch_count(const kanode_handle* h) { return h ? h->launches : 0; }
+int64_t kanode_launch_count(const kanode_handle* h) {
+    if (!h) return 0;
+    int64_t n = h->launches;
+    for (const kanode_handle* c : h->children) n += c->launches;
+    return n;
+}
 
 int kanode_adam_step_dev(kanode_handle* h, float* d_p, const float* d_grad, float* d_m, float* d_v, int64_t t, float eta,
                          float beta1, float beta2, float eps, float grad_scale) {
+    KANODE_SINGLE_ONLY(h, "kanode_adam_step_dev");
     if (int rc = enter(h)) return rc;
     if (!d_p || !d_grad || !d_m || !d_v || t < 1) return fail(h, KANODE_ERR_INVALID, "bad arguments");
     const float c1 = (float)(1.0 / (1.0 - std::pow((double)beta1, (double)t)));
@@ -533,6 +690,7 @@ int kanode_adam_step_dev(kanode_handle* h, float* d_p, const float* d_grad, floa
 }
 
 int kanode_last_timing(kanode_handle* h, float* ms3) {
+    if (h && !h->children.empty()) return kanode_last_timing(h->children[0], ms3);
     if (int rc = enter(h)) return rc;
     if (!ms3 || !h->ev_valid) return fail(h, KANODE_ERR_INVALID, "no timed loss_grad call yet");
     CK(h, cudaEventSynchronize(h->ev[3]));
@@ -541,6 +699,7 @@ int kanode_last_timing(kanode_handle* h, float* ms3) {
 }
 
 int kanode_last_gpass_timing(kanode_handle* h, float* ms, int32_t* passes) {
+    if (h && !h->children.empty()) return kanode_last_gpass_timing(h->children[0], ms, passes);
     if (int rc = enter(h)) return rc;
     if (!ms || !passes || !h->ev_valid || h->wide_gp_used < 2) return fail(h, KANODE_ERR_INVALID, "no wide loss_grad call yet");
     CK(h, cudaEventSynchronize(h->ev[3]));
@@ -550,9 +709,10 @@ int kanode_last_gpass_timing(kanode_handle* h, float* ms, int32_t* passes) {
     return 0;
 }
 
-int kanode_set_params(kanode_handle* h, const float* p, size_t np) { return set_params_host<float>(h, p, np); }
-int kanode_set_params_f64(kanode_handle* h, const double* p, size_t np) { return set_params_host<double>(h, p, np); }
+int kanode_set_params(kanode_handle* h, const float* p, size_t np) { return set_params_any<float>(h, p, np); }
+int kanode_set_params_f64(kanode_handle* h, const double* p, size_t np) { return set_params_any<double>(h, p, np); }
 int kanode_set_params_dev(kanode_handle* h, const float* d_p, size_t np) {
+    KANODE_SINGLE_ONLY(h, "kanode_set_params_dev");
     if (int rc = enter(h)) return rc;
     if (!d_p || np != h->np) return fail(h, KANODE_ERR_INVALID, "expected %zu parameters, got %zu", h->np, np);
     // device copies follow by kernels; the host copy is fetched lazily by the few entry points that read it
@@ -562,30 +722,36 @@ int kanode_set_params_dev(kanode_handle* h, const float* d_p, size_t np) {
     return params_follow_dev(h, master);
 }
 
-int kanode_rhs(kanode_handle* h, const float* u, float* du, int64_t batch) { return rhs_host<float>(h, u, du, batch); }
-int kanode_rhs_f64(kanode_handle* h, const double* u, double* du, int64_t batch) { return rhs_host<double>(h, u, du, batch); }
+static kanode_handle* first_dev(kanode_handle* h) { return h && !h->children.empty() ? h->children[0] : h; }
+static int lift(kanode_handle* h, int rc) { if (rc && h && !h->children.empty()) h->err = h->children[0]->err; return rc; }
+int kanode_rhs(kanode_handle* h, const float* u, float* du, int64_t batch) { return lift(h, rhs_host<float>(first_dev(h), u, du, batch)); }
+int kanode_rhs_f64(kanode_handle* h, const double* u, double* du, int64_t batch) { return lift(h, rhs_host<double>(first_dev(h), u, du, batch)); }
 int kanode_rhs_dev(kanode_handle* h, const float* d_u, float* d_du, int64_t batch) {
+    KANODE_SINGLE_ONLY(h, "kanode_rhs_dev");
     if (int rc = enter(h)) return rc;
     return rhs_dev<float>(h, d_u, d_du, batch);
 }
 
 int kanode_vjp(kanode_handle* h, const float* u, const float* lam, float* ubar, float* pbar, int64_t batch) {
-    return vjp_host<float>(h, u, lam, ubar, pbar, batch);
+    return lift(h, vjp_host<float>(first_dev(h), u, lam, ubar, pbar, batch));
 }
 int kanode_vjp_f64(kanode_handle* h, const double* u, const double* lam, double* ubar, double* pbar, int64_t batch) {
-    return vjp_host<double>(h, u, lam, ubar, pbar, batch);
+    return lift(h, vjp_host<double>(first_dev(h), u, lam, ubar, pbar, batch));
 }
 
 int kanode_solve(kanode_handle* h, const float* u0, int64_t batch, double t0, double t1, const double* saveat,
                  int32_t nsave, float abstol, float reltol, float* out, kanode_stats* stats) {
+    if (h && !h->children.empty()) return multi_solve<float>(h, u0, batch, t0, t1, saveat, nsave, abstol, reltol, out, stats);
     return solve_host<float>(h, u0, batch, t0, t1, saveat, nsave, abstol, reltol, out, stats);
 }
 int kanode_solve_f64(kanode_handle* h, const double* u0, int64_t batch, double t0, double t1, const double* saveat,
                      int32_t nsave, double abstol, double reltol, double* out, kanode_stats* stats) {
+    if (h && !h->children.empty()) return multi_solve<double>(h, u0, batch, t0, t1, saveat, nsave, abstol, reltol, out, stats);
     return solve_host<double>(h, u0, batch, t0, t1, saveat, nsave, abstol, reltol, out, stats);
 }
 int kanode_solve_dev(kanode_handle* h, const float* d_u0, int64_t batch, double t0, double t1, const double* saveat,
                      int32_t nsave, float abstol, float reltol, float* d_out, kanode_stats* d_stats) {
+    KANODE_SINGLE_ONLY(h, "kanode_solve_dev");
     if (int rc = enter(h)) return rc;
     return solve_dev<float>(h, d_u0, batch, t0, t1, saveat, nsave, abstol, reltol, d_out, d_stats);
 }
@@ -593,12 +759,16 @@ int kanode_solve_dev(kanode_handle* h, const float* d_u0, int64_t batch, double 
 int kanode_loss_grad(kanode_handle* h, const float* u0, int64_t batch, double t0, double t1, const double* saveat,
                      int32_t nsave, const float* target, float abstol, float reltol, float* loss, float* grad,
                      float* du0, kanode_stats* fwd_stats, kanode_stats* bwd_stats) {
+    if (h && !h->children.empty())
+        return multi_loss_grad<float>(h, u0, batch, t0, t1, saveat, nsave, target, abstol, reltol, loss, grad, du0, fwd_stats, bwd_stats, nullptr, nullptr);
     return loss_grad_host<float>(h, u0, batch, t0, t1, saveat, nsave, target, abstol, reltol, loss, grad, du0,
                                  fwd_stats, bwd_stats);
 }
 int kanode_loss_grad_f64(kanode_handle* h, const double* u0, int64_t batch, double t0, double t1, const double* saveat,
                          int32_t nsave, const double* target, double abstol, double reltol, double* loss, double* grad,
                          double* du0, kanode_stats* fwd_stats, kanode_stats* bwd_stats) {
+    if (h && !h->children.empty())
+        return multi_loss_grad<double>(h, u0, batch, t0, t1, saveat, nsave, target, abstol, reltol, loss, grad, du0, fwd_stats, bwd_stats, nullptr, nullptr);
     return loss_grad_host<double>(h, u0, batch, t0, t1, saveat, nsave, target, abstol, reltol, loss, grad, du0,
                                   fwd_stats, bwd_stats);
 }
@@ -606,6 +776,7 @@ int kanode_loss_grad_replay(kanode_handle* h, const float* u0, int64_t batch, do
                             int32_t nsave, const float* target, float abstol, float reltol, const double* fwd_t,
                             const double* bwd_t, int32_t max_steps, float* loss, float* grad, float* du0, float* out,
                             kanode_stats* fwd_stats, kanode_stats* bwd_stats) {
+    KANODE_SINGLE_ONLY(h, "kanode_loss_grad_replay");
     if (!fwd_t || !bwd_t) return fail(h, KANODE_ERR_INVALID, "replay needs both step sequences");
     return loss_grad_host<float>(h, u0, batch, t0, t1, saveat, nsave, target, abstol, reltol, loss, grad, du0,
                                  fwd_stats, bwd_stats, fwd_t, bwd_t, max_steps, out);
@@ -614,6 +785,7 @@ int kanode_loss_grad_replay_f64(kanode_handle* h, const double* u0, int64_t batc
                                 int32_t nsave, const double* target, double abstol, double reltol, const double* fwd_t,
                                 const double* bwd_t, int32_t max_steps, double* loss, double* grad, double* du0, double* out,
                                 kanode_stats* fwd_stats, kanode_stats* bwd_stats) {
+    KANODE_SINGLE_ONLY(h, "kanode_loss_grad_replay_f64");
     if (!fwd_t || !bwd_t) return fail(h, KANODE_ERR_INVALID, "replay needs both step sequences");
     return loss_grad_host<double>(h, u0, batch, t0, t1, saveat, nsave, target, abstol, reltol, loss, grad, du0,
                                   fwd_stats, bwd_stats, fwd_t, bwd_t, max_steps, out);
@@ -622,6 +794,8 @@ int kanode_solve_adjoint(kanode_handle* h, const float* u0, int64_t batch, doubl
                          float abstol, float reltol, const float* dL_dout, float* out, float* grad, float* du0,
                          kanode_stats* fwd_stats, kanode_stats* bwd_stats) {
     if (!dL_dout) return fail(h, KANODE_ERR_INVALID, "null cotangent");
+    if (h && !h->children.empty())
+        return multi_loss_grad<float>(h, u0, batch, t0, t1, saveat, nsave, nullptr, abstol, reltol, nullptr, grad, du0, fwd_stats, bwd_stats, out, dL_dout);
     return loss_grad_host<float>(h, u0, batch, t0, t1, saveat, nsave, nullptr, abstol, reltol, nullptr, grad, du0, fwd_stats, bwd_stats,
                                  nullptr, nullptr, 0, out, dL_dout);
 }
@@ -629,12 +803,15 @@ int kanode_solve_adjoint_f64(kanode_handle* h, const double* u0, int64_t batch, 
                              int32_t nsave, double abstol, double reltol, const double* dL_dout, double* out, double* grad,
                              double* du0, kanode_stats* fwd_stats, kanode_stats* bwd_stats) {
     if (!dL_dout) return fail(h, KANODE_ERR_INVALID, "null cotangent");
+    if (h && !h->children.empty())
+        return multi_loss_grad<double>(h, u0, batch, t0, t1, saveat, nsave, nullptr, abstol, reltol, nullptr, grad, du0, fwd_stats, bwd_stats, out, dL_dout);
     return loss_grad_host<double>(h, u0, batch, t0, t1, saveat, nsave, nullptr, abstol, reltol, nullptr, grad, du0, fwd_stats, bwd_stats,
                                   nullptr, nullptr, 0, out, dL_dout);
 }
 int kanode_solve_adjoint_dev(kanode_handle* h, const float* d_u0, int64_t batch, double t0, double t1, const double* saveat,
                              int32_t nsave, float abstol, float reltol, const float* d_dL_dout, float* d_out, float* d_grad,
                              float* d_du0, kanode_stats* d_fwd_stats, kanode_stats* d_bwd_stats) {
+    KANODE_SINGLE_ONLY(h, "kanode_solve_adjoint_dev");
     if (int rc = enter(h)) return rc;
     if (batch < 0 || !d_dL_dout || !d_grad) return fail(h, KANODE_ERR_INVALID, "bad arguments");
     double* d_loss = nullptr;
@@ -643,17 +820,19 @@ int kanode_solve_adjoint_dev(kanode_handle* h, const float* d_u0, int64_t batch,
                                 d_bwd_stats, d_out, nullptr, nullptr, 0, d_dL_dout);
 }
 int kanode_edge_activations(kanode_handle* h, int32_t layer, const float* x, float* act, int64_t K) {
-    return edge_activations_host<float>(h, layer, x, act, K);
+    return lift(h, edge_activations_host<float>(first_dev(h), layer, x, act, K));
 }
 int kanode_edge_activations_f64(kanode_handle* h, int32_t layer, const double* x, double* act, int64_t K) {
-    return edge_activations_host<double>(h, layer, x, act, K);
+    return lift(h, edge_activations_host<double>(first_dev(h), layer, x, act, K));
 }
 int kanode_set_regularizer(kanode_handle* h, double act_reg, double entropy_reg) {
     if (!h || !(act_reg >= 0.0) || !(entropy_reg >= 0.0)) return fail(h, KANODE_ERR_INVALID, "bad regulariser weights");
     h->reg_act = act_reg; h->reg_entropy = entropy_reg;
+    for (kanode_handle* c : h->children) { c->reg_act = act_reg; c->reg_entropy = entropy_reg; }
     return 0;
 }
 int kanode_reg_loss(kanode_handle* h, double act_reg, double entropy_reg, double* loss, float* grad) {
+    if (h && !h->children.empty()) return lift(h, kanode_reg_loss(h->children[0], act_reg, entropy_reg, loss, grad));
     if (int rc = enter(h)) return rc;
     if (!h->have_params || !loss) return fail(h, KANODE_ERR_INVALID, "bad arguments");
     double* d_l = nullptr; float* d_g = nullptr;
@@ -671,6 +850,7 @@ int kanode_reg_loss(kanode_handle* h, double act_reg, double entropy_reg, double
     return 0;
 }
 int kanode_train_begin(kanode_handle* h, float eta, float beta1, float beta2, float eps) {
+    KANODE_SINGLE_ONLY(h, "kanode_train_begin");
     if (int rc = enter(h)) return rc;
     if (!h->have_params) return fail(h, KANODE_ERR_INVALID, "parameters not set");
     if (!(eta > 0.f)) return fail(h, KANODE_ERR_INVALID, "bad learning rate");
@@ -689,6 +869,7 @@ int kanode_train_begin(kanode_handle* h, float eta, float beta1, float beta2, fl
     return 0;
 }
 int kanode_train_apply_dev(kanode_handle* h, const float* d_grad_sum, float grad_scale) {
+    KANODE_SINGLE_ONLY(h, "kanode_train_apply_dev");
     if (int rc = enter(h)) return rc;
     if (!h->train_on || !d_grad_sum) return fail(h, KANODE_ERR_INVALID, "kanode_train_begin first");
     return train_apply(h, d_grad_sum, grad_scale);
@@ -697,6 +878,7 @@ int kanode_train_step_dev(kanode_handle* h, const float* d_u0, int64_t batch, do
                           int32_t nsave, const float* d_target, float abstol, float reltol, const float* d_u0_test,
                           int64_t batch_test, double t1_test, const double* saveat_test, int32_t nsave_test,
                           const float* d_target_test, double* d_losses) {
+    KANODE_SINGLE_ONLY(h, "kanode_train_step_dev");
     if (int rc = enter(h)) return rc;
     if (!h->train_on) return fail(h, KANODE_ERR_INVALID, "kanode_train_begin first");
     if (batch <= 0 || !d_u0 || !d_target || !d_losses) return fail(h, KANODE_ERR_INVALID, "bad arguments");
@@ -717,6 +899,7 @@ int kanode_train_step_dev(kanode_handle* h, const float* d_u0, int64_t batch, do
     return 0;
 }
 int kanode_train_params(kanode_handle* h, float* p) {
+    KANODE_SINGLE_ONLY(h, "kanode_train_params");
     if (int rc = enter(h)) return rc;
     if (!h->train_on || !p) return fail(h, KANODE_ERR_INVALID, "kanode_train_begin first");
     CK(h, cudaMemcpyAsync(p, h->ws[kanode_handle::W_TR_P].p, sizeof(float) * h->np, cudaMemcpyDeviceToHost, h->stream));
@@ -728,6 +911,7 @@ int kanode_train_params(kanode_handle* h, float* p) {
 int kanode_loss_grad_dev(kanode_handle* h, const float* d_u0, int64_t batch, double t0, double t1, const double* saveat,
                          int32_t nsave, const float* d_target, float abstol, float reltol, double* d_loss_sum,
                          float* d_grad_sum, float* d_du0, kanode_stats* d_fwd_stats, kanode_stats* d_bwd_stats) {
+    KANODE_SINGLE_ONLY(h, "kanode_loss_grad_dev");
     if (int rc = enter(h)) return rc;
     if (batch < 0 || !d_loss_sum || !d_grad_sum) return fail(h, KANODE_ERR_INVALID, "bad arguments");
     return loss_grad_dev<float>(h, d_u0, batch, t0, t1, saveat, nsave, d_target, abstol, reltol, d_loss_sum,
@@ -737,6 +921,7 @@ int kanode_loss_grad_dev_f64(kanode_handle* h, const double* d_u0, int64_t batch
                              const double* saveat, int32_t nsave, const double* d_target, double abstol, double reltol,
                              double* d_loss_sum, double* d_grad_sum, double* d_du0, kanode_stats* d_fwd_stats,
                              kanode_stats* d_bwd_stats) {
+    KANODE_SINGLE_ONLY(h, "kanode_loss_grad_dev_f64");
     if (int rc = enter(h)) return rc;
     if (batch < 0 || !d_loss_sum || !d_grad_sum) return fail(h, KANODE_ERR_INVALID, "bad arguments");
     return loss_grad_dev<double>(h, d_u0, batch, t0, t1, saveat, nsave, d_target, abstol, reltol, d_loss_sum,

@@ -56,6 +56,9 @@ struct kanode_handle {
     float tr_eta = 0.f, tr_b1 = 0.9f, tr_b2 = 0.999f, tr_eps = 1e-8f;
     int64_t tr_t = 0;
     int n_out = 0;                   // output length of one sample of kanode_rhs (= n except for KANODE_RHS_MAP)
+    // kanode_create_multi: this handle routes; one child handle (own stream, own workspace) per device
+    std::vector<kanode_handle*> children;
+    bool peer_ok = false;            // device children[0] can load from every other child's memory (NVLink / PCIe P2P)
     int last_failed[2] = {0, 0};     // failed forward / adjoint solves of the last host-pointer loss_grad call
     unsigned attr_done = 0;          // per-handle (= per-device) one-time cudaFuncSetAttribute bits
     int rec_cap = 32;
@@ -71,7 +74,7 @@ struct kanode_handle {
     void* stage = nullptr; size_t stage_bytes = 0;   // pinned host staging block for the results of the host entry points
     // grow-only device workspace, keyed by purpose
     enum { W_U0, W_OUT, W_TARGET, W_STATS_F, W_STATS_B, W_SAVEAT, W_REC_T, W_REC, W_NSTEPS, W_RET, W_DG, W_FAC, W_G,
-           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_WPK32, W_WPK64, W_LAM, W_GEN, W_GEN2, W_LS, W_ATT, W_ORDER, W_WIDE_F, W_WIDE_B, W_W1T32, W_W1T64, W_W2IMG, W_W2TIMG, W_W1IMG, W_WIDE_R, W_WLG32, W_WLG64, W_GPART, W_SLAB, W_RPF, W_RPB, W_COT, W_FAILCNT, W_REG, W_ACT, W_TR_P, W_TR_M, W_TR_V, W_TR_GRAD, W_TR_OUT, W_TR_RAW, W_COUNT };
+           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_WPK32, W_WPK64, W_LAM, W_GEN, W_GEN2, W_LS, W_ATT, W_ORDER, W_WIDE_F, W_WIDE_B, W_W1T32, W_W1T64, W_W2IMG, W_W2TIMG, W_W1IMG, W_WIDE_R, W_WLG32, W_WLG64, W_GPART, W_SLAB, W_RPF, W_RPB, W_COT, W_FAILCNT, W_REG, W_ACT, W_TR_P, W_TR_M, W_TR_V, W_TR_GRAD, W_TR_OUT, W_TR_RAW, W_MULTI_G, W_MULTI_L, W_MULTI_STAGE, W_COUNT };
     DevBuf ws[W_COUNT];
     kanode::GenericModel gm{};               // layer table for the generic kernels
     // wide (batched lockstep) engine: attempts the last forward-only / dense-forward / backward call needed, counter state

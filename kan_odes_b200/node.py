@@ -67,7 +67,7 @@ class KanOde:
 
     def __init__(self, chain: Chain, rhs_kind: int = abi.RHS_CHAIN, n_state: int | None = None,
                  lap_coef: float = 0.0, dx: float = 1.0, device: int = 0, stream: int | None = None,
-                 dtype=np.float32):
+                 dtype=np.float32, devices: Sequence[int] | None = None):
         self.lib = abi.load_library()
         self.chain = chain
         self.desc = chain.desc(rhs_kind, n_state, lap_coef, dx)
@@ -82,7 +82,12 @@ class KanOde:
         self._suf = "" if self.dtype == np.float32 else "_f64"
         self._real = C.c_float if self.dtype == np.float32 else C.c_double
         h = C.c_void_p()
-        rc = self.lib.kanode_create(C.byref(self.desc), int(device), C.c_void_p(stream), C.byref(h))
+        if devices is not None and len(devices) > 1:
+            # one handle, several GPUs of the box: every batch is sharded over them inside the library (kanode_create_multi)
+            devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+            rc = self.lib.kanode_create_multi(C.byref(self.desc), devs, len(devices), C.byref(h))
+        else:
+            rc = self.lib.kanode_create(C.byref(self.desc), int(device if not devices else devices[0]), C.c_void_p(stream), C.byref(h))
         abi.check(self.lib, None, rc, "kanode_create")
         self.h = h
 
