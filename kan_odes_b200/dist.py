@@ -22,7 +22,8 @@ def shard_bounds(batch: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-_COUNT_CACHE: dict = {}
+_PACK_CACHE: dict = {}
+PACK_MAX = 1 << 16      # gradients up to this many entries travel with the loss sum and the count in ONE fp64 all-reduce
 
 
 def combine_loss_grad(loss_sum: torch.Tensor, grad_sum: torch.Tensor, local_count: int, nsave: int, n: int,
@@ -30,21 +31,36 @@ def combine_loss_grad(loss_sum: torch.Tensor, grad_sum: torch.Tensor, local_coun
     """All-reduce the UNNORMALISED sums of a step (what kanode_loss_grad_dev returns) and normalise once, globally:
         loss = sum_b sum_{s,i} (pred - X)^2 / (B * nsave * n)     (mean(abs2, ...) over the whole ensemble)
         grad = sum_b g_b(t0) / B
-    Works for any world size (1 included) and for ragged shards.  grad_sum is reduced in place; the loss sum and the
-    trajectory count travel in ONE 2-element float64 all-reduce (two collectives per step in total).
+    Works for any world size (1 included) and for ragged shards.  ONE collective per step for small models: the gradient sum
+    (np <= PACK_MAX entries), the loss sum and the trajectory count are packed into one persistent fp64 buffer [np + 2]
+    (at 8 ranks the step time of the LV ensemble is the latency of the rendezvous, not the bytes: a second tiny all-reduce
+    costs as much as the first).  Larger gradients (the PDE surrogates) are reduced in their own dtype, in place, and the
+    2-element fp64 pair follows in a second collective (noise next to their step time).
     `sync=False` keeps everything on the device (no host read-back inside a training / timing loop): the third return value
     is then the global count as a 1-element tensor instead of an int."""
-    key = (loss_sum.device, int(local_count))
-    cnt = _COUNT_CACHE.get(key)
-    if cnt is None:                                            # built once per (device, shard size): no per-step host-to-device copy
-        cnt = _COUNT_CACHE[key] = torch.tensor([float(local_count)], dtype=torch.float64, device=loss_sum.device)
-    pair = torch.cat([loss_sum.reshape(1).to(torch.float64), cnt])
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(grad_sum, group=group)
-        dist.all_reduce(pair, group=group)
-    count = pair[1:2]
-    loss = pair[0:1] / (count * (nsave * n))
-    grad = grad_sum / count.to(grad_sum.dtype)
+    npar = grad_sum.numel()
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    key = (loss_sum.device, int(local_count), npar if npar <= PACK_MAX else 0)
+    buf = _PACK_CACHE.get(key)
+    if buf is None:                                            # built once per (device, shard size, np): no per-step allocation or H2D copy
+        buf = _PACK_CACHE[key] = torch.zeros((npar if npar <= PACK_MAX else 0) + 2, dtype=torch.float64, device=loss_sum.device)
+    if npar <= PACK_MAX:
+        buf[:npar].copy_(grad_sum.reshape(-1))
+        buf[npar:npar + 1].copy_(loss_sum.reshape(1))
+        buf[npar + 1] = float(local_count)
+        if multi:
+            dist.all_reduce(buf, group=group)
+        count = buf[npar + 1:npar + 2]
+        loss = buf[npar:npar + 1] / (count * (nsave * n))
+        grad = (buf[:npar] / count).to(grad_sum.dtype).reshape(grad_sum.shape)
+    else:
+        buf[0:1].copy_(loss_sum.reshape(1)); buf[1] = float(local_count)
+        if multi:
+            dist.all_reduce(grad_sum, group=group)
+            dist.all_reduce(buf, group=group)
+        count = buf[1:2]
+        loss = buf[0:1] / (count * (nsave * n))
+        grad = grad_sum / count.to(grad_sum.dtype)
     if not sync:
         return loss, grad, count
     total = int(round(count.item()))

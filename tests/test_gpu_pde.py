@@ -171,22 +171,75 @@ def test_allen_cahn_surrogate_4096_wide_layer_fp64():
     assert _relmax(r["grad"], ref["grad"]) < 1e-7
 
 
+_SCHROD = {}
+
+
+def _schrodinger_case():
+    """BASELINE configs[4] shape: [32768,10,32768] G=10 (Re/Im split on a 16,384-point grid), one IC; the fp64 oracle result is
+    computed once (about a minute of CPU) and shared by the fp64 and the fp32 / tcgen05 tests."""
+    if not _SCHROD:
+        n = 32768
+        chain = surrogate_chain(n, 10, 10)
+        p = glorot_params(chain, seed=2)
+        x = np.linspace(-5, 5, 16384)
+        u0 = np.concatenate([2 / np.cosh(x), np.zeros_like(x)])[None, :]
+        saveat = np.array([0.1, 0.3, 0.5, 0.7, 0.9, 1.1, 1.3, 1.5])
+        tg = u0[:, None, :] * np.cos(saveat)[None, :, None]
+        orc = Oracle(chain.desc(), np.float64)
+        _SCHROD.update(chain=chain, p=p, u0=u0, saveat=saveat, tg=tg, orc=orc,
+                       ref=orc.loss_grad(p, u0, (0.0, np.pi / 2), saveat, tg))
+    return _SCHROD
+
+
 def test_schrodinger_16384_fp64():
-    """BASELINE configs[4] shape: [32768,10,32768] G=10 (Re/Im split on a 16,384-point grid), one IC, fp64 parity."""
-    n = 32768
-    chain = surrogate_chain(n, 10, 10)
-    p = glorot_params(chain, seed=2)
-    x = np.linspace(-5, 5, 16384)
-    u0 = np.concatenate([2 / np.cosh(x), np.zeros_like(x)])[None, :]
-    saveat = np.array([0.1, 0.3, 0.5, 0.7, 0.9, 1.1, 1.3, 1.5])
-    tg = u0[:, None, :] * np.cos(saveat)[None, :, None]
-    ode = K.KanOde(chain, dtype=np.float64); ode.set_params(p)
-    r = ode.loss_grad(u0, (0.0, np.pi / 2), saveat, tg)
-    ref = Oracle(chain.desc(), np.float64).loss_grad(p, u0, (0.0, np.pi / 2), saveat, tg)
+    """BASELINE configs[4] shape, one IC, fp64 parity."""
+    c = _schrodinger_case(); ref = c["ref"]
+    ode = K.KanOde(c["chain"], dtype=np.float64); ode.set_params(c["p"])
+    r = ode.loss_grad(c["u0"], (0.0, np.pi / 2), c["saveat"], c["tg"])
     assert (r["fwd_stats"].naccept == ref["fwd_stats"][:, 0]).all()
     assert (r["bwd_stats"].naccept == ref["bwd_stats"][:, 0]).all()
     assert abs(r["loss"] - ref["loss"]) < 1e-9 * abs(ref["loss"])
     assert _relmax(r["grad"], ref["grad"]) < 1e-7
+
+
+def _tc_vs_oracle(chain, p, u0, tspan, saveat, tg, orc, ref, monkeypatch, label):
+    """fp32 with the tcgen05 contraction kernels (wide_l2_fwd_tc, wide_l2_vjp_tc: n % 128 == 0) against the fp64 oracle, and
+    against the CUDA-core kernels of the same engine (KANODE_WIDE_TC=0) to show that the tensor-core kernels are the ones that
+    ran.  RHS arithmetic within 2e-5; loss / gradient of the adaptive fp32 solve within solver accuracy (fp32 cannot follow the
+    fp64 step sequence)."""
+    res = {}
+    for tc in (1, 0):
+        monkeypatch.setenv("KANODE_WIDE", "1"); monkeypatch.setenv("KANODE_WIDE_TC", str(tc))
+        ode = K.KanOde(chain, dtype=np.float32); ode.set_params(p)
+        res[tc] = (ode.rhs(u0), ode.loss_grad(u0, tspan, saveat, tg))
+        ode.close()
+    ref_rhs = orc.rhs(p, u0)
+    e_rhs = _relmax(res[1][0], ref_rhs)
+    assert e_rhs < 2e-5 and _relmax(res[0][0], ref_rhs) < 2e-5
+    assert not np.array_equal(res[1][0], res[0][0])                       # 3xTF32 on TMEM vs fp32 FFMA: close, not bit-identical
+    r = res[1][1]
+    assert (r["fwd_stats"].retcode == 0).all() and (r["bwd_stats"].retcode == 0).all()
+    e_g, e_l = _relmax(r["grad"], ref["grad"]), abs(r["loss"] - ref["loss"]) / abs(ref["loss"])
+    same = ((r["fwd_stats"].naccept == ref["fwd_stats"][:, 0]) & (r["bwd_stats"].naccept == ref["bwd_stats"][:, 0])).mean()
+    print(f"{label}: fp32/tcgen05 vs fp64 oracle: rhs {e_rhs:.2e}, loss {e_l:.2e}, gradient {e_g:.2e}, identical step counts {100 * same:.0f}% of ICs; "
+          f"tcgen05 vs CUDA cores: gradient {_relmax(r['grad'], res[0][1]['grad'].astype(np.float64)):.2e}")
+    assert e_g < 2e-2 and e_l < 5e-3
+
+
+@pytest.mark.parametrize("name,n,G,B", [("burgers1024", 1024, 5, 64), ("ac4096", 4096, 10, 32)])
+def test_tcgen05_kernels_vs_oracle_at_config_sizes_batched_fp32(name, n, G, B, monkeypatch):
+    """BASELINE configs[2] / configs[3] at their model size and a real batch (the TC kernels had only been compared
+    with the oracle at n = 256 / 384)."""
+    import bench
+    chain, kw, p, u0, ts, sa, tg = bench.pde_make(name, B, np.random.default_rng(3))
+    orc = Oracle(chain.desc(), np.float64); orc.set_threads(__import__("os").cpu_count() or 1)
+    ref = orc.loss_grad(p, u0, ts, sa, tg)
+    _tc_vs_oracle(chain, p, u0, ts, sa, tg, orc, ref, monkeypatch, f"{name} x {B}")
+
+
+def test_tcgen05_kernels_vs_oracle_schrodinger_16384_fp32(monkeypatch):
+    c = _schrodinger_case()
+    _tc_vs_oracle(c["chain"], c["p"], c["u0"], (0.0, np.pi / 2), c["saveat"], c["tg"], c["orc"], c["ref"], monkeypatch, "schrodinger16384 x 1")
 
 
 def test_hidden_source_4096_fp64():
