@@ -88,3 +88,21 @@ def test_adam_matches_flux_formula():
     m = 0.9 * m + 0.1 * g2; v = 0.999 * v + 0.001 * g2**2
     ref = ref - 5e-4 * (m / (1 - 0.9**2)) / (np.sqrt(v / (1 - 0.999**2)) + 1e-8)
     assert np.allclose(q, ref, rtol=1e-13)
+
+
+def test_mat_checkpoint_roundtrip_in_the_reference_layout(tmp_path):
+    """`.mat` checkpoint with the reference's variable names and shapes (LV_driver_KANODE.jl:251-272) and its restart read (:149-159)."""
+    import numpy as np
+    from scipy.io import loadmat
+    import kan_odes_b200 as K
+    rng = np.random.default_rng(0)
+    p_list = [rng.normal(size=240) for _ in range(5)]
+    t = np.arange(141) * 0.1
+    pred = rng.normal(size=(141, 2))
+    f = tmp_path / "LV_kanode_results.mat"
+    K.save_checkpoint(f, p_list, [3.0, 2.0, 1.0], [4.0, 3.5, 3.1], t, pred, [2, 10, 5])
+    m = loadmat(str(f))
+    assert m["p_list"].shape == (5, 240, 1) and m["loss"].shape == (5, 1) and m["kan_pred_u1"].shape == (141, 1)
+    assert np.array_equal(np.ravel(m["loss"]), [3.0, 2.0, 1.0, 0.0, 0.0])                # zero padded to len(p_list) like :257-264
+    ck = K.load_checkpoint(f)
+    assert np.array_equal(ck["p"], p_list[-1]) and ck["size_KAN"] == [2, 10, 5] and np.array_equal(ck["kan_pred_u2"], pred[:, 1])
