@@ -161,11 +161,8 @@ int small_lg_loss_grad(kanode_handle* h, const T* d_u0, int64_t B, double t0, do
         // (profiles/); KANODE_LG_SHAPE selects another one for A/B runs
         if constexpr (sizeof(T) == 4) {
             switch (h->lg_shape) {
-                case 1: return launch.template operator()<P, NORM, 2, 4, 3>();
-                case 4: return launch.template operator()<P, NORM, 1, 4, 4>();
-                case 5: return launch.template operator()<P, NORM, 1, 4, 3>();
-                case 6: return launch.template operator()<P, NORM, 1, 8, 2>();
-                default: return launch.template operator()<P, NORM, 2, KANODE_LG_WPB, KANODE_LG_MINB>();
+                case 1: return launch.template operator()<P, NORM, 2, 4, 3>();      // 12 warps/SM at 168 registers (spills): slower on B200
+                default: return launch.template operator()<P, NORM, 2, KANODE_LG_WPB, KANODE_LG_MINB>();   // 8 warps/SM, no spills
             }
         } else {
             return launch.template operator()<P, NORM, 1, 4, 2>();

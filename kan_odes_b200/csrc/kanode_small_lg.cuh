@@ -105,14 +105,17 @@ template <class T, class P, int UPL> struct LgSmem {
     static constexpr int LSS = up(7 * GM::I);           // per trajectory: stage adjoints lambda_s
     static constexpr int LSW = GM::TPW * LSS;
     static constexpr int RCW = GM::TPW * 2 * RL::RS;    // per trajectory: the two dense-forward records around t
-    static constexpr int PER_WARP = 32 * FACL + up(F1W) + LSW + RCW;
+    // per trajectory: two mailbox slots [save time (fp64) | dL/du(t_s) (I)] for the next two jumps (slot = save index & 1)
+    static constexpr int MBS = up(RL::OT + GM::I);
+    static constexpr int MBW = GM::TPW * 2 * MBS;
+    static constexpr int PER_WARP = 32 * FACL + up(F1W) + LSW + RCW + MBW;
     // packed weights in LANE blocks: lane `lig` of a group reads [UPL][P::UW] at lig*LW; the pad makes the 16-byte
     // accesses of the lanes of a group hit distinct banks (upload_packed_lg builds the same image in global memory)
     static constexpr int LW = UPL * P::UW + V;
     static constexpr int WLG = GM::LPT * LW;
     static constexpr int BAROFF = up(WLG);              // mbarrier (16 bytes) behind the weights
     static constexpr int WOFF = BAROFF + V;
-    static constexpr int F1OFF = 32 * FACL, LSOFF = F1OFF + up(F1W), RCOFF = LSOFF + LSW;   // offsets inside a warp's slice
+    static constexpr int F1OFF = 32 * FACL, LSOFF = F1OFF + up(F1W), RCOFF = LSOFF + LSW, MBOFF = RCOFF + RCW;   // offsets inside a warp's slice
     static constexpr size_t bytes(int warps) { return sizeof(T) * (size_t)(WOFF + warps * PER_WARP); }
 };
 
@@ -128,6 +131,13 @@ __device__ __forceinline__ void kadd2(float& d0, float& d1, float a0, float a1, 
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rd));
 }
 template <class T> __device__ __forceinline__ void kadd2(T& d0, T& d1, T a0, T a1, T b0, T b1) { d0 = a0 + b0; d1 = a1 + b1; }
+
+// asynchronous global -> shared copies (LDGSTS): no destination register, no scoreboard; completion by wait_all
+template <int BYTES> __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async size");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // PI controller of the lane-group kernel.  fp64 follows pi_q (kanode_math.cuh) to the letter: its step sequence equals the
 // oracle's.  fp32 evaluates the same formulas with MUFU reciprocals / ex2 and no double-precision division: the fp32 solve
@@ -207,6 +217,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
     T* f1g = wbase + SMP::F1OFF + gsl * NB * F1S;                    // this trajectory's input features [NB][F1S]
     T* lsg = wbase + SMP::LSOFF + gsl * LSS;                         // its stage adjoints [7][I]
     T* rcg = wbase + SMP::RCOFF + gsl * 2 * RS;                      // its record window: record r sits in slot r & 1
+    T* mbg = wbase + SMP::MBOFF + gsl * 2 * SMP::MBS;                // its jump mailbox: save index s sits in slot s & 1
     const int j0 = UPL * lig;                                       // first hidden unit of this lane
     const T* wlane = wsm + lig * SMP::LW;                           // its packed weights [UPL][UW]
 
@@ -252,11 +263,8 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
     // ---- window on the dense forward record: records ridx (holds t) and ridx-1 in shared memory ----
     const bool haspiece = gvalid && lig < NPIECE;
     int ridx = nsteps > 0 ? nsteps - 1 : 0;
-    double rt0 = rec_get_time(rbase + (int64_t)ridx * RS), rt1 = 0.0, pend_rt = 0.0;
-    bool prev_ok = false, pend = false;
-    T pv[V];
-#pragma unroll
-    for (int e = 0; e < V; ++e) pv[e] = T(0);
+    double rt0 = rec_get_time(rbase + (int64_t)ridx * RS), rt1 = 0.0;
+    bool prev_ok = false, pend = false;                             // pend: the lower record is in flight (cp.async)
     auto window_load = [&](int r) {                                 // blocking: this lane's piece of record r
         if (haspiece) { T v[V]; ldv(rbase + (int64_t)r * RS + lig * V, v); stv(rcg + (r & 1) * RS + lig * V, v); }
     };
@@ -393,28 +401,43 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
 
     double t = t1;
     int sp = a.nsave - 1;                                           // next preset (save) time, descending
-    // a.saveat[sp] (needed right at the next loop header: fetched TWO jumps ahead) and dL/du(t_sp) (needed at the end of the
-    // attempt that reaches t_sp: fetched one jump ahead)
-    double nxt_t = sp >= 0 ? a.saveat[sp] : 0.0, nxt2_t = sp >= 1 ? a.saveat[sp - 1] : 0.0;
-    T nxt_dg[I];
+    // Jumps: save index s travels as [a.saveat[s] | dL/du(t_s)] through mailbox slot s & 1, fetched asynchronously TWO jumps
+    // ahead by the first lane of the group (the save time is needed at the very next loop header, the cotangent at the end of the
+    // attempt that reaches t_s).  Equal consecutive save times (two jumps at one instant) switch the trajectory to plain loads.
+    constexpr int MBS = SMP::MBS, OT = RL::OT;
+    auto mb_fetch = [&](int s) {
+        if (s >= 0 && lig == 0 && gvalid) {
+            T* slot = mbg + (s & 1) * MBS;
+            cp_async<8>(slot, a.saveat + s);
 #pragma unroll
-    for (int i = 0; i < I; ++i) nxt_dg[i] = T(0);
-    auto fetch_jump = [&]() {
-        if (sp >= 0) {
-#pragma unroll
-            for (int i = 0; i < I; ++i) nxt_dg[i] = dgb[sp * I + i];
+            for (int i = 0; i < I; ++i) cp_async<(int)sizeof(T)>(slot + OT + i, dgb + s * I + i);
         }
     };
-    fetch_jump();
-    auto apply_jumps = [&](double tt) {
-        bool mod = false;
-        while (sp >= 0 && nxt_t == tt) {
+    bool mb_off = false;
+    mb_fetch(sp); mb_fetch(sp - 1);
+    cp_async_wait_all();
+    __syncwarp();
+    double nxt_t = sp >= 0 ? a.saveat[sp] : 0.0;
+    T jdg[I];                                                       // cotangent of the next jump, read from the mailbox every attempt
 #pragma unroll
-            for (int i = 0; i < I; ++i) lam[i] += nxt_dg[i];
-            --sp; mod = true;
-            nxt_t = nxt2_t;
-            if (sp >= 1) nxt2_t = a.saveat[sp - 1];
-            fetch_jump();
+    for (int i = 0; i < I; ++i) jdg[i] = sp >= 0 ? mbg[(sp & 1) * MBS + OT + i] : T(0);
+    auto apply_jumps = [&](double tt) {
+        bool mod = false, first = true;
+        while (sp >= 0 && nxt_t == tt) {
+            if (first && !mb_off) {
+#pragma unroll
+                for (int i = 0; i < I; ++i) lam[i] += jdg[i];
+                mb_fetch(sp - 2);                                   // refills the slot just consumed
+                --sp;
+                nxt_t = sp >= 0 ? rec_get_time(mbg + (sp & 1) * MBS) : 0.0;     // landed at least one attempt ago
+            } else {
+                mb_off = true;
+#pragma unroll
+                for (int i = 0; i < I; ++i) lam[i] += dgb[sp * I + i];
+                --sp;
+                nxt_t = sp >= 0 ? a.saveat[sp] : 0.0;
+            }
+            mod = true; first = false;
         }
         return mod;
     };
@@ -680,10 +703,12 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
         // ---- loopfooter!: PI controller ----
         const typename LC::Q q = LC::q(EEst, qold, q11);
         accept = rp ? true : (EEst <= (typename LC::Q)1);
-        __syncwarp();                                               // every lane of the group is past its reads of f1g
-        if (pend) {                                                 // record window: land the piece fetched one attempt ago
-            if (haspiece) stv(rcg + ((ridx - 1) & 1) * RS + lig * V, pv);
-            rt1 = pend_rt; prev_ok = true; pend = false;
+        cp_async_wait_all();                                        // copies issued at the end of the previous attempt
+        __syncwarp();                                               // ... visible to the group; every lane is past its reads of f1g
+        if (pend) { rt1 = rec_get_time(rcg + ((ridx - 1) & 1) * RS); prev_ok = true; pend = false; }   // record window: lower record landed
+        if (sp >= 0) {
+#pragma unroll
+            for (int i = 0; i < I; ++i) jdg[i] = mb_off ? dgb[sp * I + i] : mbg[(sp & 1) * MBS + OT + i];
         }
         if (!done) {
             if (accept) {
@@ -731,8 +756,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
             }
             prev_ok = false;
             if (ridx > 0) {                                         // the record below: in flight during the next attempt
-                if (haspiece) ldv(rbase + (int64_t)(ridx - 1) * RS + lig * V, pv);
-                pend_rt = rec_get_time(rbase + (int64_t)(ridx - 1) * RS);
+                if (haspiece) cp_async<16>(rcg + ((ridx - 1) & 1) * RS + lig * V, rbase + (int64_t)(ridx - 1) * RS + lig * V);
                 pend = true;
             }
         }
