@@ -528,7 +528,7 @@ def run_ours(args):
 
     import kan_odes_b200 as K
     from kan_odes_b200 import abi
-    from kan_odes_b200.dist import combine_loss_grad
+    from kan_odes_b200.dist import packed_all_reduce
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -568,13 +568,16 @@ def run_ours(args):
                 d_loss.data_ptr(), d_grad.data_ptr(), None,
                 d_fst.data_ptr() if with_stats else None, d_bst.data_ptr() if with_stats else None)
         abi.check(lib, ode.h, rc, "kanode_loss_grad_dev")
-        if world > 1 and not os.environ.get("KANODE_BENCH_NO_ALLREDUCE"):  # the only collective: gradient + loss sums
-            combine_loss_grad(d_loss, d_grad, B, SAVEAT.size, 2, sync=False)   # no host read-back inside the timed loop
+        if world > 1 and not os.environ.get("KANODE_BENCH_NO_ALLREDUCE"):
+            # the only collective of a step: [gradient sum | loss sum | count] packed by one kernel, ONE all-reduce, no host read-back
+            packed_all_reduce(ode, d_loss, d_grad, B)
             # (KANODE_BENCH_NO_ALLREDUCE=1 is a diagnostic: it isolates the collective's share of the step at N > 1; not a bench mode)
 
     ms3 = (C.c_float * 3)()
     prng = np.random.default_rng(99)                               # same on every rank: replicated parameters
-    p_steps = [p * (1.0 + 2e-3 * prng.standard_normal(p.shape)) for _ in range(args.steps)]
+    with torch.cuda.stream(stream):                                # resident like a device-side optimizer's output: the refresh is kernels only
+        p_steps = [torch.tensor(p * (1.0 + 2e-3 * prng.standard_normal(p.shape)), dtype=torch.float32, device=dev) for _ in range(args.steps)]
+    lib.kanode_set_params_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     with torch.cuda.stream(stream):
         step(True)                                                 # untimed: per-trajectory statistics
         stream.synchronize()
@@ -593,7 +596,8 @@ def run_ours(args):
         k_ms = np.zeros((args.steps, 3))
         for i in range(args.steps):
             if not args.fixed_params:                              # training conditions: the parameters move between steps, so the
-                ode.set_params(p_steps[i])                         # launch order predicted from the last step is not exact (untimed)
+                # launch order predicted from the last step is not exact (untimed; device-side refresh, the host is not blocked)
+                abi.check(lib, ode.h, lib.kanode_set_params_dev(ode.h, p_steps[i].data_ptr(), npar), "kanode_set_params_dev")
             flush.zero_()                                          # L2 flush between timed iterations (untimed)
             evs[i][0].record(stream)
             step(False)

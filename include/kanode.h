@@ -300,6 +300,15 @@ int kanode_train_step_dev(kanode_handle* h, const float* d_u0, int64_t batch, do
 int kanode_train_apply_dev(kanode_handle* h, const float* d_grad_sum, float grad_scale);
 int kanode_train_params(kanode_handle* h, float* p /* [np] host */);
 
+/* ---- data-parallel plumbing (one process per GPU): ONE collective per step ---------------------------------------------
+ * kanode_pack_sums_dev packs the un-normalised sums of kanode_loss_grad_dev* into one fp64 buffer
+ *   d_packed[np + 2] = [gradient sum (np) | loss sum | trajectory count]
+ * so that the caller all-reduces (NCCL over NVLink) exactly one buffer per step; kanode_train_apply_packed_dev then applies
+ * Adam with g = packed gradient / packed count (read on the device: no host round trip) and refreshes the parameter images. */
+int kanode_pack_sums_dev(kanode_handle* h, const float* d_grad_sum, const double* d_loss_sum, int64_t count, double* d_packed);
+int kanode_pack_sums_dev_f64(kanode_handle* h, const double* d_grad_sum, const double* d_loss_sum, int64_t count, double* d_packed);
+int kanode_train_apply_packed_dev(kanode_handle* h, const double* d_packed);
+
 /* Flux.Adam(eta, (beta1, beta2), eps) + update!(opt, p, grad)  (LV_driver_KANODE.jl:219,287; [EXT Flux 0.14.22]):
  *   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g^2;  p -= eta * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps),  g = grad_scale*d_grad.
  * All pointers are device pointers of np floats; t is the 1-based iteration count.  grad_scale lets a data-parallel

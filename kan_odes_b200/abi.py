@@ -64,7 +64,7 @@ EXPORTED_SYMBOLS = (
     "kanode_loss_grad_replay", "kanode_loss_grad_replay_f64",
     "kanode_solve_adjoint", "kanode_solve_adjoint_f64", "kanode_solve_adjoint_dev",
     "kanode_edge_activations", "kanode_edge_activations_f64", "kanode_set_regularizer", "kanode_reg_loss",
-    "kanode_create_multi", "kanode_device_count", "kanode_train_begin", "kanode_train_step_dev", "kanode_train_apply_dev", "kanode_train_params",
+    "kanode_pack_sums_dev", "kanode_pack_sums_dev_f64", "kanode_train_apply_packed_dev", "kanode_create_multi", "kanode_device_count", "kanode_train_begin", "kanode_train_step_dev", "kanode_train_apply_dev", "kanode_train_params",
 )
 
 _lib = None

@@ -357,6 +357,32 @@ int loss_grad_host(kanode_handle* h, const T* u0, int64_t B, double t0, double t
     }
 }
 
+template <class T>
+__global__ void __launch_bounds__(256) pack_sums_kernel(const T* __restrict__ g, const double* __restrict__ loss, double count, size_t np, double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) out[i] = (double)g[i];
+    else if (i == np) { out[np] = *loss; out[np + 1] = count; }
+}
+template <class T> int pack_sums(kanode_handle* h, const T* d_grad, const double* d_loss, int64_t count, double* d_packed) {
+    if (int rc = enter(h)) return rc;
+    if (!d_grad || !d_loss || !d_packed || count < 0) return fail(h, KANODE_ERR_INVALID, "bad arguments");
+    pack_sums_kernel<T><<<blocks_for((int64_t)h->np + 1, 256), 256, 0, h->stream>>>(d_grad, d_loss, (double)count, h->np, d_packed);
+    ++h->launches;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+// Adam on the all-reduced packed sums: g = packed[i] / packed[np + 1] (global trajectory count), all on the device
+__global__ void __launch_bounds__(256) adam_packed_kernel(float* __restrict__ p, const double* __restrict__ packed, float* __restrict__ m,
+                                                          float* __restrict__ v, size_t n, float eta, float b1, float b2, float eps, float c1, float c2) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float g = (float)(packed[i] / packed[n + 1]);
+    const float mi = b1 * m[i] + (1.0f - b1) * g;
+    const float vi = b2 * v[i] + (1.0f - b2) * g * g;
+    m[i] = mi; v[i] = vi;
+    p[i] -= eta * (mi * c1) / (sqrtf(vi * c2) + eps);
+}
+
 // ---- device-resident training ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) f32_to_f64_kernel(const float* __restrict__ a, double* __restrict__ b, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -873,6 +899,26 @@ int kanode_train_apply_dev(kanode_handle* h, const float* d_grad_sum, float grad
     if (int rc = enter(h)) return rc;
     if (!h->train_on || !d_grad_sum) return fail(h, KANODE_ERR_INVALID, "kanode_train_begin first");
     return train_apply(h, d_grad_sum, grad_scale);
+}
+int kanode_pack_sums_dev(kanode_handle* h, const float* d_grad_sum, const double* d_loss_sum, int64_t count, double* d_packed) {
+    KANODE_SINGLE_ONLY(h, "kanode_pack_sums_dev");
+    return pack_sums<float>(h, d_grad_sum, d_loss_sum, count, d_packed);
+}
+int kanode_pack_sums_dev_f64(kanode_handle* h, const double* d_grad_sum, const double* d_loss_sum, int64_t count, double* d_packed) {
+    KANODE_SINGLE_ONLY(h, "kanode_pack_sums_dev_f64");
+    return pack_sums<double>(h, d_grad_sum, d_loss_sum, count, d_packed);
+}
+int kanode_train_apply_packed_dev(kanode_handle* h, const double* d_packed) {
+    KANODE_SINGLE_ONLY(h, "kanode_train_apply_packed_dev");
+    if (int rc = enter(h)) return rc;
+    if (!h->train_on || !d_packed) return fail(h, KANODE_ERR_INVALID, "kanode_train_begin first");
+    float *p = (float*)h->ws[kanode_handle::W_TR_P].p, *m = (float*)h->ws[kanode_handle::W_TR_M].p, *v = (float*)h->ws[kanode_handle::W_TR_V].p;
+    ++h->tr_t;
+    const float c1 = (float)(1.0 / (1.0 - std::pow((double)h->tr_b1, (double)h->tr_t)));
+    const float c2 = (float)(1.0 / (1.0 - std::pow((double)h->tr_b2, (double)h->tr_t)));
+    adam_packed_kernel<<<blocks_for((int64_t)h->np, 256), 256, 0, h->stream>>>(p, d_packed, m, v, h->np, h->tr_eta, h->tr_b1, h->tr_b2, h->tr_eps, c1, c2);
+    ++h->launches;
+    return params_follow_dev(h, p);
 }
 int kanode_train_step_dev(kanode_handle* h, const float* d_u0, int64_t batch, double t0, double t1, const double* saveat,
                           int32_t nsave, const float* d_target, float abstol, float reltol, const float* d_u0_test,

@@ -26,6 +26,34 @@ _PACK_CACHE: dict = {}
 PACK_MAX = 1 << 16      # gradients up to this many entries travel with the loss sum and the count in ONE fp64 all-reduce
 
 
+def packed_all_reduce(ode, loss_sum: torch.Tensor, grad_sum: torch.Tensor, local_count: int, group=None) -> torch.Tensor:
+    """The data-parallel step on the device path: kanode_pack_sums_dev writes [gradient sum | loss sum | count] into ONE persistent
+    fp64 buffer with one kernel of the library (on the handle's stream = torch's current stream in the callers), then ONE
+    all-reduce.  Returns the reduced buffer [np + 2]; nothing is normalised or read back here (kanode_train_apply_packed_dev
+    consumes it on the device; `unpack` normalises for a host-side consumer)."""
+    import ctypes as C
+    npar = grad_sum.numel()
+    key = ("packed", loss_sum.device, npar)
+    buf = _PACK_CACHE.get(key)
+    if buf is None:
+        buf = _PACK_CACHE[key] = torch.zeros(npar + 2, dtype=torch.float64, device=loss_sum.device)
+    f = ode.lib.kanode_pack_sums_dev_f64 if grad_sum.dtype == torch.float64 else ode.lib.kanode_pack_sums_dev
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    rc = f(ode.h, grad_sum.data_ptr(), loss_sum.data_ptr(), int(local_count), buf.data_ptr())
+    if rc != 0:
+        raise RuntimeError(f"kanode_pack_sums_dev failed ({rc})")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, group=group)
+    return buf
+
+
+def unpack(packed: torch.Tensor, nsave: int, n: int, dtype=torch.float32):
+    """(loss, grad, count) of a reduced packed buffer: loss = sum / (B nsave n), grad = sum / B."""
+    npar = packed.numel() - 2
+    count = packed[npar + 1:npar + 2]
+    return packed[npar:npar + 1] / (count * (nsave * n)), (packed[:npar] / count).to(dtype), count
+
+
 def combine_loss_grad(loss_sum: torch.Tensor, grad_sum: torch.Tensor, local_count: int, nsave: int, n: int,
                       group=None, sync: bool = True):
     """All-reduce the UNNORMALISED sums of a step (what kanode_loss_grad_dev returns) and normalise once, globally:

@@ -308,3 +308,46 @@ def test_device_resident_training_matches_the_host_loop():
     # the handle serves the host-pointer entry points with the trained parameters afterwards (host copy refreshed lazily)
     assert np.abs(ode2.rhs(u0) - ode.rhs(u0)).max() < 1e-6
     ode.close(); ode2.close()
+
+
+def test_packed_sums_and_packed_adam_for_data_parallel_training(lv_saveat):
+    """kanode_pack_sums_dev ([gradient sum | loss sum | count] in one fp64 buffer = ONE all-reduce per step) and
+    kanode_train_apply_packed_dev (Adam with g = packed gradient / packed count read on the device) against the unpacked path."""
+    import ctypes as C
+    import torch
+    from kan_odes_b200.dist import packed_all_reduce, unpack
+    chain = lv_chain(); p = glorot_params(chain)
+    B = 64
+    u0 = np.random.default_rng(9).uniform(0.5, 2.0, (B, 2)).astype(np.float32); tg = lv_targets(u0[:1], lv_saveat).repeat(B, axis=0).astype(np.float32)
+    outs = []
+    for packed_path in (False, True):
+        ode = K.KanOde(chain, dtype=np.float32); ode.set_params(p)
+        lib = ode.lib
+        d_u0, d_tg = torch.tensor(u0, device="cuda"), torch.tensor(tg, device="cuda")
+        d_g = torch.zeros(240, device="cuda"); d_l = torch.zeros(1, dtype=torch.float64, device="cuda")
+        sa = np.ascontiguousarray(lv_saveat)
+        f = lib.kanode_loss_grad_dev
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_void_p, C.c_float, C.c_float,
+                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.kanode_train_begin.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]
+        K.abi.check(lib, ode.h, lib.kanode_train_begin(ode.h, 1e-3, 0.9, 0.999, 1e-8), "train_begin")
+        for _ in range(3):
+            K.abi.check(lib, ode.h, f(ode.h, d_u0.data_ptr(), B, 0.0, 3.5, sa.ctypes.data, sa.size, d_tg.data_ptr(), 1e-6, 1e-3, d_l.data_ptr(),
+                                      d_g.data_ptr(), None, None, None), "loss_grad_dev")
+            lib.kanode_sync(ode.h)                                 # torch's stream and the handle's own stream meet on the host in this test
+            if packed_path:
+                buf = packed_all_reduce(ode, d_l, d_g, B)          # world size 1: the pack kernel alone
+                lib.kanode_sync(ode.h)
+                loss, grad, cnt = unpack(buf, lv_saveat.size, 2)
+                assert int(cnt.item()) == B and torch.allclose(grad, d_g / B, rtol=1e-6, atol=0)
+                assert abs(loss.item() - d_l.item() / (B * lv_saveat.size * 2)) < 1e-15
+                lib.kanode_train_apply_packed_dev.argtypes = [C.c_void_p, C.c_void_p]
+                K.abi.check(lib, ode.h, lib.kanode_train_apply_packed_dev(ode.h, buf.data_ptr()), "apply_packed")
+            else:
+                lib.kanode_train_apply_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
+                K.abi.check(lib, ode.h, lib.kanode_train_apply_dev(ode.h, d_g.data_ptr(), 1.0 / B), "apply")
+            lib.kanode_sync(ode.h)
+        pt = np.empty(240, np.float32)
+        K.abi.check(lib, ode.h, lib.kanode_train_params(ode.h, pt.ctypes.data_as(C.c_void_p)), "train_params")
+        outs.append(pt); ode.close()
+    assert np.abs(outs[0] - outs[1]).max() < 2e-7 * np.abs(outs[0]).max() and np.abs(outs[0] - p).max() > 1e-4
