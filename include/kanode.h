@@ -102,7 +102,16 @@ typedef struct {
     float   grid_lo;              /* grid_lims[1], default -1f0 (kdense.jl:26) */
     float   grid_hi;              /* grid_lims[2], default  1f0               */
     float   denominator;          /* h, default Float32(2/(G-1)) (kdense.jl:27) */
+    int32_t kind;                 /* kanode_layer_kind: 0 = KDense (all fields above), 1 = Lux.Dense (MLP-NODE baseline) */
+    int32_t dense_act;            /* kind 1: output activation (enum kanode_dense_act); identity on the last layer */
 } kanode_layer_desc;
+
+/* layer kind.  KANODE_LAYER_DENSE is `Lux.Dense(in => out, act)`: y = act(W x + b), the right-hand side of the MLP-NODE baseline
+ * `Lux.Chain(Lux.Dense(2 => 50, tanh), Lux.Dense(50 => 2))` (Lotka-Volterra/LV_driver_MLP.jl:61).  Flat parameters of the layer in the
+ * ComponentArray order of that driver (:65-67): [vec(weight[out, in]); bias[out]].  grid_len / normalizer / basis / use_base_act
+ * are ignored for it.  Dense and KDense layers may be mixed in one chain; such chains run on the block-per-trajectory kernels. */
+typedef enum { KANODE_LAYER_KDENSE = 0, KANODE_LAYER_DENSE = 1 } kanode_layer_kind;
+typedef enum { KANODE_ACT_IDENTITY = 0, KANODE_ACT_TANH = 1 } kanode_dense_act;
 
 typedef struct {
     int32_t n_layers;

@@ -54,6 +54,7 @@ struct LayerDesc
     in_dims::Int32; out_dims::Int32; grid_len::Int32
     normalizer::Int32; basis::Int32; use_base_act::Int32
     grid_lo::Float32; grid_hi::Float32; denominator::Float32
+    kind::Int32; dense_act::Int32          # kind 1: Lux.Dense(in => out, act) of the MLP-NODE baseline (LV_driver_MLP.jl:61)
 end
 const MAX_LAYERS = 8
 struct Desc
@@ -95,12 +96,12 @@ end
 flatten_params(ps) = vcat((vcat(vec(p.C), p.W === nothing ? Float32[] : vec(p.W)) for p in ps)...)
 
 function Desc(c::Chain; rhs_kind = RHS_CHAIN, n_state = c.layers[1].in_dims, lap_coef = 0.0, dx = 1.0)
-    zero_l = LayerDesc(0, 0, 0, 0, 0, 0, 0f0, 0f0, 0f0)
+    zero_l = LayerDesc(0, 0, 0, 0, 0, 0, 0f0, 0f0, 0f0, 0, 0)
     ls = ntuple(MAX_LAYERS) do i
         i > length(c.layers) && return zero_l
         l = c.layers[i]
         LayerDesc(l.in_dims, l.out_dims, l.grid_len, Int32(l.normalizer.code), Int32(l.basis_func.code),
-                  l.use_base_act, l.grid_lims[1], l.grid_lims[2], l.denominator)
+                  l.use_base_act, l.grid_lims[1], l.grid_lims[2], l.denominator, 0, 0)
     end
     Desc(length(c.layers), ls, rhs_kind, n_state, lap_coef, dx)
 end

@@ -18,6 +18,8 @@ NORM_TANH, NORM_SOFTSIGN, NORM_SIGMOID = 0, 1, 2
 BASIS_RBF, BASIS_RSWAF, BASIS_IQF = 0, 1, 2
 # kanode_rhs_kind
 RHS_CHAIN, RHS_SOURCE_LAPLACIAN, RHS_MAP = 0, 1, 2
+LAYER_KDENSE, LAYER_DENSE = 0, 1
+ACT_IDENTITY, ACT_TANH = 0, 1
 # kanode_retcode
 RET_SUCCESS, RET_MAXITERS, RET_DT_LESS_THAN_MIN, RET_UNSTABLE, RET_RECORD_OVERFLOW = range(5)
 RETCODE_NAMES = ("Success", "MaxIters", "DtLessThanMin", "Unstable", "RecordOverflow")
@@ -31,6 +33,7 @@ class LayerDesc(C.Structure):
         ("in_dims", C.c_int32), ("out_dims", C.c_int32), ("grid_len", C.c_int32),
         ("normalizer", C.c_int32), ("basis", C.c_int32), ("use_base_act", C.c_int32),
         ("grid_lo", C.c_float), ("grid_hi", C.c_float), ("denominator", C.c_float),
+        ("kind", C.c_int32), ("dense_act", C.c_int32),
     ]
 
 

@@ -60,15 +60,39 @@ template <class T> __device__ __forceinline__ T block_sum(T x, GSmem<T>& sm) {
     return v[0];
 }
 
-// features of one input unit: c[q] = basis_q(x) for q < G, c[G] = swish(x) (0 without the base branch)
+// base-branch activation of a layer input: swish for KDense (kdense.jl:123); identity / tanh for Dense layers, where the output
+// activation of the layer before acts on this layer's inputs (Lux.Dense(2 => 50, tanh), LV_driver_MLP.jl:61)
+enum { ACT_SWISH = 0, ACT_IDENTITY = 1, ACT_TANH = 2 };
+template <class T> __device__ __forceinline__ void base_fwd(int act, T x, T& s) {
+    if (act == ACT_SWISH) swish_fwd(x, s);
+    else if (act == ACT_IDENTITY) s = x;
+    else s = ktanh(x);
+}
+template <class T> __device__ __forceinline__ void base_both(int act, T x, T& s, T& ds) {
+    if (act == ACT_SWISH) swish_both(x, s, ds);
+    else if (act == ACT_IDENTITY) { s = x; ds = T(1); }
+    else { s = ktanh(x); ds = T(1) - s * s; }
+}
+// inputs of the feature x weight loops: the I units plus, for a Dense layer, the virtual bias unit (feature 1)
+__device__ __forceinline__ int g_inputs(const GenericLayer& L) { return L.I + L.bias; }
+
+// features of one input unit: c[q] = basis_q(x) for q < G, c[G] = base activation of x (0 without the base branch)
 template <class T>
 __device__ __forceinline__ void g_features(const GenericLayer& L, const float* grid, T xi, T* c) {
-    const T xn = normalize_rt(L.norm, xi);
-    const T inv_h = (T)L.inv_h;
-    for (int g = 0; g < L.G; ++g) c[g] = basis_val(L.basis, (xn - (T)grid[g]) * inv_h);
+    if (L.G > 0) {
+        const T xn = normalize_rt(L.norm, xi);
+        const T inv_h = (T)L.inv_h;
+        for (int g = 0; g < L.G; ++g) c[g] = basis_val(L.basis, (xn - (T)grid[g]) * inv_h);
+    }
     T s = T(0);
-    if (L.use_base) swish_fwd(xi, s);
+    if (L.use_base) base_fwd(L.act, xi, s);
     c[L.G] = s;
+}
+// ... of unit i of the layer input vector x (i == L.I: the bias unit, which has no entry in x)
+template <class T>
+__device__ __forceinline__ void g_features_at(const GenericLayer& L, const float* grid, const T* x, int i, T* c) {
+    if (i >= L.I) { for (int g = 0; g < L.G; ++g) c[g] = T(0); c[L.G] = T(1); return; }
+    g_features(L, grid, x[i], c);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -81,13 +105,14 @@ __device__ void g_layer_forward(const GenericModel& m, int l, const T* __restric
     const int I = L.I, O = L.O, G = L.G, GP = L.G + 1;
     const T* C = p + L.offC;
     const T* W = p + L.offW;
-    if (O > I && (long long)I * GP <= GEN_FEAT) {
+    const int IB = g_inputs(L);
+    if (O > I && (long long)IB * GP <= GEN_FEAT) {
         __syncthreads();
-        for (int i = threadIdx.x; i < I; i += blockDim.x) g_features(L, grid, x[i], sm.feat + i * GP);
+        for (int i = threadIdx.x; i < IB; i += blockDim.x) g_features_at(L, grid, x, i, sm.feat + i * GP);
         __syncthreads();
         for (int o = threadIdx.x; o < O; o += blockDim.x) {
             T acc = T(0);
-            for (int i = 0; i < I; ++i) {
+            for (int i = 0; i < IB; ++i) {
                 const T* f = sm.feat + i * GP;
                 for (int g = 0; g < G; ++g) acc += C[((long long)i * G + g) * O + o] * f[g];
                 if (L.use_base) acc += W[(long long)i * O + o] * f[G];
@@ -103,17 +128,20 @@ __device__ void g_layer_forward(const GenericModel& m, int l, const T* __restric
         T acc[GEN_ACC];
 #pragma unroll
         for (int k = 0; k < GEN_ACC; ++k) acc[k] = T(0);
-        for (int i = threadIdx.x; i < I; i += blockDim.x) {
-            const T xi = x[i];
-            const T xn = normalize_rt(L.norm, xi);
-            for (int g = 0; g < G; ++g) {
-                const T b = basis_val(L.basis, (xn - (T)grid[g]) * inv_h);
-                const T* col = C + ((long long)i * G + g) * O + o0;
+        for (int i = threadIdx.x; i < IB; i += blockDim.x) {
+            const T xi = i < I ? x[i] : T(0);
+            if (G > 0 && i < I) {
+                const T xn = normalize_rt(L.norm, xi);
+                for (int g = 0; g < G; ++g) {
+                    const T b = basis_val(L.basis, (xn - (T)grid[g]) * inv_h);
+                    const T* col = C + ((long long)i * G + g) * O + o0;
 #pragma unroll
-                for (int k = 0; k < GEN_ACC; ++k) if (k < oc) acc[k] += col[k] * b;
+                    for (int k = 0; k < GEN_ACC; ++k) if (k < oc) acc[k] += col[k] * b;
+                }
             }
             if (L.use_base) {
-                T s; swish_fwd(xi, s);
+                T s = T(1);                                            // the bias unit's feature
+                if (i < I) base_fwd(L.act, xi, s);
                 const T* col = W + (long long)i * O + o0;
 #pragma unroll
                 for (int k = 0; k < GEN_ACC; ++k) if (k < oc) acc[k] += col[k] * s;
@@ -167,7 +195,7 @@ __device__ void g_layer_reverse(const GenericModel& m, int l, const T* __restric
             }
             T xb = xnbar * normalize_deriv_rt(L.norm, xn);
             if (L.use_base) {
-                T s, ds; swish_both(xi, s, ds);
+                T s, ds; base_both(L.act, xi, s, ds);
                 const T* col = W + (long long)i * O;
                 T sbar = T(0);
                 for (int o = 0; o < O; ++o) sbar += col[o] * ybar[o];
@@ -209,7 +237,7 @@ __device__ void g_layer_reverse(const GenericModel& m, int l, const T* __restric
                 xnbar += db * inv_h * sm.res[threadIdx.x * GP + g];
             }
             T xb = xnbar * normalize_deriv_rt(L.norm, xn);
-            if (L.use_base) { T s, ds; swish_both(xi, s, ds); xb += sm.res[threadIdx.x * GP + G] * ds; }
+            if (L.use_base) { T s, ds; base_both(L.act, xi, s, ds); xb += sm.res[threadIdx.x * GP + G] * ds; }
             xbar[i] = xb;
         }
     }
@@ -437,9 +465,9 @@ __global__ void __launch_bounds__(GEN_BT) generic_vjp_kernel(const __grid_consta
     for (int l = 0; l < m.n_layers; ++l) {
         const GenericLayer& L = m.L[l];
         const float* grid = m.grid + L.goff;
-        for (int i = threadIdx.x; i < L.I; i += blockDim.x) {
+        for (int i = threadIdx.x; i < g_inputs(L); i += blockDim.x) {
             T c[GEN_MAX_G + 1];
-            g_features(L, grid, rec[L.rx + i], c);
+            g_features_at(L, grid, rec + L.rx, i, c);
             for (int o = 0; o < L.O; ++o) {
                 const T a = rec[L.ry + o];
                 for (int g = 0; g < L.G; ++g) atomicAdd(&pbar[L.offC + ((long long)i * L.G + g) * L.O + o], a * c[g]);
@@ -611,40 +639,41 @@ __device__ void g_gphase_layer(const GenericModel& m, int l, const T* recs, cons
         es += r * r;
         gnew[j] = g1;
     };
-    if (O > I && 7LL * I * GQ <= GEN_FEAT) {          // thread per output; features of all inputs in smem
+    const int IB = g_inputs(L);
+    if (O > I && 7LL * IB * GQ <= GEN_FEAT) {         // thread per output; features of all inputs in smem
         __syncthreads();
-        for (int idx = threadIdx.x; idx < 7 * I; idx += blockDim.x) {
-            const int s = idx / I, i = idx - s * I;
-            g_features(L, grid, recs[s * RL + L.rx + i], sm.feat + (long long)idx * GQ);
+        for (int idx = threadIdx.x; idx < 7 * IB; idx += blockDim.x) {
+            const int s = idx / IB, i = idx - s * IB;
+            g_features_at(L, grid, recs + s * RL + L.rx, i, sm.feat + (long long)idx * GQ);
         }
         __syncthreads();
         for (int o = threadIdx.x; o < O; o += blockDim.x) {
             T ab[7], at[7];
 #pragma unroll
             for (int s = 0; s < 7; ++s) { const T yb = recs[s * RL + L.ry + o]; ab[s] = wb[s] * yb; at[s] = wbt[s] * yb; }
-            for (int i = 0; i < I; ++i)
+            for (int i = 0; i < IB; ++i)
                 for (int q = 0; q < GQ; ++q) {
-                    if (q == G && !L.use_base) continue;
+                    if (q == G ? !L.use_base : i >= I) continue;
                     T vb = T(0), vt = T(0);
 #pragma unroll
-                    for (int s = 0; s < 7; ++s) { const T c = sm.feat[((long long)s * I + i) * GQ + q]; vb += ab[s] * c; vt += at[s] * c; }
+                    for (int s = 0; s < 7; ++s) { const T c = sm.feat[((long long)s * IB + i) * GQ + q]; vb += ab[s] * c; vt += at[s] * c; }
                     finalize(q < G ? L.offC + ((long long)i * G + q) * O + o : L.offW + (long long)i * O + o, vb, vt);
                 }
         }
         __syncthreads();
         return;
     }
-    for (int i = threadIdx.x; i < I; i += blockDim.x) {     // thread per input unit; features in registers
+    for (int i = threadIdx.x; i < IB; i += blockDim.x) {    // thread per input unit (incl. the bias unit); features in registers
         T c[7][GP];
 #pragma unroll
         for (int s = 0; s < 7; ++s) {
-            const T xi = recs[s * RL + L.rx + i];
-            const T xn = normalize_rt(L.norm, xi);
+            const T xi = i < I ? recs[s * RL + L.rx + i] : T(0);
+            const T xn = (G > 0 && i < I) ? normalize_rt(L.norm, xi) : T(0);
 #pragma unroll
-            for (int q = 0; q < GP - 1; ++q) c[s][q] = q < G ? basis_val(L.basis, (xn - (T)grid[q < G ? q : 0]) * (T)L.inv_h) : T(0);
-            T sw = T(0);
-            if (L.use_base) swish_fwd(xi, sw);
-            c[s][GP - 1] = sw;                                 // swish kept in the last slot
+            for (int q = 0; q < GP - 1; ++q) c[s][q] = (q < G && i < I) ? basis_val(L.basis, (xn - (T)grid[q < G ? q : 0]) * (T)L.inv_h) : T(0);
+            T sw = i < I ? T(0) : T(1);
+            if (L.use_base && i < I) base_fwd(L.act, xi, sw);
+            c[s][GP - 1] = sw;                                 // base activation kept in the last slot
         }
         for (int o = 0; o < O; ++o) {
             T ab[7], at[7];
@@ -653,7 +682,7 @@ __device__ void g_gphase_layer(const GenericModel& m, int l, const T* recs, cons
 #pragma unroll
             for (int q = 0; q < GP; ++q) {
                 const bool is_sw = (q == GP - 1);
-                if (is_sw ? !L.use_base : q >= G) continue;
+                if (is_sw ? !L.use_base : (q >= G || i >= I)) continue;
                 T vb = T(0), vt = T(0);
 #pragma unroll
                 for (int s = 0; s < 7; ++s) { vb += ab[s] * c[s][q]; vt += at[s] * c[s][q]; }
@@ -727,14 +756,14 @@ __global__ void __launch_bounds__(GEN_BT) generic_backward_kernel(const __grid_c
         for (int l = 0; l < m.n_layers; ++l) {
             const GenericLayer& L = m.L[l];
             const float* grid = m.grid + L.goff;
-            for (int i = tid; i < L.I; i += bt) {
+            for (int i = tid; i < g_inputs(L); i += bt) {
                 T c0[GEN_MAX_G + 1], c1[GEN_MAX_G + 1];
-                g_features(L, grid, recs[L.rx + i], c0);
-                if (two) g_features(L, grid, recs[RL + L.rx + i], c1);
+                g_features_at(L, grid, recs + L.rx, i, c0);
+                if (two) g_features_at(L, grid, recs + RL + L.rx, i, c1);
                 for (int o = 0; o < L.O; ++o) {
                     const T a0 = recs[L.ry + o], a1 = two ? recs[RL + L.ry + o] : T(0);
                     for (int q = 0; q <= L.G; ++q) {
-                        if (q == L.G && !L.use_base) continue;
+                        if (q == L.G ? !L.use_base : i >= L.I) continue;
                         const T k0 = a0 * c0[q], k1 = two ? a1 * c1[q] : T(0);
                         const T x1 = k0 / a.abstol, x2 = (k1 - k0) / a.abstol;
                         s1 += x1 * x1; s2 += x2 * x2;
@@ -912,13 +941,21 @@ inline int generic_init(kanode_handle* h) {
     for (int l = 0; l < d.n_layers; ++l) {
         const kanode_layer_desc& s = d.layers[l];
         GenericLayer& L = m.L[l];
-        L.I = s.in_dims; L.O = s.out_dims; L.G = s.grid_len; L.norm = s.normalizer; L.basis = s.basis; L.use_base = s.use_base_act;
-        L.inv_h = 1.0f / s.denominator;
-        L.goff = goff;
-        if (s.grid_len <= GEN_MAX_G) for (int g = 0; g < s.grid_len; ++g) m.grid[goff + g] = grid_point(s, g);
-        goff += s.grid_len <= GEN_MAX_G ? s.grid_len : 0;
-        L.offC = off; off += (long long)L.O * L.G * L.I;
-        L.offW = off; if (L.use_base) off += (long long)L.O * L.I;
+        L.I = s.in_dims; L.O = s.out_dims; L.goff = goff;
+        if (s.kind == KANODE_LAYER_DENSE) {
+            // y = act(W x + b): no spline part; the base branch carries W with the activation of the layer BEFORE on the inputs
+            // (identity on the first layer), and a virtual input unit with feature 1 carries b — [vec(W); b] is an O x (I+1) block
+            L.G = 0; L.norm = 0; L.basis = 0; L.use_base = 1; L.bias = 1; L.inv_h = 1.0f;
+            L.act = (l > 0 && d.layers[l - 1].kind == KANODE_LAYER_DENSE && d.layers[l - 1].dense_act == KANODE_ACT_TANH) ? 2 : 1;
+            L.offC = off; L.offW = off; off += (long long)L.O * (L.I + 1);
+        } else {
+            L.G = s.grid_len; L.norm = s.normalizer; L.basis = s.basis; L.use_base = s.use_base_act; L.act = 0; L.bias = 0;
+            L.inv_h = 1.0f / s.denominator;
+            if (s.grid_len <= GEN_MAX_G) for (int g = 0; g < s.grid_len; ++g) m.grid[goff + g] = grid_point(s, g);
+            goff += s.grid_len <= GEN_MAX_G ? s.grid_len : 0;
+            L.offC = off; off += (long long)L.O * L.G * L.I;
+            L.offW = off; if (L.use_base) off += (long long)L.O * L.I;
+        }
         L.rx = roff; roff += L.I;
         L.ry = roff; roff += L.O;
     }
@@ -930,9 +967,11 @@ inline int generic_init(kanode_handle* h) {
 inline int generic_supported(kanode_handle* h) {
     const kanode_desc& d = h->desc;
     for (int l = 0; l < d.n_layers; ++l) {
-        if (d.layers[l].grid_len > GEN_MAX_G) return fail(h, KANODE_ERR_UNSUPPORTED, "grid_len > %d", GEN_MAX_G);
+        if (d.layers[l].kind == KANODE_LAYER_KDENSE && d.layers[l].grid_len > GEN_MAX_G) return fail(h, KANODE_ERR_UNSUPPORTED, "grid_len > %d", GEN_MAX_G);
         if (d.rhs_kind != KANODE_RHS_SOURCE_LAPLACIAN && l > 0 && d.layers[l].in_dims > GEN_ACT)
             return fail(h, KANODE_ERR_UNSUPPORTED, "hidden width %d > %d", d.layers[l].in_dims, GEN_ACT);
+        if (d.rhs_kind == KANODE_RHS_SOURCE_LAPLACIAN && d.layers[l].kind != KANODE_LAYER_KDENSE)
+            return fail(h, KANODE_ERR_UNSUPPORTED, "the hidden-source model takes KDense layers");
         if (d.rhs_kind == KANODE_RHS_SOURCE_LAPLACIAN && (d.layers[l].in_dims > GEN_PW || d.layers[l].out_dims > GEN_PW))
             return fail(h, KANODE_ERR_UNSUPPORTED, "pointwise chain wider than %d", GEN_PW);
     }

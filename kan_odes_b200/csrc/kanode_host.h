@@ -14,6 +14,9 @@ namespace kanode {
 constexpr int GEN_MAX_G = 32;
 struct GenericLayer {
     int I, O, G, norm, basis, use_base;
+    int act;                   // base-branch activation of the inputs: 0 = swish (KDense), 1 = identity, 2 = tanh (Dense layers: the
+                               // output activation of the layer before acts on this layer's inputs)
+    int bias;                  // 1: a virtual input unit I with feature 1 carries the bias (its weights W[I*O + o] = b[o])
     float inv_h;               // Float32 1/h (utils.jl:9)
     int goff;                  // offset of this layer's grid points in GenericModel::grid
     long long offC, offW;      // offsets into the flat parameter vector
@@ -88,7 +91,7 @@ struct kanode_handle {
     struct WideGraph { cudaGraphExec_t exec = nullptr; std::vector<char> sig; int nodes = 0; };
     WideGraph wide_graphs[6];
     int wide_graph = 1;                      // KANODE_WIDE_GRAPH=0: launch every kernel directly
-    int wide_graph_maxn = 8192;              // larger states: direct launches (kernels are long, per-pass timing stays available)
+    int wide_graph_maxn = 1 << 30;           // KANODE_WIDE_GRAPH_MAXN: states above this launch directly (keeps the per-pass CUDA events: profiling)
     std::vector<cudaEvent_t> wide_gp_ev;     // event pairs around the g passes of the last wide loss_grad call
     int wide_gp_used = 0;
     bool wide_counters_zeroed[2] = {false, false};
@@ -115,10 +118,17 @@ inline size_t count_params(const kanode_desc* d) {
     size_t np = 0;
     for (int l = 0; l < d->n_layers; ++l) {
         const kanode_layer_desc& s = d->layers[l];
+        if (l > 0 && d->layers[l - 1].out_dims != s.in_dims) return 0;
+        if (s.kind == KANODE_LAYER_DENSE) {                           // Lux.Dense: weight[out, in] + bias[out]
+            if (s.in_dims < 1 || s.out_dims < 1 || s.dense_act < 0 || s.dense_act > 1) return 0;
+            if (l == d->n_layers - 1 && s.dense_act != KANODE_ACT_IDENTITY) return 0;
+            np += (size_t)(s.in_dims + 1) * s.out_dims;
+            continue;
+        }
+        if (s.kind != KANODE_LAYER_KDENSE) return 0;
         if (s.in_dims < 1 || s.out_dims < 1 || s.grid_len < 2) return 0;
         if (s.normalizer < 0 || s.normalizer > 2 || s.basis < 0 || s.basis > 2) return 0;
         if (!(s.grid_hi > s.grid_lo) || !(s.denominator > 0)) return 0;
-        if (l > 0 && d->layers[l - 1].out_dims != s.in_dims) return 0;
         np += (size_t)s.in_dims * s.grid_len * s.out_dims;            // kdense.jl:101
         if (s.use_base_act) np += (size_t)s.in_dims * s.out_dims;     // kdense.jl:103
     }

@@ -17,6 +17,7 @@ struct SmallKey { int I, H, G, norm; };
 inline bool small_match(const kanode_desc& d, SmallKey& k) {
     if (d.rhs_kind != KANODE_RHS_CHAIN || d.n_layers != 2) return false;
     const kanode_layer_desc &a = d.layers[0], &b = d.layers[1];
+    if (a.kind != KANODE_LAYER_KDENSE || b.kind != KANODE_LAYER_KDENSE) return false;
     if (a.basis != KANODE_BASIS_RBF || b.basis != KANODE_BASIS_RBF || !a.use_base_act || !b.use_base_act) return false;
     if (a.grid_len != b.grid_len || a.normalizer != b.normalizer || a.grid_lo != b.grid_lo || a.grid_hi != b.grid_hi ||
         a.denominator != b.denominator) return false;

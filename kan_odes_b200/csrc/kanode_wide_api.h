@@ -8,6 +8,7 @@ struct WideKey { int H, G; };
 inline bool wide_match(const kanode_desc& d, WideKey& k) {
     if (d.rhs_kind != KANODE_RHS_CHAIN || d.n_layers != 2) return false;
     const kanode_layer_desc &a = d.layers[0], &b = d.layers[1];
+    if (a.kind != KANODE_LAYER_KDENSE || b.kind != KANODE_LAYER_KDENSE) return false;
     if (a.basis != KANODE_BASIS_RBF || b.basis != KANODE_BASIS_RBF || !a.use_base_act || !b.use_base_act) return false;
     if (a.grid_len != b.grid_len || a.grid_len > 16) return false;
     if (a.in_dims != b.out_dims || a.in_dims < 16) return false;     // narrow states belong to the thread-per-trajectory kernels
@@ -20,7 +21,7 @@ inline bool wide_match(const kanode_desc& d, WideKey& k) {
 inline bool wsrc_match(const kanode_desc& d, int& G) {
     if (d.rhs_kind != KANODE_RHS_SOURCE_LAPLACIAN || d.n_layers != 1) return false;
     const kanode_layer_desc& a = d.layers[0];
-    if (a.in_dims != 1 || a.out_dims != 1 || a.basis != KANODE_BASIS_RBF || !a.use_base_act) return false;
+    if (a.kind != KANODE_LAYER_KDENSE || a.in_dims != 1 || a.out_dims != 1 || a.basis != KANODE_BASIS_RBF || !a.use_base_act) return false;
     G = a.grid_len;
     return G == 5 || G == 10;
 }

@@ -129,6 +129,49 @@ class KDense:
         d.use_base_act = int(self.use_base_act)
         d.grid_lo, d.grid_hi = float(self.grid_lims[0]), float(self.grid_lims[1])
         d.denominator = float(self.denominator)
+        d.kind, d.dense_act = abi.LAYER_KDENSE, 0
+
+
+identity = _Named("identity", abi.ACT_IDENTITY)
+
+
+@dataclass
+class Dense:
+    """`Lux.Dense(in => out, act)`: y = act(W x + b) — the layers of the MLP-NODE baseline
+    `Lux.Chain(Lux.Dense(2 => 50, tanh), Lux.Dense(50 => 2))` (Lotka-Volterra/LV_driver_MLP.jl:61).  Parameters
+    `{"weight": [out, in], "bias": [out]}`; flat order [vec(weight); bias] like `getdata(ComponentArray(p_))` (:65-67).
+    `act` is `tanh` or `identity` (the last layer of a chain must be `identity`)."""
+    in_dims: int
+    out_dims: int
+    act: _Named = None
+    use_base_act: bool = True      # Chain.parameterlength / unflatten use the KDense protocol names
+
+    def __post_init__(self):
+        if self.act is None:
+            self.act = identity
+        if self.act in (tanh, tanh_fast):
+            self.act = _Named("tanh", abi.ACT_TANH)
+        elif self.act is not identity and self.act.name != "tanh":
+            raise NotImplementedError("Dense activations on the hot path: tanh, identity")
+        self.grid_len = 0
+
+    def initialparameters(self, rng: np.random.Generator) -> dict:
+        return {"weight": glorot_uniform(rng, self.out_dims, self.in_dims), "bias": np.zeros(self.out_dims, np.float32)}
+
+    def initialstates(self, rng=None) -> dict:
+        return {}
+
+    def parameterlength(self) -> int:
+        return (self.in_dims + 1) * self.out_dims
+
+    def statelength(self) -> int:
+        return 0
+
+    def _fill(self, d: abi.LayerDesc) -> None:
+        d.in_dims, d.out_dims, d.grid_len = self.in_dims, self.out_dims, 0
+        d.normalizer = d.basis = d.use_base_act = 0
+        d.grid_lo, d.grid_hi, d.denominator = -1.0, 1.0, 1.0
+        d.kind, d.dense_act = abi.LAYER_DENSE, self.act.code
 
 
 @dataclass
@@ -227,7 +270,7 @@ def flatten_params(ps: dict) -> np.ndarray:
     """getdata(ComponentArray(pM)): [vec(C1); vec(W1); vec(C2); vec(W2); ...] column-major vec."""
     parts = []
     for name in sorted(ps, key=lambda s: int(s.split("_")[1])):
-        for key in ("C", "W"):
+        for key in ("C", "W", "weight", "bias"):
             if key in ps[name]:
                 parts.append(np.asarray(ps[name][key], dtype=np.float32).reshape(-1, order="F"))
     return np.concatenate(parts)
@@ -239,6 +282,12 @@ def unflatten_params(chain: Chain, p: np.ndarray) -> dict:
     out, off = {}, 0
     for i, l in enumerate(chain.layers):
         d = {}
+        if isinstance(l, Dense):
+            n = l.out_dims * l.in_dims
+            d["weight"] = p[off:off + n].reshape((l.out_dims, l.in_dims), order="F"); off += n
+            d["bias"] = p[off:off + l.out_dims]; off += l.out_dims
+            out[f"layer_{i + 1}"] = d
+            continue
         n = l.out_dims * l.grid_len * l.in_dims
         d["C"] = p[off:off + n].reshape((l.out_dims, l.grid_len * l.in_dims), order="F"); off += n
         if l.use_base_act:

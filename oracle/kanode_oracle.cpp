@@ -118,6 +118,8 @@ inline float fastpower(double x, double y) {
 // ---------------------------------------------------------------------------------
 template <class T> struct Layer {
     int I, O, G, norm, basis, use_base;
+    int kind = 0, dense_act = 0;   // kind 1: Lux.Dense, y = act(W x + b) (LV_driver_MLP.jl:61); params [vec(W[O,I]); b[O]] at offW, offB
+    size_t offB = 0;
     std::vector<T> grid;  // Float32 LinRange values promoted to T (kdense.jl:90)
     T inv_h;              // Float32 (1/h) promoted to T (utils.jl:9)
     size_t offC, offW;
@@ -136,6 +138,11 @@ size_t param_count(const kanode_desc* d) {
     size_t np = 0;
     for (int l = 0; l < d->n_layers; ++l) {
         const auto& s = d->layers[l];
+        if (s.kind == KANODE_LAYER_DENSE) {
+            if (s.in_dims < 1 || s.out_dims < 1) return 0;
+            np += (size_t)(s.in_dims + 1) * s.out_dims;               // weight[out, in] + bias[out]
+            continue;
+        }
         if (s.in_dims < 1 || s.out_dims < 1 || s.grid_len < 2) return 0;
         np += (size_t)s.in_dims * s.grid_len * s.out_dims;            // kdense.jl:101
         if (s.use_base_act) np += (size_t)s.in_dims * s.out_dims;     // kdense.jl:103
@@ -152,6 +159,14 @@ template <class T> bool build_model(const kanode_desc* d, Model<T>& m) {
         Layer<T> L;
         L.I = s.in_dims; L.O = s.out_dims; L.G = s.grid_len;
         L.norm = s.normalizer; L.basis = s.basis; L.use_base = s.use_base_act;
+        if (s.kind == KANODE_LAYER_DENSE) {
+            L.kind = 1; L.dense_act = s.dense_act; L.G = 0; L.use_base = 0; L.inv_h = T(1);
+            L.offC = off; L.offW = off; off += (size_t)L.O * L.I; L.offB = off; off += (size_t)L.O;
+            m.maxw = std::max(m.maxw, std::max(L.I, L.O));
+            if (l > 0 && d->layers[l - 1].out_dims != s.in_dims) return false;
+            m.L.push_back(std::move(L));
+            continue;
+        }
         L.grid.resize(L.G);
         for (int g = 0; g < L.G; ++g) {
             // Julia LinRange{Float32}: lerpi(j,d,a,b) = T((1-t)*a + t*b), t = j/d in Float64
@@ -179,13 +194,13 @@ template <class T> bool build_model(const kanode_desc* d, Model<T>& m) {
 
 // per-layer saved intermediates for the reverse pass
 template <class T> struct Tape {
-    std::vector<std::vector<T>> x, xn, b, db, sw, dsw;  // per layer
+    std::vector<std::vector<T>> x, xn, b, db, sw, dsw, z;  // per layer (z: pre-activations of Dense layers)
     void init(const Model<T>& m) {
         const size_t nl = m.L.size();
-        x.resize(nl); xn.resize(nl); b.resize(nl); db.resize(nl); sw.resize(nl); dsw.resize(nl);
+        x.resize(nl); xn.resize(nl); b.resize(nl); db.resize(nl); sw.resize(nl); dsw.resize(nl); z.resize(nl);
         for (size_t l = 0; l < nl; ++l) {
             const auto& L = m.L[l];
-            x[l].resize(L.I); xn[l].resize(L.I); sw[l].resize(L.I); dsw[l].resize(L.I);
+            x[l].resize(L.I); xn[l].resize(L.I); sw[l].resize(L.I); dsw[l].resize(L.I); z[l].resize(L.O);
             b[l].resize((size_t)L.I * L.G); db[l].resize((size_t)L.I * L.G);
         }
     }
@@ -199,6 +214,17 @@ void chain_forward(const Model<T>& m, const T* p, const T* xin, T* yout, Tape<T>
         const auto& L = m.L[l];
         nxt.assign(L.O, T(0));
         const T* C = p + L.offC; const T* W = p + L.offW;
+        if (L.kind == 1) {                                             // Lux.Dense: y = act(W x + b)  (LV_driver_MLP.jl:61)
+            for (int i = 0; i < L.I; ++i) tp.x[l][i] = cur[i];
+            for (int o = 0; o < L.O; ++o) {
+                T zz = p[L.offB + o];
+                for (int i = 0; i < L.I; ++i) zz += W[(size_t)i * L.O + o] * cur[i];
+                tp.z[l][o] = zz;
+                nxt[o] = L.dense_act == KANODE_ACT_TANH ? std::tanh(zz) : zz;
+            }
+            cur.swap(nxt);
+            continue;
+        }
         for (int i = 0; i < L.I; ++i) {
             const T xi = cur[i];
             tp.x[l][i] = xi;
@@ -233,6 +259,16 @@ void chain_reverse(const Model<T>& m, const T* p, const T* ybar, T* xbar, T* pba
         nxt.assign(L.I, T(0));
         const T* C = p + L.offC; const T* W = p + L.offW;
         T* Cb = pbar ? pbar + L.offC : nullptr; T* Wb = pbar ? pbar + L.offW : nullptr;
+        if (L.kind == 1) {                                             // Dense: zbar = ybar .* act'(z); Wbar += zbar x'; bbar += zbar; xbar = W' zbar
+            for (int o = 0; o < L.O; ++o) {
+                const T th = L.dense_act == KANODE_ACT_TANH ? std::tanh(tp.z[l][o]) : T(0);
+                const T zb = cur[o] * (L.dense_act == KANODE_ACT_TANH ? (T(1) - th * th) : T(1));
+                if (pbar) { pbar[L.offB + o] += zb; for (int i = 0; i < L.I; ++i) Wb[(size_t)i * L.O + o] += zb * tp.x[l][i]; }
+                for (int i = 0; i < L.I; ++i) nxt[i] += W[(size_t)i * L.O + o] * zb;
+            }
+            cur.swap(nxt);
+            continue;
+        }
         for (int i = 0; i < L.I; ++i) {
             T xnbar = 0;
             for (int g = 0; g < L.G; ++g) {

@@ -145,3 +145,40 @@ def test_failed_solves_are_reported_not_averaged_in():
     r = ode.loss_grad(u0, (0.0, 1.0), sa, tg, allow_failed=True)
     assert r["solver_failed"] and (r["fwd_stats"].retcode != 0).any()
     ode.close()
+
+
+def test_mlp_node_baseline_matches_oracle(lv_saveat):
+    """The MLP-NODE baseline `Lux.Chain(Lux.Dense(2 => 50, tanh), Lux.Dense(50 => 2))` (LV_driver_MLP.jl:61-76) as a second RHS kind:
+    RHS, VJP, solve and the adjoint gradient against the oracle (which states the Dense layer in its natural act(Wx + b) form)."""
+    mlp = K.Chain(K.Dense(2, 50, K.tanh), K.Dense(50, 2))
+    assert mlp.parameterlength() == 252                                   # LV_driver_MLP.jl prints "parameter size: 252"
+    rng = np.random.default_rng(4)
+    ps, _ = K.setup(np.random.default_rng(0), mlp)
+    ps["layer_1"]["bias"] = rng.normal(size=50).astype(np.float32) * 0.3; ps["layer_2"]["bias"] = np.array([0.1, -0.2], np.float32)
+    p = K.flatten_params(ps).astype(np.float64)
+    assert np.array_equal(K.unflatten_params(mlp, p)["layer_2"]["bias"], p[-2:])
+    orc = Oracle(mlp.desc(), np.float64)
+    u = rng.uniform(0.5, 2.0, (9, 2)); lam = rng.normal(size=(9, 2))
+    ode = K.KanOde(mlp, dtype=np.float64); ode.set_params(p)
+    assert np.abs(ode.rhs(u) - orc.rhs(p, u)).max() < 1e-13
+    ub, pb = ode.vjp(u, lam); ub0, pb0 = orc.vjp(p, u, lam)
+    assert np.abs(ub - ub0).max() < 1e-12 and np.abs(pb - pb0).max() < 1e-11
+    u0 = rng.uniform(0.5, 2.0, (6, 2)); tg = lv_targets(u0, lv_saveat)
+    ref = orc.loss_grad(p, u0, TSPAN, lv_saveat, tg, want_out=True)
+    r = ode.loss_grad(u0, TSPAN, lv_saveat, tg)
+    assert (r["fwd_stats"].naccept == ref["fwd_stats"][:, 0]).all() and (r["bwd_stats"].naccept == ref["bwd_stats"][:, 0]).all()
+    assert (r["bwd_stats"].nf == ref["bwd_stats"][:, 2]).all()
+    assert abs(r["loss"] - ref["loss"]) < 1e-10 * ref["loss"] and _relmax(r["grad"], ref["grad"]) < 1e-7
+    assert _relmax(ode.solve(u0, TSPAN, lv_saveat).array, ref["out"]) < 1e-9
+    ode.close()
+    ode32 = K.KanOde(mlp, dtype=np.float32); ode32.set_params(p)
+    r32 = ode32.loss_grad(u0, TSPAN, lv_saveat, tg)
+    assert _relmax(r32["grad"], ref["grad"]) < 5e-3 and abs(r32["loss"] - ref["loss"]) < 1e-3 * ref["loss"]
+    ode32.close()
+    # a mixed chain (KDense -> Dense) runs on the same kernels
+    mix = K.Chain(K.KDense(2, 6, 4, normalizer=K.softsign), K.Dense(6, 2))
+    pm = glorot_params(mix, seed=5).astype(np.float64); pm[-2:] = [0.05, -0.03]
+    om = Oracle(mix.desc(), np.float64); odm = K.KanOde(mix, dtype=np.float64); odm.set_params(pm)
+    rm = odm.loss_grad(u0, (0.0, 1.0), [0.5, 1.0], tg[:, :2]); rfm = om.loss_grad(pm, u0, (0.0, 1.0), [0.5, 1.0], tg[:, :2])
+    assert _relmax(rm["grad"], rfm["grad"]) < 1e-7
+    odm.close()
