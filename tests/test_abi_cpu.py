@@ -42,10 +42,19 @@ def test_param_count_matches_parameterlength(lib):
     assert lib.kanode_param_count(C.byref(bad)) == 0
 
 
-def test_desc_struct_layout_matches_header():
-    assert C.sizeof(abi.LayerDesc) == 36
-    assert C.sizeof(abi.Desc) == 4 + 8 * 36 + 4 + 4 + 4 + 8 + 8   # with 4 bytes padding before the doubles
-    assert C.sizeof(abi.Stats) == 16
+def test_desc_struct_layout_matches_header(tmp_path):
+    """ctypes mirrors of the descriptor structs against the C compiler's view of include/kanode.h (sizes and field offsets)."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "kanode.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", '
+                   'sizeof(kanode_layer_desc), sizeof(kanode_desc), sizeof(kanode_stats), offsetof(kanode_layer_desc, kind), '
+                   'offsetof(kanode_desc, rhs_kind), offsetof(kanode_desc, lap_coef), offsetof(kanode_desc, dx));return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", str(abi.REPO_ROOT / "include"), "-o", str(exe), str(src)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [C.sizeof(abi.LayerDesc), C.sizeof(abi.Desc), C.sizeof(abi.Stats), abi.LayerDesc.kind.offset,
+                   abi.Desc.rhs_kind.offset, abi.Desc.lap_coef.offset, abi.Desc.dx.offset]
+    assert C.sizeof(abi.LayerDesc) == 44 and C.sizeof(abi.Stats) == 16
 
 
 def test_create_without_gpu_fails_loudly(lib):
