@@ -596,6 +596,8 @@ int kanode_create(const kanode_desc* desc, int device, void* stream, kanode_hand
     h->desc = *desc; h->device = device; h->np = np; h->n = desc->n_state;
     h->n_out = desc->rhs_kind == KANODE_RHS_MAP ? desc->layers[desc->n_layers - 1].out_dims : desc->n_state;
     h->params.assign(np, 0.0);
+    h->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+    if (const char* e = std::getenv("KANODE_LG_PERSIST")) h->lg_persist = std::atoi(e);
     if (const char* e = std::getenv("KANODE_LG_SHAPE")) h->lg_shape = std::atoi(e);
     if (const char* e = std::getenv("KANODE_BWD_MAXIT")) h->bwd_maxiters = std::atoi(e);     // timing experiments only
     if (const char* e = std::getenv("KANODE_SCHEDULE")) h->schedule = std::atoi(e);

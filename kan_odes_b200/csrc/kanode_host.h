@@ -67,6 +67,8 @@ struct kanode_handle {
     int rec_cap = 32;
     int64_t order_B[2] = {0, 0};     // batch size the cached launch order (per dtype) was built for; 0 = none
     int schedule = 1;                // 1: launch order of the adjoint warps from the last call's iteration counts (KANODE_SCHEDULE)
+    int sm_count = 148;              // multiprocessors of the device (grid of the persistent adjoint kernel)
+    int lg_persist = 1;              // 1: persistent adjoint launch, warps draw tickets (KANODE_LG_PERSIST=0: one block per 4 warp positions)
     int lg_shape = 0;                // launch shape of the lane-group adjoint kernel (KANODE_LG_SHAPE; 0 = default)
     int64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fwd start / bwd start / reduce start / end
@@ -77,7 +79,7 @@ struct kanode_handle {
     void* stage = nullptr; size_t stage_bytes = 0;   // pinned host staging block for the results of the host entry points
     // grow-only device workspace, keyed by purpose
     enum { W_U0, W_OUT, W_TARGET, W_STATS_F, W_STATS_B, W_SAVEAT, W_REC_T, W_REC, W_NSTEPS, W_RET, W_DG, W_FAC, W_G,
-           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_WPK32, W_WPK64, W_LAM, W_GEN, W_GEN2, W_LS, W_ATT, W_ORDER, W_WIDE_F, W_WIDE_B, W_W1T32, W_W1T64, W_W2IMG, W_W2TIMG, W_W1IMG, W_WIDE_R, W_WLG32, W_WLG64, W_GPART, W_SLAB, W_RPF, W_RPB, W_COT, W_FAILCNT, W_REG, W_ACT, W_TR_P, W_TR_M, W_TR_V, W_TR_GRAD, W_TR_OUT, W_TR_RAW, W_MULTI_G, W_MULTI_L, W_MULTI_STAGE, W_COUNT };
+           W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_WPK32, W_WPK64, W_LAM, W_GEN, W_GEN2, W_LS, W_ATT, W_ORDER, W_WIDE_F, W_WIDE_B, W_W1T32, W_W1T64, W_W2IMG, W_W2TIMG, W_W1IMG, W_WIDE_R, W_WLG32, W_WLG64, W_GPART, W_SLAB, W_RPF, W_RPB, W_COT, W_FAILCNT, W_REG, W_ACT, W_TR_P, W_TR_M, W_TR_V, W_TR_GRAD, W_TR_OUT, W_TR_RAW, W_MULTI_G, W_MULTI_L, W_MULTI_STAGE, W_TICKET, W_COUNT };
     DevBuf ws[W_COUNT];
     kanode::GenericModel gm{};               // layer table for the generic kernels
     // wide (batched lockstep) engine: attempts the last forward-only / dense-forward / backward call needed, counter state

@@ -118,24 +118,35 @@ int small_lg_loss_grad(kanode_handle* h, const T* d_u0, int64_t B, double t0, do
         bw.abstol = (T)abstol; bw.reltol = (T)reltol; bw.maxiters = h->bwd_maxiters;
         bw.rec = rec; bw.cap = cap; bw.nsteps = nsteps; bw.retcode = retc; bw.dg = dg; bw.gpart = gpart;
         bw.du0 = d_du0; bw.stats = d_bst; bw.attempts = nullptr; bw.rp_t = d_rp_bwd; bw.rp_cap = rp_cap;
-        // launch order from the previous call's per-warp iteration counts (same batch size, dtype and launch shape)
+        // launch order from the previous call's per-trajectory step margins (same batch size and dtype)
         const int slot = sizeof(T) == 4 ? 0 : 1;
-        const int64_t nslots = (int64_t)nblk * WPB;
         bool ordered = false;
-        if (h->schedule && !d_rp_bwd && nwarps >= 512 && nslots < (1ll << 30)) {
-            int *att = nullptr, *ord = nullptr;
-            ENSURE(h, W_ATT, sizeof(int) * (size_t)nslots * 2, att);
-            ENSURE(h, W_ORDER, sizeof(int) * (size_t)nslots * 2, ord);
-            att += (size_t)slot * nslots; ord += (size_t)slot * nslots;
+        if (h->schedule && !d_rp_bwd && nwarps >= 512 && B < (1ll << 30)) {
+            int *mar = nullptr, *ord = nullptr;
+            constexpr size_t NCNT = (size_t)32 * LG_OBLK * LG_NBK;         // class counts of the order kernels behind the permutations
+            ENSURE(h, W_ATT, sizeof(int) * (size_t)B * 2, mar);
+            ENSURE(h, W_ORDER, sizeof(int) * ((size_t)B * 2 + NCNT), ord);
+            int* cnt = ord + (size_t)B * 2;
+            mar += (size_t)slot * B; ord += (size_t)slot * B;
             if (h->order_B[slot] == B) {
-                lg_order_kernel<<<1, 1024, 0, h->stream>>>(att, (int)nslots, ord);
-                ++h->launches;
+                lg_order_count_kernel<<<LG_OBLK, 1024, 0, h->stream>>>(mar, (int)B, cnt);
+                lg_order_scatter_kernel<<<LG_OBLK, 1024, 0, h->stream>>>(mar, (int)B, cnt, ord);
+                h->launches += 2;
                 bw.order = ord; ordered = true;
             }
-            bw.wattempts = att;
+            bw.tmargin = mar;
             h->order_B[slot] = B;
         }
         (void)ordered;
+        // persistent launch: MINB blocks per SM, warps draw their positions from a ticket counter (kanode_small_lg.cuh)
+        int* ticket = nullptr;
+        const bool fresh_ticket = h->ws[kanode_handle::W_TICKET].bytes == 0;
+        ENSURE(h, W_TICKET, sizeof(int) * 4, ticket);
+        if (fresh_ticket) CK(h, cudaMemsetAsync(ticket, 0, sizeof(int) * 4, h->stream));
+        ticket += 2 * slot;
+        bw.ticket = ticket; bw.nwarps = nwarps;
+        const unsigned resident = (unsigned)(MINB * h->sm_count);
+        const unsigned grid = (h->lg_persist && nblk > resident) ? resident : nblk;
         const size_t smem = SMP::bytes(WPB);
         auto kern = small_backward_lg_kernel<T, P, NORM, UPL, WPB, MINB>;
         const unsigned abit = sizeof(T) == 4 ? 1u : 2u;                  // once per handle = per device and launch shape
@@ -146,9 +157,9 @@ int small_lg_loss_grad(kanode_handle* h, const T* d_u0, int64_t B, double t0, do
         cudaEventRecord(h->ev[0], h->stream);
         small_forward_kernel<T, P, NORM, true, true><<<blocks_for(B, 64), 64, 0, h->stream>>>(prm, a);
         cudaEventRecord(h->ev[1], h->stream);
-        kern<<<nblk, 32 * WPB, smem, h->stream>>>(prm, bw);
+        kern<<<grid, 32 * WPB, smem, h->stream>>>(prm, bw);
         cudaEventRecord(h->ev[2], h->stream);
-        reduce_partials_kernel<T><<<dim3(NSLAB, (P::NP + 255) / 256), 256, 0, h->stream>>>(gpart, (int64_t)nblk * WPB, P::NP, slab);
+        reduce_partials_kernel<T><<<dim3(NSLAB, (P::NP + 255) / 256), 256, 0, h->stream>>>(gpart, nwarps, P::NP, slab);   // rows = warp positions handed out
         reduce_slabs_kernel<T><<<(P::NP + 255) / 256, 256, 0, h->stream>>>(slab, NSLAB, P::NP, d_grad_sum, 1.0);
         cudaEventRecord(h->ev[3], h->stream);
         h->launches += 4;

@@ -63,11 +63,21 @@ template <class T> struct LgBwdArgs {
     int* attempts;           // [B] or null
     const double* rp_t;      // replay: [B][rp_cap] end times of the accepted backward steps (descending), NaN-padded; or null
     int rp_cap;
-    // launch order (optional): warp slot -> logical warp (= block of TPW consecutive trajectories).  Warps predicted to need
-    // many attempts (from the previous call's counts) are started first, so their serial chain of steps does not end up as the
-    // tail of the launch.  gpart is indexed by the LOGICAL warp: the gradient sum does not depend on the order.
-    const int* order;        // [warp slots] or null (identity)
-    int* wattempts;          // [warp slots] loop iterations of each logical warp (feeds the next call's order), or null
+    // launch order (optional): position -> trajectory (position = warp position * TPW + group).  A trajectory needs many extra
+    // attempts when its error-controlled step falls below the spacing of the save times: a clipped remainder follows every
+    // proposed step and the solve takes 50-120 attempts instead of ~40.  Which trajectories do so cannot be known in advance
+    // and changes with the parameters; what IS stable from one training step to the next is how far a trajectory is from
+    // that regime: its step MARGIN = min over attempts of (proposed dt) / (distance to the next save time), > 1 for an
+    // unremarkable solve.  Trajectories are started in ascending order of the previous call's margin: the ones at risk first,
+    // the certainly harmless ones last, so the serial chain of a long solve does not end up as the tail of the launch.
+    // gpart is indexed by the warp POSITION; the order is a stable (deterministic) function of the margins.
+    const int* order;        // [B] permutation of the trajectories, or null (identity)
+    int* tmargin;            // [B] bit pattern of the (positive) fp32 margin of each trajectory (feeds the next call's order), or null
+    // persistent launch: the grid holds only the resident warps (blocks per SM x SMs); every warp draws its next position from
+    // ticket[0] until nwarps are handed out, so a warp that ends early does not wait for the slowest warp of its block and no
+    // wave of blocks is left half empty.  ticket[1] counts retired warps: the last one zeroes both for the next launch.
+    int* ticket;
+    int64_t nwarps;          // warp positions (= ceil(B / TPW))
 };
 
 template <class T, class P, int UPL_> struct LgGeom {
@@ -221,11 +231,17 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
     const int j0 = UPL * lig;                                       // first hidden unit of this lane
     const T* wlane = wsm + lig * SMP::LW;                           // its packed weights [UPL][UW]
 
-    const int64_t wslot = (int64_t)blockIdx.x * WPB + warp;         // launch position of this warp
-    const int64_t wg = a.order ? a.order[wslot] : wslot;            // logical warp: trajectories wg*TPW ..
-    const int64_t b = wg * TPW + grp;
-    const bool active = gvalid && b < a.B;
-    const int64_t bq = active ? b : 0;                              // clamped: idle groups read trajectory 0, never write
+    for (;;) {
+    int tk = 0;
+    if (lane == 0) tk = atomicAdd(a.ticket, 1);
+    const int wslot = __shfl_sync(0xffffffffu, tk, 0);              // position of this pass of the warp
+    if (wslot >= a.nwarps) break;
+    const bool active = gvalid && (int64_t)wslot * TPW + grp < a.B;
+    auto trajectory = [&]() -> int64_t {                            // the trajectory at this position (re-read at the end: not kept live)
+        const int64_t pos = (int64_t)wslot * TPW + grp;
+        return (active && a.order) ? (int64_t)a.order[pos] : pos;
+    };
+    const int64_t bq = active ? trajectory() : 0;                   // clamped: idle groups read trajectory 0, never write
 
     const int nsteps = active ? a.nsteps[bq] : 0;
     int ret = active ? a.retcode[bq] : RET_SUCCESS;
@@ -518,7 +534,8 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
     using LC = LgCtrl<T>;
     typename LC::Q qold = (typename LC::Q)Ctrl::qoldinit, q11 = (typename LC::Q)1;
     double dtpropose = dt;
-    bool accept = false, modified = false;
+    bool accept = false, modified = false, clipped = false;
+    float margin = 1e30f;
     int iter = 0;
     if (!(t > t0)) done = true;
     const double* rp = a.rp_t ? a.rp_t + bq * (int64_t)a.rp_cap : nullptr;
@@ -532,6 +549,11 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
         ++iter;
         const double tstop = (sp >= 0) ? fmax(nxt_t, t0) : t0;
         const double dtmin_t = fmax(eps_of(t), dtmin0);
+        {   // step margin (launch order of the next call; no effect on this solve): counted once a step has been clipped
+            const float want = (float)fmin(fabs(dt), dtmax), room = (float)(t - tstop);
+            if (!done && clipped) margin = fminf(margin, want * krcp(room));
+            clipped |= want >= room;
+        }
         dt = fmin(fmax(fmin(fabs(dt), dtmax), dtmin_t), t - tstop);
         double rp_next = t0;
         if (rp) {                                                   // replay: the step ends where the recorded one ended
@@ -765,7 +787,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
 
     // ---- results: per-warp gradient sum (fixed order over the trajectories of the warp), du0, statistics ----
     const bool ok = active && !skipped && ret == RET_SUCCESS;
-    T* gp = a.gpart + wg * NP;
+    T* gp = a.gpart + (int64_t)wslot * NP;
 #pragma unroll
     for (int o = 0; o < I; ++o)
 #pragma unroll
@@ -792,51 +814,86 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
                 gp[q < G ? P::OC1 + (i * G + q) * P::H + j : P::OW1 + i * P::H + j] = tot;
             }
         }
-    if (lane == 0 && a.wattempts) a.wattempts[wg] = iter;
     if (active && lig == 0) {
+        const int64_t b = trajectory();
         if (skipped) { nf = 0; naccept = 0; nreject = 0; }
         if (a.du0)
 #pragma unroll
             for (int i = 0; i < I; ++i) a.du0[b * I + i] = skipped ? T(0) : lam[i];
         if (a.stats) a.stats[b] = kanode_stats{naccept, nreject, nf, ret};
         if (a.attempts) a.attempts[b] = naccept + nreject;
+        if (a.tmargin) a.tmargin[b] = __float_as_int(margin);
+    }
+    __syncwarp();                                                   // the next pass rewrites this warp's shared-memory slices
+    }
+    if (lane == 0) {                                                // last warp out re-arms the ticket for the next launch
+        const int total = (int)(gridDim.x * WPB);
+        if (atomicAdd(a.ticket + 1, 1) == total - 1) { a.ticket[0] = 0; a.ticket[1] = 0; __threadfence(); }
     }
 }
 
-// Launch order from the previous call's per-warp iteration counts: logical warps with more than 5/4 of the mean count first
-// (any order among them), the others behind them in their natural order.  One block; n is a few thousand.
-__global__ void __launch_bounds__(1024) lg_order_kernel(const int* __restrict__ att, int n, int* __restrict__ order) {
-    __shared__ unsigned long long ssum;
-    __shared__ int snlong, sbase[2], swarp[2][32];
+// Launch order from the previous call's per-trajectory step margins (LgBwdArgs::order): a STABLE counting sort into LG_NBK
+// margin classes (class 0: margin < 1, then 64 classes per octave), smallest margins first, index order inside a class — a
+// deterministic function of the margins.  LG_OBLK blocks of 32 warps; every warp owns a contiguous segment, lanes with equal
+// class find each other with match.any (one instruction per element whatever LG_NBK is).  Two launches: lg_order_count_kernel
+// fills cnt[warp][class], lg_order_scatter_kernel turns it into first positions and writes the permutation.
+constexpr int LG_NBK = 64, LG_OBLK = 8;
+__device__ __forceinline__ int lg_margin_class(int bits) {
+    const float m = __int_as_float(bits);
+    if (!(m >= 1.0f)) return 0;
+    const int c = 1 + (int)(__log2f(m) * 64.0f);
+    return c < LG_NBK - 1 ? c : LG_NBK - 1;
+}
+__device__ __forceinline__ int lg_order_segment(int n) { return ((n + 32 * LG_OBLK - 1) / (32 * LG_OBLK) + 31) / 32 * 32; }   // whole warp iterations
+__global__ void __launch_bounds__(1024) lg_order_count_kernel(const int* __restrict__ key, int n, int* __restrict__ cnt) {
+    __shared__ int c_sm[32][LG_NBK];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) { ssum = 0ull; snlong = 0; }
+    for (int i = tid; i < 32 * LG_NBK; i += blockDim.x) (&c_sm[0][0])[i] = 0;
     __syncthreads();
-    unsigned long long loc = 0;
-    for (int i = tid; i < n; i += blockDim.x) loc += (unsigned long long)att[i];
-    for (int d = 16; d > 0; d >>= 1) loc += __shfl_down_sync(0xffffffffu, loc, d);
-    if (lane == 0) atomicAdd(&ssum, loc);
+    const int seg = lg_order_segment(n);
+    const int64_t lo64 = (int64_t)(blockIdx.x * 32 + w) * seg;
+    const int lo = (int)(lo64 < n ? lo64 : n), hi = (int)(lo64 + seg < n ? lo64 + seg : n);
+    const unsigned below = (1u << lane) - 1u;
+    for (int i0 = lo; i0 < hi; i0 += 32) {
+        const int i = i0 + lane;
+        const int c = i < hi ? lg_margin_class(key[i]) : LG_NBK + lane;      // idle lanes: classes of their own
+        const unsigned m = __match_any_sync(0xffffffffu, c);
+        if (i < hi && (m & below) == 0) c_sm[w][c] += __popc(m);
+        __syncwarp();
+    }
     __syncthreads();
-    const int thr = (int)((ssum * 5ull) / (4ull * (unsigned long long)(n > 0 ? n : 1)));
-    int cnt = 0;
-    for (int i = tid; i < n; i += blockDim.x) cnt += att[i] > thr;
-    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, d);
-    if (lane == 0) atomicAdd(&snlong, cnt);
+    for (int i = tid; i < 32 * LG_NBK; i += blockDim.x) cnt[(size_t)blockIdx.x * 32 * LG_NBK + i] = (&c_sm[0][0])[i];
+}
+__global__ void __launch_bounds__(1024) lg_order_scatter_kernel(const int* __restrict__ key, int n, const int* __restrict__ cnt, int* __restrict__ order) {
+    __shared__ int first[32][LG_NBK];                                // first position of (this block's warp, class)
+    __shared__ int tot[LG_NBK];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid < LG_NBK) {                                              // members of class `tid`: all warps; the warps before this block
+        int all = 0, before = 0;
+        for (int k = 0; k < 32 * LG_OBLK; ++k) { const int v = cnt[(size_t)k * LG_NBK + tid]; if (k < (int)blockIdx.x * 32) before += v; all += v; }
+        tot[tid] = all;
+        int acc = before;
+        for (int k = 0; k < 32; ++k) { first[k][tid] = acc; acc += cnt[((size_t)blockIdx.x * 32 + k) * LG_NBK + tid]; }
+    }
     __syncthreads();
-    if (tid == 0) { sbase[0] = snlong; sbase[1] = 0; }               // [0]: next position of a short warp, [1]: of a long one
+    if (tid == 0) { int acc = 0; for (int k = 0; k < LG_NBK; ++k) { const int v = tot[k]; tot[k] = acc; acc += v; } }
     __syncthreads();
-    for (int c0 = 0; c0 < n; c0 += blockDim.x) {
-        const int i = c0 + tid;
-        const bool in = i < n, lg = in && att[i] > thr;
-        const unsigned ml = __ballot_sync(0xffffffffu, lg), ms = __ballot_sync(0xffffffffu, in && !lg);
-        if (lane == 0) { swarp[1][w] = __popc(ml); swarp[0][w] = __popc(ms); }
-        __syncthreads();
-        int offl = 0, offs = 0;
-        for (int k = 0; k < w; ++k) { offl += swarp[1][k]; offs += swarp[0][k]; }
-        const unsigned below = (1u << lane) - 1u;
-        if (in) order[lg ? sbase[1] + offl + __popc(ml & below) : sbase[0] + offs + __popc(ms & below)] = i;
-        __syncthreads();
-        if (tid == 0) { int tl = 0, ts_ = 0; for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { tl += swarp[1][k]; ts_ += swarp[0][k]; } sbase[1] += tl; sbase[0] += ts_; }
-        __syncthreads();
+    const int seg = lg_order_segment(n);
+    const int64_t lo64 = (int64_t)(blockIdx.x * 32 + w) * seg;
+    const int lo = (int)(lo64 < n ? lo64 : n), hi = (int)(lo64 + seg < n ? lo64 + seg : n);
+    const unsigned below = (1u << lane) - 1u;
+    for (int i0 = lo; i0 < hi; i0 += 32) {
+        const int i = i0 + lane;
+        const int c = i < hi ? lg_margin_class(key[i]) : LG_NBK + lane;
+        const unsigned m = __match_any_sync(0xffffffffu, c);
+        int base = 0;
+        if (i < hi) base = tot[c] + first[w][c];
+        __syncwarp();
+        if (i < hi) {
+            order[base + __popc(m & below)] = i;
+            if ((m & below) == 0) first[w][c] += __popc(m);
+        }
+        __syncwarp();
     }
 }
 
