@@ -261,6 +261,7 @@ def run_pde_workload(name, B, dtype, steps, warmup, world, rank, local, peaks, w
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+            abi.check(lib, ode.h, lib.kanode_peer_status(ode.h), "kanode_peer_status")   # a timed-out exchange is an error, not a number
         sampler.stop_flag = True; sampler.join()
         launches = ode.launch_count() - launches0
         total_ms = torch.tensor([sum(x.elapsed_time(y) for x, y in evs)], dtype=torch.float64, device=dev)
@@ -572,6 +573,14 @@ def run_ours(args):
     ode.set_params(p)
     npar = ode.np_
     dev = torch.device("cuda", local)
+    # the step's collective: the library's own peer-memory kernel (pack + exchange over NVLink + sum in ONE launch, kanode_peer.cu);
+    # KANODE_BENCH_NCCL=1 keeps the pack kernel + NCCL all-reduce for an A/B
+    collective = "none"
+    if world > 1:
+        from kan_odes_b200.dist import peer_setup
+        collective = "nccl all-reduce of one packed buffer"
+        if not os.environ.get("KANODE_BENCH_NCCL") and peer_setup(ode):
+            collective = "peer-memory kernel (CUDA IPC mailboxes over NVLink), no NCCL call in the step"
     with torch.cuda.stream(stream):
         d_u0 = torch.tensor(u0, dtype=tdt, device=dev)
         d_tg = torch.tensor(tg, dtype=tdt, device=dev)
@@ -630,6 +639,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+            abi.check(lib, ode.h, lib.kanode_peer_status(ode.h), "kanode_peer_status")   # a timed-out exchange is an error, not a number
         sampler.stop_flag = True; sampler.join()
         launches = ode.launch_count() - launches0
         if world > 1:
@@ -722,7 +732,7 @@ def run_ours(args):
                    "global_batch": world * B, "tspan": list(TSPAN), "nsave": int(SAVEAT.size), "abstol": 1e-6,
                    "reltol": 1e-3, "params": "glorot_uniform seed 0" + ("" if args.fixed_params else ", perturbed 0.2% (relative, seed 99) before every timed step"),
                    "l2": "256 MiB flush between timed steps",
-                   "parallelism": f"dp{world} (trajectories sharded, gradient all-reduce only)"},
+                   "parallelism": f"dp{world} (trajectories sharded, gradient all-reduce only)", "collective": collective},
         "train_steps_per_s": args.steps / (total_ms / 1e3),
         "rhs_evals_per_s": world * (nf_f + nf_b) * args.steps / (total_ms / 1e3),
         "rhs_evals_per_step_per_gpu": {"forward": nf_f, "backward_fused_fwd_vjp": nf_b},

@@ -318,6 +318,29 @@ int kanode_pack_sums_dev(kanode_handle* h, const float* d_grad_sum, const double
 int kanode_pack_sums_dev_f64(kanode_handle* h, const double* d_grad_sum, const double* d_loss_sum, int64_t count, double* d_packed);
 int kanode_train_apply_packed_dev(kanode_handle* h, const double* d_packed);
 
+/* ---- the step's collective fused into the packing kernel, over NVLink peer memory (one process per GPU, one node) -------
+ * The reference has no multi-device path; the data-parallel step of SURVEY.md 8(e) is "gradient sum -> all-reduce".  For the
+ * small models ([gradient | loss | count] <= KANODE_PEER_MAX_ENTRIES doubles) that collective is latency, not bytes, so the
+ * library does it itself instead of calling NCCL: every process owns a MAILBOX in its GPU's memory, exported to its peers as a
+ * CUDA IPC handle.  kanode_pack_allreduce_dev launches ONE kernel that packs the sums, stores them straight into every peer's
+ * mailbox over NVLink, publishes an epoch flag (release, system scope), waits for the peers' flags and adds the world's
+ * contributions in rank order — every rank gets bit-identical sums, nothing goes through the host.
+ *   kanode_peer_export   allocates the mailbox and writes its 64-byte cudaIpcMemHandle_t to `ipc_handle`
+ *   kanode_peer_attach   opens the mailboxes of all ranks (`ipc_handles` = world x 64 bytes, in rank order; exchange them with
+ *                        any host-side all-gather); world <= KANODE_PEER_MAX_WORLD; world == 1 needs no peers
+ *   kanode_pack_allreduce_dev(_f64)   d_packed[np + 2] = sum over ranks of [gradient sum | loss sum | count]; every rank must
+ *                        make the same sequence of calls.  A peer that does not arrive within ~10 s poisons the result with
+ *                        NaN and the next kanode_peer_status returns KANODE_ERR_SOLVER instead of hanging the GPU.
+ *   kanode_peer_status   blocks until the handle's stream is idle; 0, or the error of a timed-out exchange */
+#define KANODE_PEER_MAX_WORLD 16
+#define KANODE_PEER_MAX_ENTRIES 4096
+#define KANODE_IPC_HANDLE_BYTES 64
+int kanode_peer_export(kanode_handle* h, void* ipc_handle /* [64] host */);
+int kanode_peer_attach(kanode_handle* h, int32_t rank, int32_t world, const void* ipc_handles /* [world][64] host */);
+int kanode_pack_allreduce_dev(kanode_handle* h, const float* d_grad_sum, const double* d_loss_sum, int64_t count, double* d_packed);
+int kanode_pack_allreduce_dev_f64(kanode_handle* h, const double* d_grad_sum, const double* d_loss_sum, int64_t count, double* d_packed);
+int kanode_peer_status(kanode_handle* h);
+
 /* Flux.Adam(eta, (beta1, beta2), eps) + update!(opt, p, grad)  (LV_driver_KANODE.jl:219,287; [EXT Flux 0.14.22]):
  *   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g^2;  p -= eta * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps),  g = grad_scale*d_grad.
  * All pointers are device pointers of np floats; t is the 1-based iteration count.  grad_scale lets a data-parallel

@@ -68,6 +68,7 @@ EXPORTED_SYMBOLS = (
     "kanode_solve_adjoint", "kanode_solve_adjoint_f64", "kanode_solve_adjoint_dev",
     "kanode_edge_activations", "kanode_edge_activations_f64", "kanode_set_regularizer", "kanode_reg_loss",
     "kanode_pack_sums_dev", "kanode_pack_sums_dev_f64", "kanode_train_apply_packed_dev", "kanode_create_multi", "kanode_device_count", "kanode_train_begin", "kanode_train_step_dev", "kanode_train_apply_dev", "kanode_train_params",
+    "kanode_peer_export", "kanode_peer_attach", "kanode_pack_allreduce_dev", "kanode_pack_allreduce_dev_f64", "kanode_peer_status",
 )
 
 _lib = None
@@ -119,6 +120,13 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.kanode_last_timing.restype = C.c_int
     lib.kanode_last_gpass_timing.argtypes = [vp, vp, vp]
     lib.kanode_last_gpass_timing.restype = C.c_int
+    lib.kanode_peer_export.argtypes = [vp, vp]
+    lib.kanode_peer_attach.argtypes = [vp, C.c_int32, C.c_int32, vp]
+    lib.kanode_pack_allreduce_dev.argtypes = [vp, vp, vp, i64, vp]
+    lib.kanode_pack_allreduce_dev_f64.argtypes = [vp, vp, vp, i64, vp]
+    lib.kanode_peer_status.argtypes = [vp]
+    for name in ("kanode_peer_export", "kanode_peer_attach", "kanode_pack_allreduce_dev", "kanode_pack_allreduce_dev_f64", "kanode_peer_status"):
+        getattr(lib, name).restype = C.c_int
     lib.kanode_launch_count.restype = C.c_int64
     lib.kanode_launch_count.argtypes = [vp]
     for name in ("kanode_create", "kanode_destroy", "kanode_sync", "kanode_set_params", "kanode_set_params_dev",

@@ -17,6 +17,7 @@ UNITS = {
     "kanode_api.cu": ["kanode_small.cuh", "kanode_small_host.h", "kanode_generic.cuh"],
     "kanode_lg.cu": ["kanode_small.cuh", "kanode_small_host.h", "kanode_small_lg.cuh"],
     "kanode_wide.cu": ["kanode_wide.cuh", "kanode_wsrc.cuh"],
+    "kanode_peer.cu": [],
 }
 SOURCES = list(UNITS)
 NVCC_FLAGS = ["-std=c++20", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",

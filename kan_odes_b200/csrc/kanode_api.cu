@@ -667,6 +667,7 @@ int kanode_destroy(kanode_handle* h) {
     }
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    kanode::peer_release(h);
     for (auto& b : h->ws) if (b.p) cudaFree(b.p);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->aux_ev) if (e) cudaEventDestroy(e);

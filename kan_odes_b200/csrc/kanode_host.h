@@ -77,6 +77,13 @@ struct kanode_handle {
     bool ev_valid = false;
     std::string err;
     void* stage = nullptr; size_t stage_bytes = 0;   // pinned host staging block for the results of the host entry points
+    // peer-memory all-reduce (kanode_peer.cu): this rank's mailbox (own cudaMalloc: exported over CUDA IPC), the peers' mailboxes
+    // as mapped here, the call counter (epoch) and a device error word
+    void* peer_box = nullptr;
+    void* peer_map[KANODE_PEER_MAX_WORLD] = {};
+    int peer_rank = -1, peer_world = 0;
+    unsigned long long peer_epoch = 0;
+    int* peer_err = nullptr;
     // grow-only device workspace, keyed by purpose
     enum { W_U0, W_OUT, W_TARGET, W_STATS_F, W_STATS_B, W_SAVEAT, W_REC_T, W_REC, W_NSTEPS, W_RET, W_DG, W_FAC, W_G,
            W_LOSS, W_GRAD, W_DU0, W_PARAMS, W_PARAMS64, W_WPK32, W_WPK64, W_LAM, W_GEN, W_GEN2, W_LS, W_ATT, W_ORDER, W_WIDE_F, W_WIDE_B, W_W1T32, W_W1T64, W_W2IMG, W_W2TIMG, W_W1IMG, W_WIDE_R, W_WLG32, W_WLG64, W_GPART, W_SLAB, W_RPF, W_RPB, W_COT, W_FAILCNT, W_REG, W_ACT, W_TR_P, W_TR_M, W_TR_V, W_TR_GRAD, W_TR_OUT, W_TR_RAW, W_MULTI_G, W_MULTI_L, W_MULTI_STAGE, W_TICKET, W_COUNT };
@@ -99,6 +106,8 @@ struct kanode_handle {
     bool wide_counters_zeroed[2] = {false, false};
     const void* wide_counters_ptr[2] = {nullptr, nullptr};
 };
+
+namespace kanode { void peer_release(kanode_handle* h); }   // kanode_peer.cu: closes the mapped mailboxes, frees the own one
 
 inline int fail(kanode_handle* h, int code, const char* fmt, ...) {
     char buf[512];

@@ -173,6 +173,8 @@ int small_lg_loss_grad(kanode_handle* h, const T* d_u0, int64_t B, double t0, do
         if constexpr (sizeof(T) == 4) {
             switch (h->lg_shape) {
                 case 1: return launch.template operator()<P, NORM, 2, 4, 3>();      // 12 warps/SM at 168 registers (spills): slower on B200
+                case 2: return launch.template operator()<P, NORM, 2, 3, 2>();      // 6 warps/SM (occupancy experiment)
+                case 3: return launch.template operator()<P, NORM, 2, 2, 2>();      // 4 warps/SM (occupancy experiment)
                 default: return launch.template operator()<P, NORM, 2, KANODE_LG_WPB, KANODE_LG_MINB>();   // 8 warps/SM, no spills
             }
         } else {

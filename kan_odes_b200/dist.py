@@ -24,6 +24,52 @@ def shard_bounds(batch: int, rank: int, world: int) -> Tuple[int, int]:
 
 _PACK_CACHE: dict = {}
 PACK_MAX = 1 << 16      # gradients up to this many entries travel with the loss sum and the count in ONE fp64 all-reduce
+PEER_MAX_ENTRIES = 4096  # KANODE_PEER_MAX_ENTRIES: [gradient | loss | count] up to this size go through the library's own peer-memory all-reduce
+IPC_HANDLE_BYTES = 64
+
+
+def peer_setup(ode, group=None) -> bool:
+    """Connect the handles of all ranks for the library's own all-reduce over NVLink peer memory (kanode_peer.cu): every rank
+    exports the CUDA IPC handle of its mailbox, the 64-byte handles are all-gathered through torch.distributed (host objects:
+    works on any backend), and every rank maps its peers' mailboxes.  Returns False (and leaves the NCCL path in place) when the
+    model is too large for the mailbox or the GPUs cannot map each other; the decision is made collectively, so either all
+    ranks use the peer path or none does."""
+    import ctypes as C
+    from . import abi
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    if ode.np_ + 2 > PEER_MAX_ENTRIES or world > 16:
+        return False
+    mine = (C.c_ubyte * IPC_HANDLE_BYTES)()
+    abi.check(ode.lib, ode.h, ode.lib.kanode_peer_export(ode.h, mine), "kanode_peer_export")
+    handles = [bytes(mine)]
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(mine), group=group)
+    blob = (C.c_ubyte * (IPC_HANDLE_BYTES * world)).from_buffer_copy(b"".join(handles))
+    ok = ode.lib.kanode_peer_attach(ode.h, rank, world, blob) == 0
+    if world > 1:                                             # all or none
+        flags = [None] * world
+        dist.all_gather_object(flags, ok, group=group)
+        ok = all(flags)
+    ode._peer_ok = ok
+    return ok
+
+
+def peer_all_reduce(ode, loss_sum: torch.Tensor, grad_sum: torch.Tensor, local_count: int) -> torch.Tensor:
+    """ONE kernel per step and rank: packs [gradient sum | loss sum | count], stores it into every rank's mailbox over NVLink,
+    waits for the world and sums in rank order (kanode_pack_allreduce_dev).  Same result layout as packed_all_reduce."""
+    npar = grad_sum.numel()
+    key = ("peer", loss_sum.device, npar)
+    buf = _PACK_CACHE.get(key)
+    if buf is None:
+        buf = _PACK_CACHE[key] = torch.zeros(npar + 2, dtype=torch.float64, device=loss_sum.device)
+    f = ode.lib.kanode_pack_allreduce_dev_f64 if grad_sum.dtype == torch.float64 else ode.lib.kanode_pack_allreduce_dev
+    rc = f(ode.h, grad_sum.data_ptr(), loss_sum.data_ptr(), int(local_count), buf.data_ptr())
+    if rc != 0:
+        from . import abi
+        abi.check(ode.lib, ode.h, rc, "kanode_pack_allreduce_dev")
+    return buf
 
 
 def packed_all_reduce(ode, loss_sum: torch.Tensor, grad_sum: torch.Tensor, local_count: int, group=None) -> torch.Tensor:
@@ -32,6 +78,8 @@ def packed_all_reduce(ode, loss_sum: torch.Tensor, grad_sum: torch.Tensor, local
     all-reduce.  Returns the reduced buffer [np + 2]; nothing is normalised or read back here (kanode_train_apply_packed_dev
     consumes it on the device; `unpack` normalises for a host-side consumer)."""
     import ctypes as C
+    if getattr(ode, "_peer_ok", False):                       # peer_setup succeeded on every rank: no NCCL call in the step
+        return peer_all_reduce(ode, loss_sum, grad_sum, local_count)
     npar = grad_sum.numel()
     key = ("packed", loss_sum.device, npar)
     buf = _PACK_CACHE.get(key)

@@ -90,6 +90,11 @@ class KanOde:
             rc = self.lib.kanode_create(C.byref(self.desc), int(device if not devices else devices[0]), C.c_void_p(stream), C.byref(h))
         abi.check(self.lib, None, rc, "kanode_create")
         self.h = h
+        self.device = int(device if not devices else devices[0])
+
+    def sync(self):
+        """Block until the handle's stream(s) are idle (kanode_sync)."""
+        abi.check(self.lib, self.h, self.lib.kanode_sync(self.h), "kanode_sync")
 
     def close(self):
         if getattr(self, "h", None):
