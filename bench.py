@@ -604,6 +604,7 @@ def run_ours(args):
             packed_all_reduce(ode, d_loss, d_grad, B)
             # (KANODE_BENCH_NO_ALLREDUCE=1 is a diagnostic: it isolates the collective's share of the step at N > 1; not a bench mode)
 
+    align = world > 1 and not os.environ.get("KANODE_BENCH_NO_ALIGN") and not os.environ.get("KANODE_BENCH_NO_ALLREDUCE")
     ms3 = (C.c_float * 3)()
     prng = np.random.default_rng(99)                               # same on every rank: replicated parameters
     with torch.cuda.stream(stream):                                # resident like a device-side optimizer's output: the refresh is kernels only
@@ -630,6 +631,10 @@ def run_ours(args):
                 # launch order predicted from the last step is not exact (untimed; device-side refresh, the host is not blocked)
                 abi.check(lib, ode.h, lib.kanode_set_params_dev(ode.h, p_steps[i].data_ptr(), npar), "kanode_set_params_dev")
             flush.zero_()                                          # L2 flush between timed iterations (untimed)
+            if align:
+                # untimed device-side rendezvous: the refresh + flush above are not part of a step, but a rank that finishes
+                # them late would make every other rank wait INSIDE its timed region (the step's collective is a rendezvous)
+                packed_all_reduce(ode, d_loss, d_grad, B)
             evs[i][0].record(stream)
             step(False)
             evs[i][1].record(stream)
@@ -651,7 +656,8 @@ def run_ours(args):
                 k_ms[i] = [ms3[0], ms3[1], ms3[2]]
             torch.cuda.synchronize()
             dist.barrier()
-        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        step_ms = [a.elapsed_time(b) for a, b in evs]
+        total_ms = sum(step_ms)
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -731,13 +737,15 @@ def run_ours(args):
         "config": {"workload": "lotka_volterra_kan_ode_2_10_2_g5_ensemble", "batch_per_gpu": B,
                    "global_batch": world * B, "tspan": list(TSPAN), "nsave": int(SAVEAT.size), "abstol": 1e-6,
                    "reltol": 1e-3, "params": "glorot_uniform seed 0" + ("" if args.fixed_params else ", perturbed 0.2% (relative, seed 99) before every timed step"),
-                   "l2": "256 MiB flush between timed steps",
+                   "l2": "256 MiB flush between timed steps" + (", then an untimed device-side rendezvous of the ranks" if align else ""),
                    "parallelism": f"dp{world} (trajectories sharded, gradient all-reduce only)", "collective": collective},
         "train_steps_per_s": args.steps / (total_ms / 1e3),
         "rhs_evals_per_s": world * (nf_f + nf_b) * args.steps / (total_ms / 1e3),
         "rhs_evals_per_step_per_gpu": {"forward": nf_f, "backward_fused_fwd_vjp": nf_b},
         "failed_trajectories": failed,
-        "kernel_ms": {"forward": fwd_ms, "backward": bwd_ms, "grad_reduce": red_ms},
+        "kernel_ms": {"forward": fwd_ms, "backward": bwd_ms, "grad_reduce": red_ms,
+                      "backward_min": float(k_ms[:, 1].min()), "backward_max": float(k_ms[:, 1].max())},
+        "step_ms_spread": {"min": float(min(step_ms)), "max": float(max(step_ms)), "note": "this rank's timed steps (CUDA events)"},
         "roofline": {"kernel": "small_backward_lg_kernel", "bound": "ffma", "achieved": achieved_tf,
                      "peak": ffma_peak, "unit": "TFLOP/s", "frac": achieved_tf / ffma_peak,
                      "peak_source": peaks["ffma_source"], "derived_peak": FFMA_PEAK_TFLOPS,
