@@ -158,13 +158,14 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
         d_target = nullptr;
     } else if (!d_target) return fail(h, KANODE_ERR_INVALID, "null target");
     auto engine = [&]() -> int {
-        {   // small-model registry: lane-group adjoint engine (kanode_lg.cu)
+        {   // small-model registry: lane-group adjoint engine (kanode_lg.cu); it runs the forward solve BEFORE it joins a late target
             bool handled = false;
             const int rcl = small_lg_loss_grad<T>(h, d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum, d_grad_sum,
                                                   d_du0, d_fst, d_bst, d_out_opt, d_rp_fwd, d_rp_bwd, rp_cap, &handled);
             if (handled) return rcl;
             if (d_rp_fwd || d_rp_bwd) return fail(h, KANODE_ERR_UNSUPPORTED, "dt-replay is implemented by the small-model ensemble kernels only");
         }
+        if (int rcj = join_late_target(h)) return rcj;                   // the other engines read the target in their forward kernels
         WideKey wk;
         if (h->wide && wide_match(h->desc, wk) && wide_batch_ok(h, B))
             return wide_loss_grad(h, wk, generic_params<T>(h), d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum,
@@ -176,7 +177,9 @@ int loss_grad_dev(kanode_handle* h, const T* d_u0, int64_t B, double t0, double 
         return generic_loss_grad<T>(h, d_u0, B, t0, t1, d_saveat, nsave, d_target, abstol, reltol, d_loss_sum, d_grad_sum,
                                     d_du0, d_fst, d_bst, d_out_opt);
     };
-    if (int rc = engine()) return rc;
+    const int rc_engine = engine();
+    if (int rcj = join_late_target(h)) return rcj;                       // whatever path was taken: the main stream is behind the copy
+    if (rc_engine) return rc_engine;
     // sparsity regulariser (reg_loss, LV_driver_KANODE.jl:187-201): the sums are un-normalised (caller divides the loss by
     // B*nsave*n and the gradient by B), so reg enters with those factors
     if (!d_cot && (h->reg_act != 0.0 || h->reg_entropy != 0.0))
@@ -299,6 +302,11 @@ int loss_grad_host(kanode_handle* h, const T* u0, int64_t B, double t0, double t
         if (cot) {
             ENSURE(h, W_COT, sizeof(T) * (nout ? nout : 1), d_cot);
             CK(h, cudaMemcpyAsync(d_cot, cot, sizeof(T) * nout, cudaMemcpyHostToDevice, h->stream));
+        } else if (h->overlap_h2d && h->aux_stream && (h->overlap_h2d > 1 || sizeof(T) * nout >= (1u << 20))) {   // 2: any size (tests)
+            // the target is the bulk of the step's input bytes and the forward solve needs only u0: register the copy, the
+            // engine starts it on the second stream behind its own small uploads and joins when it first reads the target
+            h->late_src = target; h->late_dst = d_tg; h->late_bytes = sizeof(T) * nout;
+            h->target_late = true; h->late_started = false;
         } else CK(h, cudaMemcpyAsync(d_tg, target, sizeof(T) * nout, cudaMemcpyHostToDevice, h->stream));
         double *d_rpf = nullptr, *d_rpb = nullptr; T* d_out = nullptr;
         if (rp_fwd) {
@@ -598,6 +606,7 @@ int kanode_create(const kanode_desc* desc, int device, void* stream, kanode_hand
     h->params.assign(np, 0.0);
     h->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     if (const char* e = std::getenv("KANODE_LG_PERSIST")) h->lg_persist = std::atoi(e);
+    if (const char* e = std::getenv("KANODE_OVERLAP_H2D")) h->overlap_h2d = std::atoi(e);
     if (const char* e = std::getenv("KANODE_LG_SHAPE")) h->lg_shape = std::atoi(e);
     if (const char* e = std::getenv("KANODE_BWD_MAXIT")) h->bwd_maxiters = std::atoi(e);     // timing experiments only
     if (const char* e = std::getenv("KANODE_SCHEDULE")) h->schedule = std::atoi(e);

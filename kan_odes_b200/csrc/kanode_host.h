@@ -72,8 +72,14 @@ struct kanode_handle {
     int lg_shape = 0;                // launch shape of the lane-group adjoint kernel (KANODE_LG_SHAPE; 0 = default)
     int64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fwd start / bwd start / reduce start / end
-    cudaStream_t aux_stream = nullptr;                           // concurrent launch of the predicted-long trajectories
+    // host entry points: the target (the bulk of a step's host->device bytes) is copied on aux_stream while the forward solve
+    // already runs on the u0 that arrived first; aux_ev[0] = fork (aux waits for the main stream), aux_ev[1] = target landed.
+    // target_late: the engine must wait for aux_ev[1] before it reads the target (kanode_api.cu: join_late_target)
+    cudaStream_t aux_stream = nullptr;
     cudaEvent_t aux_ev[2] = {nullptr, nullptr};
+    bool target_late = false, late_started = false;
+    const void* late_src = nullptr; void* late_dst = nullptr; size_t late_bytes = 0;   // the deferred target copy
+    int overlap_h2d = 1;             // KANODE_OVERLAP_H2D=0: every copy on the main stream
     bool ev_valid = false;
     std::string err;
     void* stage = nullptr; size_t stage_bytes = 0;   // pinned host staging block for the results of the host entry points
@@ -123,6 +129,28 @@ inline int fail(kanode_handle* h, int code, const char* fmt, ...) {
             return fail(h, e_ == cudaErrorMemoryAllocation ? KANODE_ERR_NOMEM : KANODE_ERR_CUDA, "%s: %s",  \
                         #call, cudaGetErrorString(e_));                                                     \
     } while (0)
+
+// Deferred target copy of the host entry points.  The copy engine serves host->device copies in submission order, so the big
+// copy must be SUBMITTED after the small ones the engine still has to make (save times, weight images) or the forward solve
+// would wait behind it: the host entry point only registers the copy, the engine starts it on aux_stream right before its
+// forward launch (start_late_target) and joins when it first reads the target (join_late_target; an engine that reads the
+// target in its forward kernels joins first, which degenerates to a plain copy on the main stream).
+inline int start_late_target(kanode_handle* h) {
+    if (!h->target_late || h->late_started) return 0;
+    CK(h, cudaEventRecord(h->aux_ev[0], h->stream));                   // behind everything already queued on the main stream
+    CK(h, cudaStreamWaitEvent(h->aux_stream, h->aux_ev[0], 0));
+    CK(h, cudaMemcpyAsync(h->late_dst, h->late_src, h->late_bytes, cudaMemcpyHostToDevice, h->aux_stream));
+    CK(h, cudaEventRecord(h->aux_ev[1], h->aux_stream));
+    h->late_started = true;
+    return 0;
+}
+inline int join_late_target(kanode_handle* h) {
+    if (!h->target_late) return 0;
+    h->target_late = false;
+    if (h->late_started) { h->late_started = false; CK(h, cudaStreamWaitEvent(h->stream, h->aux_ev[1], 0)); }
+    else CK(h, cudaMemcpyAsync(h->late_dst, h->late_src, h->late_bytes, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
 
 inline size_t count_params(const kanode_desc* d) {
     if (!d || d->n_layers < 1 || d->n_layers > KANODE_MAX_LAYERS) return 0;

@@ -80,6 +80,24 @@ int small_pack_dev(kanode_handle* h, const float* d_p, bool* handled) {
     return rc;
 }
 
+// dL/du(t_s) and the loss from stored predictions: dg = 2 (pred - X) / (I nsave), loss += (pred - X)^2 — what the forward
+// kernel does in place when the target is already on the device.  Used when a host entry point's target copy is still in
+// flight while the forward solve runs (kanode_api.cu: target_late): NaN predictions (unsaved points of a failed solve) give
+// zero cotangent and no loss, as in the forward kernel.  Layouts: pred / target / dg [B][nsave][I] (one flat index).
+template <class T>
+__global__ void __launch_bounds__(256) loss_dg_kernel(const T* __restrict__ pred, const T* __restrict__ target, int64_t count, T scale,
+                                                     T* __restrict__ dg, double* __restrict__ loss_sum) {
+    double lsum = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const T v = pred[i];
+        T d = T(0);
+        if (v == v) { const T e = v - target[i]; lsum += (double)e * (double)e; d = scale * e; }
+        dg[i] = d;
+    }
+    for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+    if ((threadIdx.x & 31) == 0 && lsum != 0.0) atomicAdd(loss_sum, lsum);
+}
+
 #ifndef KANODE_LG_NSLAB
 #define KANODE_LG_NSLAB 32
 #endif
@@ -154,8 +172,23 @@ int small_lg_loss_grad(kanode_handle* h, const T* d_u0, int64_t B, double t0, do
             CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             h->attr_done |= abit;
         }
+        // a host entry point's target copy may still be in flight (kanode_api.cu): solve forward on u0 alone, keep the
+        // predictions, and form dL/du(t_s) and the loss once the copy has landed
+        const bool late = h->target_late && d_target && !d_rp_fwd;
+        if (late) {
+            if (!a.out) { T* pred = nullptr; ENSURE(h, W_OUT, sizeof(T) * (size_t)nsave * I * B, pred); a.out = pred; }
+            a.target = nullptr;
+        }
+        if (late) { if (int rcs = start_late_target(h)) return rcs; }    // every small upload of this call is already submitted
         cudaEventRecord(h->ev[0], h->stream);
         small_forward_kernel<T, P, NORM, true, true><<<blocks_for(B, 64), 64, 0, h->stream>>>(prm, a);
+        if (late) {
+            if (int rcj = join_late_target(h)) return rcj;
+            const int64_t cnt = (int64_t)B * nsave * I;
+            const unsigned nb = (unsigned)std::min<int64_t>((cnt + 255) / 256, (int64_t)8 * h->sm_count);
+            loss_dg_kernel<T><<<nb, 256, 0, h->stream>>>(a.out, d_target, cnt, T(2) / (T)((double)I * nsave), dg, d_loss_sum);
+            ++h->launches;
+        }
         cudaEventRecord(h->ev[1], h->stream);
         kern<<<grid, 32 * WPB, smem, h->stream>>>(prm, bw);
         cudaEventRecord(h->ev[2], h->stream);
@@ -169,12 +202,12 @@ int small_lg_loss_grad(kanode_handle* h, const T* d_u0, int64_t B, double t0, do
     };
     auto run = [&]<class P, int NORM>() -> int {
         // launch shapes (warps per block, blocks per SM the kernel is compiled for): the default comes from B200 measurements
-        // (profiles/); KANODE_LG_SHAPE selects another one for A/B runs
+        // (profiles/, DESIGN.md 5: 4 / 6 / 8 warps per SM at 255 registers = 2.68 / 2.22 / 1.93 ms; 9 warps at 224 registers
+        // 2.33 ms, 10 at 200 registers 2.74 ms — fewer registers cost more than the extra warps hide);
+        // KANODE_LG_SHAPE selects another one for A/B runs
         if constexpr (sizeof(T) == 4) {
             switch (h->lg_shape) {
                 case 1: return launch.template operator()<P, NORM, 2, 4, 3>();      // 12 warps/SM at 168 registers (spills): slower on B200
-                case 2: return launch.template operator()<P, NORM, 2, 3, 2>();      // 6 warps/SM (occupancy experiment)
-                case 3: return launch.template operator()<P, NORM, 2, 2, 2>();      // 4 warps/SM (occupancy experiment)
                 default: return launch.template operator()<P, NORM, 2, KANODE_LG_WPB, KANODE_LG_MINB>();   // 8 warps/SM, no spills
             }
         } else {

@@ -201,8 +201,8 @@ __device__ __forceinline__ void lg_merge(const T (&x)[N], int stride, int off, T
     ct[NB - 1] = mh * (Tab<T>::bt(NB - 1) * v5 + Tab<T>::bt(NB) * v6);
 }
 
-template <class T, class P, int NORM, int UPL, int WPB, int MINB>
-__global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const __grid_constant__ P prm, const LgBwdArgs<T> a) {
+template <class T, class P, int NORM, int UPL, int WPB>
+__device__ __forceinline__ void small_backward_lg_body(const P& prm, const LgBwdArgs<T>& a) {
     using GM = LgGeom<T, P, UPL>;
     using SMP = LgSmem<T, P, UPL>;
     using RL = RecLayout<T, P::I>;
@@ -832,6 +832,10 @@ __global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const
     }
 }
 
+template <class T, class P, int NORM, int UPL, int WPB, int MINB>
+__global__ void __launch_bounds__(32 * WPB, MINB) small_backward_lg_kernel(const __grid_constant__ P prm, const LgBwdArgs<T> a) {
+    small_backward_lg_body<T, P, NORM, UPL, WPB>(prm, a);
+}
 // Launch order from the previous call's per-trajectory step margins (LgBwdArgs::order): a STABLE counting sort into LG_NBK
 // margin classes (class 0: margin < 1, then 64 classes per octave), smallest margins first, index order inside a class — a
 // deterministic function of the margins.  LG_OBLK blocks of 32 warps; every warp owns a contiguous segment, lanes with equal

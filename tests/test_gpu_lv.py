@@ -254,6 +254,28 @@ def test_scheduled_backward_with_long_trajectory_warps_matches_plain(lv_saveat):
     assert _relmax(b["grad"], a["grad"].astype(np.float64)) < 1e-4
 
 
+def test_target_copy_overlapping_the_forward_solve_gives_the_same_step(lv_saveat, monkeypatch):
+    """Host entry point: the target travels on a second stream while the forward solve runs on u0; dL/du(t_s) and the loss
+    are then formed from the stored predictions (loss_dg_kernel) instead of inside the forward kernel.  Same arithmetic on the
+    same values: identical gradient and statistics, loss equal up to the order of the atomic partial sums."""
+    chain = lv_chain()
+    p = glorot_params(chain, seed=0)
+    rng = np.random.default_rng(41)
+    u0 = rng.uniform(0.5, 2.0, (1500, 2)); tg = rng.uniform(0.0, 3.0, (1500, 35, 2))
+    res = {}
+    for mode in ("0", "2"):                                   # 0: every copy on the main stream, 2: overlap at any size
+        monkeypatch.setenv("KANODE_OVERLAP_H2D", mode)
+        for dt in (np.float32, np.float64):
+            ode = K.KanOde(chain, dtype=dt); ode.set_params(p)
+            res[mode, dt] = ode.loss_grad(u0, TSPAN, lv_saveat, tg)
+            ode.close()
+    for dt in (np.float32, np.float64):
+        a, b = res["0", dt], res["2", dt]
+        assert np.array_equal(a["grad"], b["grad"]) and np.array_equal(a["du0"], b["du0"])
+        assert np.array_equal(a["bwd_stats"].nf, b["bwd_stats"].nf) and np.array_equal(a["fwd_stats"].nf, b["fwd_stats"].nf)
+        assert abs(a["loss"] - b["loss"]) <= 1e-6 * abs(a["loss"])
+
+
 def test_lean_loss_grad_call_matches_full(lv_saveat):
     """`want_du0=False, want_stats=False` (the Zygote.gradient(loss, p) shape of the call) returns the same loss / gradient."""
     chain = lv_chain()
