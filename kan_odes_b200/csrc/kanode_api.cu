@@ -680,6 +680,7 @@ int kanode_destroy(kanode_handle* h) {
     for (auto& b : h->ws) if (b.p) cudaFree(b.p);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->aux_ev) if (e) cudaEventDestroy(e);
+    if (h->order_ev) cudaEventDestroy(h->order_ev);
     for (auto& e : h->wide_gp_ev) cudaEventDestroy(e);
     if (h->stage) cudaFreeHost(h->stage);
     for (auto& g : h->wide_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);

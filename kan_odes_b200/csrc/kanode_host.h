@@ -77,6 +77,7 @@ struct kanode_handle {
     // target_late: the engine must wait for aux_ev[1] before it reads the target (kanode_api.cu: join_late_target)
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t aux_ev[2] = {nullptr, nullptr};
+    cudaEvent_t order_ev = nullptr;  // launch-order kernels of the lane-group adjoint (on aux_stream, under the forward solve) done
     bool target_late = false, late_started = false;
     const void* late_src = nullptr; void* late_dst = nullptr; size_t late_bytes = 0;   // the deferred target copy
     int overlap_h2d = 1;             // KANODE_OVERLAP_H2D=0: every copy on the main stream

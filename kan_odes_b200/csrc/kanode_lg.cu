@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) loss_dg_kernel(const T* __restrict__ pred
 }
 
 #ifndef KANODE_LG_NSLAB
-#define KANODE_LG_NSLAB 32
+#define KANODE_LG_NSLAB 296        // two slabs per SM
 #endif
 
 template <class T>
@@ -138,7 +138,7 @@ int small_lg_loss_grad(kanode_handle* h, const T* d_u0, int64_t B, double t0, do
         bw.du0 = d_du0; bw.stats = d_bst; bw.attempts = nullptr; bw.rp_t = d_rp_bwd; bw.rp_cap = rp_cap;
         // launch order from the previous call's per-trajectory step margins (same batch size and dtype)
         const int slot = sizeof(T) == 4 ? 0 : 1;
-        bool ordered = false;
+        bool ordered = false, order_forked = false;
         if (h->schedule && !d_rp_bwd && nwarps >= 512 && B < (1ll << 30)) {
             int *mar = nullptr, *ord = nullptr;
             constexpr size_t NCNT = (size_t)32 * LG_OBLK * LG_NBK;         // class counts of the order kernels behind the permutations
@@ -147,15 +147,26 @@ int small_lg_loss_grad(kanode_handle* h, const T* d_u0, int64_t B, double t0, do
             int* cnt = ord + (size_t)B * 2;
             mar += (size_t)slot * B; ord += (size_t)slot * B;
             if (h->order_B[slot] == B) {
-                lg_order_count_kernel<<<LG_OBLK, 1024, 0, h->stream>>>(mar, (int)B, cnt);
-                lg_order_scatter_kernel<<<LG_OBLK, 1024, 0, h->stream>>>(mar, (int)B, cnt, ord);
+                // the order depends only on the previous call's margins: its two kernels run on the second stream, under the
+                // forward solve (fork behind everything queued on the main stream; the adjoint launch joins below)
+                // (host entry point with the target copy pending: the second stream belongs to that copy, which is the longer
+                // pole — the order kernels and the forward solve both fit under it on the main stream)
+                cudaStream_t so = h->stream;
+                if (h->aux_stream && !h->target_late) {
+                    if (!h->order_ev) CK(h, cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
+                    CK(h, cudaEventRecord(h->aux_ev[0], h->stream));
+                    CK(h, cudaStreamWaitEvent(h->aux_stream, h->aux_ev[0], 0));
+                    so = h->aux_stream;
+                }
+                lg_order_count_kernel<<<LG_OBLK, 1024, 0, so>>>(mar, (int)B, cnt);
+                lg_order_scatter_kernel<<<LG_OBLK, 1024, 0, so>>>(mar, (int)B, cnt, ord);
+                if (so != h->stream) { CK(h, cudaEventRecord(h->order_ev, so)); order_forked = true; }
                 h->launches += 2;
                 bw.order = ord; ordered = true;
             }
             bw.tmargin = mar;
             h->order_B[slot] = B;
         }
-        (void)ordered;
         // persistent launch: MINB blocks per SM, warps draw their positions from a ticket counter (kanode_small_lg.cuh)
         int* ticket = nullptr;
         const bool fresh_ticket = h->ws[kanode_handle::W_TICKET].bytes == 0;
@@ -180,6 +191,7 @@ int small_lg_loss_grad(kanode_handle* h, const T* d_u0, int64_t B, double t0, do
             a.target = nullptr;
         }
         if (late) { if (int rcs = start_late_target(h)) return rcs; }    // every small upload of this call is already submitted
+        else if (int rcj = join_late_target(h)) return rcj;              // (replay: the forward kernel reads the target itself)
         cudaEventRecord(h->ev[0], h->stream);
         small_forward_kernel<T, P, NORM, true, true><<<blocks_for(B, 64), 64, 0, h->stream>>>(prm, a);
         if (late) {
@@ -189,11 +201,12 @@ int small_lg_loss_grad(kanode_handle* h, const T* d_u0, int64_t B, double t0, do
             loss_dg_kernel<T><<<nb, 256, 0, h->stream>>>(a.out, d_target, cnt, T(2) / (T)((double)I * nsave), dg, d_loss_sum);
             ++h->launches;
         }
+        if (order_forked) CK(h, cudaStreamWaitEvent(h->stream, h->order_ev, 0));
         cudaEventRecord(h->ev[1], h->stream);
         kern<<<grid, 32 * WPB, smem, h->stream>>>(prm, bw);
         cudaEventRecord(h->ev[2], h->stream);
         reduce_partials_kernel<T><<<dim3(NSLAB, (P::NP + 255) / 256), 256, 0, h->stream>>>(gpart, nwarps, P::NP, slab);   // rows = warp positions handed out
-        reduce_slabs_kernel<T><<<(P::NP + 255) / 256, 256, 0, h->stream>>>(slab, NSLAB, P::NP, d_grad_sum, 1.0);
+        reduce_slabs_kernel<T><<<(P::NP + 7) / 8, 256, 0, h->stream>>>(slab, NSLAB, P::NP, d_grad_sum, 1.0);   // a warp per column
         cudaEventRecord(h->ev[3], h->stream);
         h->launches += 4;
         h->ev_valid = true;

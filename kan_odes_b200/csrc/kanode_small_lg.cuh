@@ -902,7 +902,8 @@ __global__ void __launch_bounds__(1024) lg_order_scatter_kernel(const int* __res
 }
 
 // out[c] = scale * sum_r part[r][c]: rows are per-warp gradient sums.  Two deterministic stages: slab sums in fp64
-// (grid.x slabs, thread per column, coalesced rows), then the sum over slabs.
+// (grid.x slabs of consecutive rows — two per SM so the 10 MB of partials stream at HBM speed —, thread per column,
+// coalesced rows), then the sum over slabs: a warp per column, lanes stride over the slabs, fixed shuffle tree.
 template <class T>
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const T* __restrict__ part, int64_t rows, int cols, double* __restrict__ slab) {
     const int c = blockIdx.y * blockDim.x + threadIdx.x;
@@ -915,11 +916,13 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const T* __restric
 }
 template <class OutT>
 __global__ void __launch_bounds__(256) reduce_slabs_kernel(const double* __restrict__ slab, int nslab, int cols, OutT* __restrict__ out, double scale) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= cols) return;                                           // whole warps leave together
     double acc = 0.0;
-    for (int s = 0; s < nslab; ++s) acc += slab[(int64_t)s * cols + c];
-    out[c] = (OutT)(acc * scale);
+    for (int s = lane; s < nslab; s += 32) acc += slab[(int64_t)s * cols + c];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) out[c] = (OutT)(acc * scale);
 }
 
 }  // namespace kanode
