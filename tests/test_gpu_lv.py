@@ -216,9 +216,10 @@ def test_training_loop_reduces_loss_and_adam_kernel_matches_host():
 
 
 def test_scheduled_backward_with_long_trajectory_warps_matches_plain(lv_saveat):
-    """Second call with the same batch: the warp iteration counts of the first call decide the launch order of the adjoint
-    warps (long ones first, kanode_lg.cu).  The per-warp gradient partials are indexed by the logical warp, so the result does
-    not depend on the order: identical step counts and gradients, and the long solves still match the oracle."""
+    """Second call with the same batch: the step margins recorded by the first call decide the launch order of the adjoint
+    solves (trajectories sorted by margin: risky ones first, kanode_lg.cu).  The per-trajectory arithmetic does not depend on
+    the order and the per-warp gradient partials are summed in a fixed order: identical step counts, gradients equal to
+    summation round-off, and the long solves still match the oracle."""
     chain = lv_chain()
     p = glorot_params(chain, seed=0)
     B = 8192
