@@ -775,7 +775,7 @@ def run_ours(args):
         line[other] = leg; line[f"value_{other}"] = leg["value"]; line[f"ms_per_step_{other}"] = leg["ms_per_step"]
         nh = lv_device_leg(chain, p, u0, tg, f64, local, 3, 3, schedule=False)
         line["no_history"] = {"ms_per_step": nh["ms_per_step"], "value": nh["value"],
-                              "note": "launch order of the adjoint warps NOT taken from the previous call's step counts (KANODE_SCHEDULE=0)"}
+                              "note": "adjoint solves launched in natural order, NOT sorted by the previous call's step margins (KANODE_SCHEDULE=0)"}
         line["cfg1"] = cfg1_gpu_latency(local)
         if not args.no_cpu:
             line["parity"] = lv_parity(chain, p, u0, tg, ndt, local)

@@ -329,7 +329,7 @@ int kanode_train_apply_packed_dev(kanode_handle* h, const double* d_packed);
  *   kanode_peer_attach   opens the mailboxes of all ranks (`ipc_handles` = world x 64 bytes, in rank order; exchange them with
  *                        any host-side all-gather); world <= KANODE_PEER_MAX_WORLD; world == 1 needs no peers
  *   kanode_pack_allreduce_dev(_f64)   d_packed[np + 2] = sum over ranks of [gradient sum | loss sum | count]; every rank must
- *                        make the same sequence of calls.  A peer that does not arrive within ~10 s poisons the result with
+ *                        make the same sequence of calls.  A peer that does not arrive within ~20 s poisons the result with
  *                        NaN and the next kanode_peer_status returns KANODE_ERR_SOLVER instead of hanging the GPU.
  *   kanode_peer_status   blocks until the handle's stream is idle; 0, or the error of a timed-out exchange */
 #define KANODE_PEER_MAX_WORLD 16

@@ -14,7 +14,7 @@
 //     spins on the packets of its own mailbox until both epochs match — no flag array, no memory fence anywhere (a system-scope
 //     fence per step, or worse an acquire load in the spin loop, costs 0.2 - 1.2 ms at 8 ranks: measured) — and adds the
 //     world's entries in rank order: every rank computes bit-identical sums.
-// No host involvement, no second kernel, no NCCL.  A peer that never arrives poisons the result with NaN after ~10 s and
+// No host involvement, no second kernel, no NCCL.  A peer that never arrives poisons the result with NaN after ~20 s and
 // sets an error word instead of hanging the GPU.
 //
 // Reference: none (the reference is single-process); the step being served is Zygote.gradient(loss, p) -> Flux.update!
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) peer_pack_allreduce_kernel(const T* __res
             uint4 pk = ld_packet(p);
             unsigned spins = 0;
             while (pk.y != ep || pk.w != ep) {
-                if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 10000000000ull) { ok = false; break; }
+                if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 20000000000ull) { ok = false; break; }
                 __nanosleep(100);
                 pk = ld_packet(p);
             }
@@ -174,7 +174,7 @@ int kanode_peer_status(kanode_handle* h) {
     CK(h, cudaStreamSynchronize(h->stream));
     int e = 0;
     CK(h, cudaMemcpy(&e, h->peer_err, sizeof e, cudaMemcpyDeviceToHost));
-    if (e) return fail(h, KANODE_ERR_SOLVER, "peer all-reduce: a rank did not arrive within 10 s; the packed sums of that step are NaN");
+    if (e) return fail(h, KANODE_ERR_SOLVER, "peer all-reduce: a rank did not arrive within 20 s; the packed sums of that step are NaN");
     return 0;
 }
 
