@@ -45,6 +45,15 @@
 #ifndef KANODE_LG_RCP1
 #define KANODE_LG_RCP1 1
 #endif
+#ifndef KANODE_LG_PAIRC
+#define KANODE_LG_PAIRC 1        // step-end pass: FFMA2 over pairs of components (1) instead of (g_new, error) pairs (0): the
+                                 // finish pairs components, so (0) re-pairs ~100 registers per attempt with MOVs; 1.934 -> 1.914 ms
+#endif
+#ifndef KANODE_LG_STAGE_UNROLL
+#define KANODE_LG_STAGE_UNROLL 1 // unroll factor of the pipelined stage loop (5 = fully unrolled)
+#endif
+#define KANODE_LG_PRAGMA(x) _Pragma(#x)
+#define KANODE_LG_UNROLL(n) KANODE_LG_PRAGMA(unroll n)
 #ifndef KANODE_LG_WPB
 #define KANODE_LG_WPB 4          // warps per block
 #endif
@@ -608,7 +617,7 @@ __device__ __forceinline__ void small_backward_lg_body(const P& prm, const LgBwd
         for (int u = 0; u < UPL; ++u)
 #pragma unroll
             for (int i = 0; i < I; ++i) { Jc[u][i] = J0[u][i]; Dc[u][i] = D0[u][i]; }
-#pragma unroll 1
+        KANODE_LG_UNROLL(KANODE_LG_STAGE_UNROLL)
         for (int s = 0; s < NB - 1; ++s) {
             T Jn[UPL][I], Dn[UPL][I];
             stage_a(s + 1, Jn, Dn);
@@ -704,8 +713,16 @@ __device__ __forceinline__ void small_backward_lg_body(const P& prm, const LgBwd
                 for (int k = 0; k < NB; ++k)
 #pragma unroll
                     for (int o = 0; o < I; ++o)
+#if KANODE_LG_PAIRC
+#pragma unroll
+                        for (int e = 0; e < V; e += 2) {                // pairs of COMPONENTS (the pairing of the finish below): no re-pairing moves
+                            kfma2b(vb[o][e], vb[o][e + 1], c[k][e], c[k][e + 1], ab[o][k]);
+                            kfma2b(vt[o][e], vt[o][e + 1], c[k][e], c[k][e + 1], at[o][k]);
+                        }
+#else
 #pragma unroll
                         for (int e = 0; e < V; ++e) kfma2b(vb[o][e], vt[o][e], ab[o][k], at[o][k], c[k][e]);
+#endif
 #pragma unroll
                 for (int o = 0; o < I; ++o) {
                     T gn[V];
@@ -735,8 +752,16 @@ __device__ __forceinline__ void small_backward_lg_body(const P& prm, const LgBwd
                 for (int k = 0; k < NB; ++k)
 #pragma unroll
                     for (int u = 0; u < UPL; ++u)
+#if KANODE_LG_PAIRC
+#pragma unroll
+                        for (int e = 0; e < V; e += 2) {
+                            kfma2b(vb[u][e], vb[u][e + 1], c[k][e], c[k][e + 1], ab[u][k]);
+                            kfma2b(vt[u][e], vt[u][e + 1], c[k][e], c[k][e + 1], at[u][k]);
+                        }
+#else
 #pragma unroll
                         for (int e = 0; e < V; ++e) kfma2b(vb[u][e], vt[u][e], ab[u][k], at[u][k], c[k][e]);
+#endif
 #pragma unroll
                 for (int u = 0; u < UPL; ++u) {
                     T gn[V];
