@@ -32,26 +32,30 @@ def peer_setup(ode, group=None) -> bool:
     """Connect the handles of all ranks for the library's own all-reduce over NVLink peer memory (kanode_peer.cu): every rank
     exports the CUDA IPC handle of its mailbox, the 64-byte handles are all-gathered through torch.distributed (host objects:
     works on any backend), and every rank maps its peers' mailboxes.  Returns False (and leaves the NCCL path in place) when the
-    model is too large for the mailbox or the GPUs cannot map each other; the decision is made collectively, so either all
-    ranks use the peer path or none does."""
+    model is too large for the mailbox or a GPU cannot export / map a mailbox.  Every rank takes part in every gather whatever
+    happened locally, and the decision is collective: either all ranks use the peer path or none does."""
     import ctypes as C
-    from . import abi
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
-    if ode.np_ + 2 > PEER_MAX_ENTRIES or world > 16:
-        return False
+
+    def everyone(flag: bool) -> bool:
+        if world == 1:
+            return flag
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(flag), group=group)
+        return all(flags)
+
     mine = (C.c_ubyte * IPC_HANDLE_BYTES)()
-    abi.check(ode.lib, ode.h, ode.lib.kanode_peer_export(ode.h, mine), "kanode_peer_export")
+    ok = ode.np_ + 2 <= PEER_MAX_ENTRIES and world <= 16 and ode.lib.kanode_peer_export(ode.h, mine) == 0
     handles = [bytes(mine)]
     if world > 1:
         handles = [None] * world
         dist.all_gather_object(handles, bytes(mine), group=group)
+    if not everyone(ok):                                       # some rank could not export: nobody attaches
+        ode._peer_ok = False
+        return False
     blob = (C.c_ubyte * (IPC_HANDLE_BYTES * world)).from_buffer_copy(b"".join(handles))
-    ok = ode.lib.kanode_peer_attach(ode.h, rank, world, blob) == 0
-    if world > 1:                                             # all or none
-        flags = [None] * world
-        dist.all_gather_object(flags, ok, group=group)
-        ok = all(flags)
+    ok = everyone(ode.lib.kanode_peer_attach(ode.h, rank, world, blob) == 0)
     ode._peer_ok = ok
     return ok
 

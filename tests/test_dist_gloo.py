@@ -52,6 +52,56 @@ def _worker(rank, world, port, batch, q):
     dist.destroy_process_group()
 
 
+class _StubLib:
+    """Stands in for libkanode_b200.so in the collective decision of peer_setup (no GPU here): rank `bad` fails at `stage`."""
+    def __init__(self, rank, bad, stage):
+        self.rank, self.bad, self.stage, self.attached = rank, bad, stage, False
+
+    def kanode_peer_export(self, h, buf):
+        buf[0] = 1 + self.rank
+        return -5 if (self.rank == self.bad and self.stage == "export") else 0
+
+    def kanode_peer_attach(self, h, rank, world, blob):
+        assert bytes(blob)[0] == 1 and bytes(blob)[64] == 2      # handles arrive in rank order
+        if self.rank == self.bad and self.stage == "attach":
+            return -5
+        self.attached = True
+        return 0
+
+
+class _StubOde:
+    def __init__(self, rank, bad, stage, np_=240):
+        self.lib, self.h, self.np_ = _StubLib(rank, bad, stage), None, np_
+
+
+def _peer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from kan_odes_b200.dist import peer_setup
+    res = []
+    for bad, stage, np_ in ((-1, "", 240), (1, "export", 240), (0, "attach", 240), (-1, "", 5000)):
+        ode = _StubOde(rank, bad, stage, np_)
+        res.append((peer_setup(ode), ode._peer_ok))
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_setup_is_all_or_none_and_never_leaves_a_rank_waiting():
+    """peer_setup's collective decision (kan_odes_b200/dist.py): a rank whose GPU cannot export or map a mailbox, or a model too
+    large for it, sends EVERY rank to the NCCL path — and every rank still takes part in every gather (no hang)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 23
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = dict(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    want = [(True, True), (False, False), (False, False), (False, False)]
+    assert got[0] == want and got[1] == want
+
+
 @pytest.mark.parametrize("batch", [8, 7])      # even and ragged shards
 def test_two_rank_gloo_matches_single_process(batch):
     from conftest import glorot_params, lv_chain, lv_targets
