@@ -711,7 +711,7 @@ def run_ours(args):
             if world > 1:
                 dist.barrier()
             workloads[name] = run_pde_workload(name, bpg, "f32", max(3, min(args.steps, 5)), 3, world, rank, local, read_peaks(),
-                                               with_cpu=not args.no_cpu)
+                                               with_cpu=world == 1 and not args.no_cpu)   # CPU baselines: rank 0 at N = 1 only
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
